@@ -1,0 +1,170 @@
+/*
+ * sla.h -- C ABI of the B200-native auction hot path (libsla_b200.so).
+ *
+ * This is the drop-in boundary for DXist/sparse_linear_assignment v0.1.5: the Rust crate keeps its public
+ * API and its host-side CSR storage, and the bodies of
+ *     KhoslaSolver::solve                       (reference src/ksparse.rs:153-251)
+ *     ForwardAuctionSolver::solve_with_params   (reference src/symmetric.rs:217-332, bid_and_assign 334-468,
+ *                                                push_all_left 471-508)
+ * call the entry points below over FFI (binding shown in INTEGRATION.md, rust/ffi.rs).  The reference has no
+ * FFI of its own, so every entry point cites the reference interface it stands in for.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status (SLA_OK == 0); no
+ * exceptions cross the boundary; `sla_last_error` returns a message for the last failure.  Index type on the
+ * boundary is uint32_t (the reference's u16 instantiation is widened by the host wrapper; the unassigned
+ * sentinel SLA_NONE == u32::MAX truncates to u16::MAX).  A context is not thread-safe (one CUDA stream per
+ * context, like `&mut self` in the reference); distinct contexts may be used from distinct threads.
+ * There is no CPU fallback: every call fails with SLA_ERR_NO_DEVICE when no sm_100 GPU is usable.
+ */
+#ifndef SLA_B200_H
+#define SLA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLA_OK 0
+#define SLA_ERR_INVALID 1   /* a reference `ensure!` would fail: bad sizes, empty input, index out of range */
+#define SLA_ERR_CUDA 2      /* CUDA runtime / driver error (message has the CUDA error string) */
+#define SLA_ERR_NO_DEVICE 3 /* no usable GPU */
+#define SLA_ERR_STATE 4     /* call order (solve before upload, ...) or safety round limit hit */
+#define SLA_ERR_ALLOC 5     /* device or pinned-host allocation failed */
+
+#define SLA_NONE 0xFFFFFFFFu /* I::MAX "unassigned" sentinel, reference src/solution.rs:27-34 */
+
+#define SLA_ALGO_KHOSLA 0
+#define SLA_ALGO_FORWARD 1
+
+typedef struct sla_ctx sla_ctx;
+
+/* Result scalars of one solve.  Mirrors the reference's observable post-conditions:
+ *   num_unassigned, eps            -> AuctionSolution fields (src/solution.rs:35-39)
+ *   nits                           -> KhoslaSolver::nits (ksparse.rs:84; bids made, dropped ones included) or
+ *                                     ForwardAuctionSolver::nits (symmetric.rs:88; Jacobi rounds)
+ *   nreductions, optimal_soln_found-> symmetric.rs:89-90
+ *   values_negated                 -> 1 when AuctionSolver::init_solve would have negated `values` in place
+ *                                     (solver.rs:209-216); the host wrapper must then negate its own copy.
+ * The remaining fields are instrumentation the reference does not have. */
+typedef struct sla_stats {
+    uint32_t num_unassigned;
+    uint32_t nits;
+    uint32_t nreductions;
+    uint32_t optimal_soln_found;
+    double eps;
+    uint64_t rounds;      /* synchronous Jacobi rounds, all phases */
+    uint64_t bids;        /* sum over rounds of bidders */
+    uint64_t bid_arcs;    /* sum over rounds of (column, value) pairs examined: the unit of BASELINE.json's metric */
+    uint32_t dropped;     /* Khosla: persons dropped by the price threshold (ksparse.rs:218-220) */
+    uint32_t values_negated;
+    uint64_t wide_rounds; /* rounds run by the grid-wide kernels */
+    uint64_t tail_rounds; /* rounds run by the single-CTA persistent engine */
+    uint32_t kernel_launches; /* kernels launched for this solve (graph nodes included) */
+    uint32_t graph_launches;
+    float ms_solve;       /* device time of the solve, CUDA events on the context's stream, D2H excluded */
+    float ms_total;       /* ms_solve + result copies */
+} sla_stats;
+
+/* One record per bid-scan launch when option "profile" is 1 (host-driven loop, CUDA events around each kernel). */
+typedef struct sla_round_profile {
+    uint32_t round;
+    uint32_t engine;   /* 0 = wide kernels, 1 = single-CTA tail engine (covers `rounds_covered` rounds) */
+    uint32_t bidders;
+    uint32_t rounds_covered;
+    uint64_t arcs;
+    float bid_ms;
+    float assign_ms;
+} sla_round_profile;
+
+/* ---- context: replaces the state owned by the solver structs (ksparse.rs:73-85, symmetric.rs:75-98);
+ *      created from `new(row_capacity, column_capacity, arcs_capacity)` (solver.rs:9-13), freed in Drop ---- */
+int sla_ctx_create(int device, size_t row_capacity, size_t col_capacity, size_t arc_capacity, sla_ctx **out);
+void sla_ctx_destroy(sla_ctx *ctx);
+const char *sla_last_error(const sla_ctx *ctx); /* ctx may be NULL: error of the last failed sla_ctx_create */
+void *sla_ctx_stream(sla_ctx *ctx);             /* the context's cudaStream_t, for event timing by the caller */
+int sla_ctx_device(const sla_ctx *ctx);
+const char *sla_version(void);
+
+/* Options: "tail_max" (bidders at or below which the tail engine runs, <= 2048), "graph" (1: CUDA-graph
+ * super-rounds, 0: host-driven loop), "zero_price_skip" (1: skip the price gather while all prices are
+ * exactly 0, i.e. the first round after init_solve), "profile" (1: record sla_round_profile entries),
+ * "super_rounds" (rounds captured per graph). */
+int sla_set_option(sla_ctx *ctx, const char *key, int64_t value);
+
+/* ---- CSR mirror: the host keeps ownership of i_starts_stops / column_indices / values built by
+ *      init / add_value / extend_from_values (solver.rs:41-101, 191-205); this copies them to HBM and
+ *      computes the value statistics the solves need (min, max, max |a_ij|; ksparse.rs:171-179,
+ *      symmetric.rs:246).  row_ptr has num_rows + 1 entries (row extents are (row_ptr[i], row_ptr[i+1]),
+ *      equivalent to the reference's (i_starts_stops[i], j_counts[i]), solver.rs:88-97).
+ *      Performs validate_input (solver.rs:232-243) plus the column bound the reference only debug_asserts. */
+int sla_upload_csr(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *row_ptr,
+                   const uint32_t *column_indices, const double *values, uint64_t nnz);
+
+/* Same, source arrays already in device memory (device-side generators, multi-GPU shards). */
+int sla_upload_csr_device(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *d_row_ptr,
+                          const uint32_t *d_column_indices, const double *d_values, uint64_t nnz);
+
+/* Synthetic k-regular instance generated directly in HBM (shapes of the reference's
+ * benches/benchmark.rs:49-79 and 16-47): every row has k distinct sorted columns, integer costs uniform in
+ * [value_lo, value_hi); planted != 0 adds one arc of a fixed permutation per row so that a perfect matching
+ * exists.  sla_generate_host writes the bit-identical instance into host arrays (row_ptr: num_rows+1,
+ * cols/vals: num_rows*k). */
+int sla_generate_device(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed,
+                        uint32_t value_lo, uint32_t value_hi, int planted);
+int sla_generate_host(uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed, uint32_t value_lo,
+                      uint32_t value_hi, int planted, uint32_t *row_ptr, uint32_t *column_indices, double *values);
+
+/* ---- solves.  eps / start_eps: NaN means None; max_iterations: 0 means None (100000, symmetric.rs:190).
+ *      Output pointers are host memory (any may be NULL: the result then stays resident and can be fetched
+ *      with sla_download_solution): person_to_object[num_rows], object_to_person[num_cols], prices[num_cols]. */
+int sla_khosla_solve(sla_ctx *ctx, int maximize, double eps, uint32_t *person_to_object,
+                     uint32_t *object_to_person, double *prices, sla_stats *stats);
+int sla_forward_solve(sla_ctx *ctx, int maximize, double eps, double start_eps, uint32_t max_iterations,
+                      uint32_t *person_to_object, uint32_t *object_to_person, double *prices, sla_stats *stats);
+int sla_download_solution(sla_ctx *ctx, uint32_t *person_to_object, uint32_t *object_to_person, double *prices);
+
+/* ---- post-processing on the resident solution (the steps right after the path) ----
+ * get_objective (solver.rs:110-142): exact for integer-valued weights; for other weights the device sum is
+ * order-independent but not the reference's left-to-right order (the host wrappers keep a sequential sum).
+ * ecs_satisfied (solver.rs:154-189).  validate_matching: person_to_object / object_to_person mutually
+ * consistent, and the recount of unassigned persons. */
+int sla_get_objective(sla_ctx *ctx, double *objective);
+int sla_ecs_satisfied(sla_ctx *ctx, double eps, double toleration, int *satisfied);
+int sla_validate_matching(sla_ctx *ctx, uint32_t *num_unassigned, int *consistent);
+
+int sla_get_round_profile(sla_ctx *ctx, sla_round_profile *out, size_t capacity, size_t *count);
+
+/* ---- batch of independent instances (BASELINE.json config 4; the reference only clones solvers in a loop,
+ *      benches/benchmark.rs:109,137).  Instance b owns rows [row_off[b], row_off[b+1]) and columns
+ *      [col_off[b], col_off[b+1]) of the concatenated arrays; column indices are local to the instance;
+ *      row_ptr holds global arc offsets (total_rows + 1 entries).  One CTA runs one whole solve. ---- */
+int sla_batch_upload(sla_ctx *ctx, uint32_t num_instances, const uint32_t *row_off, const uint32_t *col_off,
+                     const uint32_t *row_ptr, const uint32_t *column_indices, const double *values);
+int sla_batch_generate_device(sla_ctx *ctx, uint32_t num_instances, uint32_t first_instance_id, uint32_t num_rows,
+                              uint32_t num_cols, uint32_t k, uint64_t seed, uint32_t value_lo, uint32_t value_hi,
+                              int planted);
+int sla_batch_solve(sla_ctx *ctx, int algo, int maximize, double eps, double start_eps, uint32_t max_iterations,
+                    uint32_t *person_to_object, uint32_t *object_to_person, double *prices,
+                    sla_stats *per_instance_stats /* num_instances entries or NULL */, sla_stats *total);
+
+/* ---- row-partitioned single instance (BASELINE.json config 5): this context holds persons
+ *      [row_begin, row_begin + num_rows) of a global instance with `global_rows` persons; object state
+ *      (prices, owners, packed best-bid words) is replicated on every rank.  One round is
+ *          sla_part_bid   -> all-reduce(MAX) of the `best` words (and the price candidates) by the caller
+ *          sla_part_assign-> applies the winners; returns this rank's next queue length.
+ *      The caller (sparse_linear_assignment_b200.distributed) owns the collectives. ---- */
+int sla_part_begin(sla_ctx *ctx, int algo, int maximize, uint32_t row_begin, uint32_t global_rows, double eps,
+                   double global_w_min, double global_w_max);
+int sla_part_local_value_range(sla_ctx *ctx, double *w_min, double *w_max, double *first_value);
+int sla_part_bid(sla_ctx *ctx);
+int sla_part_buffers(sla_ctx *ctx, void **d_best_words, void **d_price_candidates, uint64_t *num_words);
+int sla_part_assign(sla_ctx *ctx, uint32_t *local_queue_len, uint32_t *local_dropped);
+int sla_part_finish(sla_ctx *ctx, uint32_t *person_to_object /* local rows */, uint32_t *object_to_person,
+                    double *prices, sla_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLA_B200_H */

@@ -1,0 +1,771 @@
+// sla_api.cu -- host side of libsla_b200.so: context, CSR mirror, solve drivers (CUDA-graph super-rounds or a
+// host-driven loop), post-processing, and the extern "C" boundary declared in include/sla.h.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sla.h"
+#include "sla_kernels.cuh"
+
+using namespace sla;
+
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_create_error;
+
+struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t generation = 0;
+    int lpr = 0;
+    int super_rounds = 0;
+};
+
+}  // namespace
+
+struct sla_batch_state;
+struct sla_part_state;
+
+struct sla_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+
+    // capacities (elements)
+    size_t cap_rows = 0, cap_cols = 0, cap_arcs = 0;
+    // CSR mirror
+    uint32_t* d_row_ptr = nullptr;
+    uint32_t* d_cols = nullptr;
+    double* d_vals = nullptr;
+    // solve state
+    double* d_prices = nullptr;
+    uint32_t* d_p2o = nullptr;
+    uint32_t* d_o2p = nullptr;
+    unsigned long long* d_best = nullptr;
+    uint32_t* d_queue[2] = {nullptr, nullptr};
+    uint32_t* d_slot_obj = nullptr;
+    double* d_slot_bid = nullptr;
+    DevState* d_state = nullptr;
+    DevCsrStats* d_csr_stats = nullptr;
+    uint32_t* d_scratch = nullptr;   // 16 words
+    double* d_partial = nullptr;     // objective partial sums, one per block
+    // pinned staging
+    DevState* h_state = nullptr;
+    DevCsrStats* h_csr_stats = nullptr;
+    uint32_t* h_scratch = nullptr;
+    double* h_partial = nullptr;
+
+    // problem
+    bool has_csr = false, has_solution = false, best_dirty = true;
+    uint32_t n_rows = 0, n_cols = 0;
+    uint64_t nnz = 0;
+    double v_min = 0, v_max = 0, first_value = 0;
+    int dev_sign = 1;   // effective values = dev_sign * uploaded values (in-place negation of solver.rs:214-216)
+    int lpr = 4;
+
+    // options
+    int opt_graph = 1, opt_tail_max = 1024, opt_skip_zero = 1, opt_profile = 0, opt_super_rounds = 6;
+    double opt_timeout_s = 900.0;   // wall-clock guard of one solve ("timeout_s" option / SLA_TIMEOUT_S)
+    uint64_t generation = 1;   // bumped whenever a device buffer is reallocated
+    GraphSlot graphs[2];
+    int grid_wide = 0;
+
+    std::vector<sla_round_profile> profile;
+
+    sla_batch_state* batch = nullptr;
+    sla_part_state* part = nullptr;
+};
+
+namespace {
+
+int fail(sla_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(ctx, SLA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+template <class T>
+int dev_alloc(sla_ctx* ctx, T** p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return fail(ctx, SLA_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    return SLA_OK;
+}
+
+Params make_params(const sla_ctx* c) {
+    Params p;
+    p.row_ptr = c->d_row_ptr; p.cols = c->d_cols; p.vals = c->d_vals;
+    p.prices = c->d_prices; p.p2o = c->d_p2o; p.o2p = c->d_o2p; p.best = c->d_best;
+    p.queue[0] = c->d_queue[0]; p.queue[1] = c->d_queue[1];
+    p.slot_obj = c->d_slot_obj; p.slot_bid = c->d_slot_bid; p.st = c->d_state;
+    return p;
+}
+
+void drop_graphs(sla_ctx* c) {
+    for (auto& g : c->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = GraphSlot();
+    }
+}
+
+int ensure_capacity(sla_ctx* ctx, size_t rows, size_t cols, size_t arcs) {
+    bool changed = false;
+    if (rows > ctx->cap_rows || !ctx->d_row_ptr) {
+        size_t n = rows > ctx->cap_rows ? rows : ctx->cap_rows;
+        int rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_row_ptr, n + 8))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_p2o, n))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_queue[0], n))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_queue[1], n))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_slot_obj, n))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_slot_bid, n))) return rc;
+        ctx->cap_rows = n;
+        changed = true;
+    }
+    if (cols > ctx->cap_cols || !ctx->d_prices) {
+        size_t n = cols > ctx->cap_cols ? cols : ctx->cap_cols;
+        int rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_prices, n))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_o2p, n))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_best, n))) return rc;
+        ctx->cap_cols = n;
+        ctx->best_dirty = true;
+        changed = true;
+    }
+    if (arcs > ctx->cap_arcs || !ctx->d_cols) {
+        size_t n = arcs > ctx->cap_arcs ? arcs : ctx->cap_arcs;
+        int rc;
+        // +8: scan_row reads whole aligned 4-arc chunks, so the tail of the last row may be over-read
+        if ((rc = dev_alloc(ctx, &ctx->d_cols, n + 8))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_vals, n + 8))) return rc;
+        CU(cudaMemsetAsync(ctx->d_cols, 0, (n + 8) * sizeof(uint32_t), ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_vals, 0, (n + 8) * sizeof(double), ctx->stream));
+        ctx->cap_arcs = n;
+        changed = true;
+    }
+    if (changed) {
+        ctx->generation += 1;
+        drop_graphs(ctx);
+        ctx->has_csr = false;
+        ctx->has_solution = false;
+    }
+    return SLA_OK;
+}
+
+int pick_lpr(uint64_t nnz, uint32_t n_rows) {
+    const double avg = n_rows ? (double)nnz / (double)n_rows : 1.0;
+    int lpr = 1;
+    while (lpr < 32 && (double)(lpr * 4) < avg) lpr *= 2;
+    return lpr;
+}
+
+// ---- kernel dispatch on lanes-per-row -----------------------------------------------------------------
+template <int LPR>
+void launch_super_round_t(sla_ctx* c, const Params& p, bool forward) {
+    bid_wide_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
+    assign_wide_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
+    tail_kernel<LPR><<<1, kTailThreads, 0, c->stream>>>(p);
+    if (forward) {
+        ecs_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
+        phase_apply_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
+    }
+}
+
+void launch_super_round(sla_ctx* c, const Params& p, bool forward) {
+    switch (c->lpr) {
+        case 1: launch_super_round_t<1>(c, p, forward); break;
+        case 2: launch_super_round_t<2>(c, p, forward); break;
+        case 4: launch_super_round_t<4>(c, p, forward); break;
+        case 8: launch_super_round_t<8>(c, p, forward); break;
+        case 16: launch_super_round_t<16>(c, p, forward); break;
+        default: launch_super_round_t<32>(c, p, forward); break;
+    }
+}
+
+template <int LPR>
+void launch_one_t(sla_ctx* c, const Params& p, int which) {
+    switch (which) {
+        case 0: bid_wide_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 1: assign_wide_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 2: tail_kernel<LPR><<<1, kTailThreads, 0, c->stream>>>(p); break;
+        case 3: ecs_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        default: phase_apply_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+    }
+}
+void launch_one(sla_ctx* c, const Params& p, int which) {
+    switch (c->lpr) {
+        case 1: launch_one_t<1>(c, p, which); break;
+        case 2: launch_one_t<2>(c, p, which); break;
+        case 4: launch_one_t<4>(c, p, which); break;
+        case 8: launch_one_t<8>(c, p, which); break;
+        case 16: launch_one_t<16>(c, p, which); break;
+        default: launch_one_t<32>(c, p, which); break;
+    }
+}
+
+int kernels_per_super_round(bool forward) { return forward ? 5 : 3; }
+
+int get_graph(sla_ctx* ctx, bool forward, cudaGraphExec_t* out) {
+    GraphSlot& g = ctx->graphs[forward ? 1 : 0];
+    if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == ctx->opt_super_rounds) {
+        *out = g.exec;
+        return SLA_OK;
+    }
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    const Params p = make_params(ctx);
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    for (int r = 0; r < ctx->opt_super_rounds; ++r) launch_super_round(ctx, p, forward);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (e != cudaSuccess) return fail(ctx, SLA_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        g.exec = nullptr;
+        return fail(ctx, SLA_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    g.generation = ctx->generation;
+    g.lpr = ctx->lpr;
+    g.super_rounds = ctx->opt_super_rounds;
+    *out = g.exec;
+    return SLA_OK;
+}
+
+double get_toleration_host(double c) {
+    // reference src/solver.rs:144-146: 1 / 2^(53 - (log2(c + 1e-7) as u32)), saturating cast
+    const double l = std::log2(c + 1e-7);
+    uint32_t li = !(l > 0.0) ? 0u : (l >= 4294967295.0 ? 4294967295u : (uint32_t)l);
+    const uint32_t e = 53u - li;
+    const uint64_t pw = e < 64 ? ((uint64_t)1 << e) : 0;
+    return 1.0 / (double)pw;
+}
+
+uint32_t person_bits(uint32_t n_rows) {
+    uint32_t m = n_rows > 1 ? n_rows - 1 : 1;
+    uint32_t b = 0;
+    while (m) { ++b; m >>= 1; }
+    return b;
+}
+
+int poll_state(sla_ctx* ctx) {
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SLA_OK;
+}
+
+int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz);
+
+// The solve driver shared by both algorithms.
+int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double start_eps_in, uint32_t max_iterations,
+                 uint32_t* h_p2o, uint32_t* h_o2p, double* h_prices, sla_stats* stats) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (!ctx->has_csr) return fail(ctx, SLA_ERR_STATE, "solve called before a CSR was uploaded");
+    CU(cudaSetDevice(ctx->device));
+    const bool forward = (algo == SLA_ALGO_FORWARD);
+    const uint32_t N = ctx->n_rows, M = ctx->n_cols;
+
+    // ---- sign normalisation, reference src/solver.rs:207-216 (the device keeps the uploaded values and a sign) ----
+    const double first_eff = ctx->dev_sign > 0 ? ctx->first_value : -ctx->first_value;
+    const bool positive = first_eff >= 0.0;
+    const bool flip = (maximize != 0) != positive;
+    if (flip) ctx->dev_sign = -ctx->dev_sign;
+    const double w_min = ctx->dev_sign > 0 ? ctx->v_min : -ctx->v_max;
+    const double w_max = ctx->dev_sign > 0 ? ctx->v_max : -ctx->v_min;
+
+    DevState s;
+    memset(&s, 0, sizeof s);
+    s.qlen[0] = N;
+    s.cur = 0;
+    s.identity = 1;
+    s.zero_prices = 1;
+    s.algo = forward ? ALGO_FORWARD : ALGO_KHOSLA;
+    s.pbits = person_bits(N);
+    s.tail_max = (uint32_t)ctx->opt_tail_max;
+    s.skip_zero = (uint32_t)ctx->opt_skip_zero;
+    s.sign_flip = ctx->dev_sign < 0 ? 0x80000000u : 0u;
+    s.n_rows = N;
+    s.n_cols = M;
+    s.safety_rounds_left = 1ull << 40;
+    s.tail_round_cap = 1u << 19;
+    if (!forward) {
+        // reference src/ksparse.rs:160-181
+        const double m = (double)M;
+        s.eps = std::isnan(eps_in) ? 1.0 / m : eps_in;
+        s.threshold = (m / 2.0) * (w_max - w_min + s.eps);
+        s.max_iterations = 0xFFFFFFFFu;
+    } else {
+        // reference src/symmetric.rs:229-273
+        const double target = std::isnan(eps_in) ? 1.0 / (double)N : eps_in;
+        s.target_eps = target;
+        s.max_iterations = max_iterations ? max_iterations : 100000u;
+        const double c = std::fmax(std::fabs(w_min), std::fabs(w_max));
+        s.tol = get_toleration_host(c);
+        bool start_opt = !std::isnan(start_eps_in) ? (start_eps_in < target) : false;
+        if (N != M) {
+            start_opt = true;
+            s.eps = target - 2.220446049250313e-16;
+        } else {
+            s.eps = !std::isnan(start_eps_in) ? start_eps_in : c / 2.0;
+        }
+        s.start_opt = start_opt ? 1u : 0u;
+    }
+    *ctx->h_state = s;
+
+    const Params p = make_params(ctx);
+    uint32_t launches = 0, graph_launches = 0;
+    ctx->profile.clear();
+    ctx->has_solution = false;
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_state, ctx->h_state, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
+    init_solve_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, N, M, ctx->best_dirty ? 1 : 0);
+    launches += 1;
+    ctx->best_dirty = true;   // until the solve ends at a round boundary
+
+    const bool use_graph = ctx->opt_graph && !ctx->opt_profile;
+    bool done = false;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto timed_out = [&]() {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > ctx->opt_timeout_s;
+    };
+    if (use_graph) {
+        cudaGraphExec_t exec = nullptr;
+        int rc = get_graph(ctx, forward, &exec);
+        if (rc) return rc;
+        while (!done) {
+            CU(cudaGraphLaunch(exec, ctx->stream));
+            graph_launches += 1;
+            launches += (uint32_t)(ctx->opt_super_rounds * kernels_per_super_round(forward));
+            if ((rc = poll_state(ctx))) return rc;
+            done = ctx->h_state->done != 0;
+            if (!done && timed_out()) return fail(ctx, SLA_ERR_STATE, "solve exceeded the wall-clock guard (timeout_s)");
+        }
+    } else {
+        // Host-driven loop: one super-round per iteration, state polled after each.  With "profile" the wide
+        // kernels and the tail engine are bracketed by CUDA events on the solve stream.
+        DevState prev = s;
+        while (!done) {
+            const bool wide = !prev.done && prev.qlen[prev.cur] > prev.tail_max;
+            if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+            launch_one(ctx, p, 0);
+            if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+            launch_one(ctx, p, 1);
+            if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+            launches += 2;
+            if (ctx->opt_profile) {
+                int rc = poll_state(ctx);   // state after the wide pair, before control step A
+                if (rc) return rc;
+                if (wide) {
+                    sla_round_profile r;
+                    memset(&r, 0, sizeof r);
+                    r.round = (uint32_t)prev.rounds;
+                    r.engine = 0;
+                    r.bidders = prev.qlen[prev.cur];
+                    r.rounds_covered = 1;
+                    r.arcs = ctx->h_state->bid_arcs - prev.bid_arcs;
+                    cudaEventElapsedTime(&r.bid_ms, ctx->ev[1], ctx->ev[2]);
+                    cudaEventElapsedTime(&r.assign_ms, ctx->ev[2], ctx->ev[3]);
+                    ctx->profile.push_back(r);
+                }
+                CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+            }
+            launch_one(ctx, p, 2);
+            launches += 1;
+            if (ctx->opt_profile) {
+                CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+                const DevState mid = *ctx->h_state;
+                int rc = poll_state(ctx);
+                if (rc) return rc;
+                if (ctx->h_state->tail_rounds > mid.tail_rounds) {
+                    sla_round_profile r;
+                    memset(&r, 0, sizeof r);
+                    r.round = (uint32_t)(mid.rounds + (wide ? 1 : 0));
+                    r.engine = 1;
+                    r.bidders = wide ? mid.qlen[mid.cur ^ 1u] : mid.qlen[mid.cur];
+                    r.rounds_covered = (uint32_t)(ctx->h_state->tail_rounds - mid.tail_rounds);
+                    r.arcs = ctx->h_state->bid_arcs - mid.bid_arcs;
+                    cudaEventElapsedTime(&r.bid_ms, ctx->ev[1], ctx->ev[2]);
+                    ctx->profile.push_back(r);
+                }
+            }
+            if (forward) {
+                launch_one(ctx, p, 3);
+                launch_one(ctx, p, 4);
+                launches += 2;
+            }
+            int rc = poll_state(ctx);
+            if (rc) return rc;
+            prev = *ctx->h_state;
+            done = prev.done != 0;
+            if (!done && timed_out()) return fail(ctx, SLA_ERR_STATE, "solve exceeded the wall-clock guard (timeout_s)");
+        }
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    const DevState f = *ctx->h_state;
+    if (f.safety_rounds_left <= 1) return fail(ctx, SLA_ERR_STATE, "safety round limit reached");
+    ctx->best_dirty = false;
+    ctx->has_solution = true;
+
+    if (h_p2o) CU(cudaMemcpyAsync(h_p2o, ctx->d_p2o, (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_o2p) CU(cudaMemcpyAsync(h_o2p, ctx->d_o2p, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_prices) CU(cudaMemcpyAsync(h_prices, ctx->d_prices, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->nreductions = f.nreductions;
+        stats->optimal_soln_found = f.optimal;
+        stats->eps = f.eps;
+        stats->rounds = f.rounds;
+        stats->bids = f.bids;
+        stats->bid_arcs = f.bid_arcs;
+        stats->dropped = f.dropped;
+        stats->values_negated = flip ? 1u : 0u;
+        stats->wide_rounds = f.wide_rounds;
+        stats->tail_rounds = f.tail_rounds;
+        stats->kernel_launches = launches;
+        stats->graph_launches = graph_launches;
+        if (forward) {
+            stats->nits = f.nits;
+            stats->num_unassigned = f.qlen[f.cur];
+        } else {
+            stats->nits = (uint32_t)f.bids;
+            stats->num_unassigned = f.dropped;
+        }
+        cudaEventElapsedTime(&stats->ms_solve, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&stats->ms_total, ctx->ev[0], ctx->ev[2]);
+    }
+    return SLA_OK;
+}
+
+// After the three CSR arrays are resident: statistics + validation (solver.rs:232-243).
+int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz) {
+    DevCsrStats init;
+    init.min_key = ~0ull; init.max_key = 0ull; init.bad_cols = 0; init.bad_rows = 0;
+    *ctx->h_csr_stats = init;
+    CU(cudaMemcpyAsync(ctx->d_csr_stats, ctx->h_csr_stats, sizeof(DevCsrStats), cudaMemcpyHostToDevice, ctx->stream));
+    csr_stats_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(ctx->d_row_ptr, ctx->d_cols, ctx->d_vals, num_rows,
+                                                                      num_cols, nnz, ctx->d_csr_stats);
+    CU(cudaMemcpyAsync(ctx->h_csr_stats, ctx->d_csr_stats, sizeof(DevCsrStats), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_partial, ctx->d_vals, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_scratch, ctx->d_row_ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_scratch + 1, ctx->d_row_ptr + num_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    ctx->has_csr = false;
+    if (ctx->h_scratch[0] != 0 || (uint64_t)ctx->h_scratch[1] != nnz)
+        return fail(ctx, SLA_ERR_INVALID, "row_ptr[0] must be 0 and row_ptr[num_rows] must equal nnz");
+    if (ctx->h_csr_stats->bad_rows) return fail(ctx, SLA_ERR_INVALID, "row extents are not monotone");
+    if (ctx->h_csr_stats->bad_cols) return fail(ctx, SLA_ERR_INVALID, "column index out of range (>= num_cols)");
+    ctx->n_rows = num_rows;
+    ctx->n_cols = num_cols;
+    ctx->nnz = nnz;
+    ctx->v_min = order_key_to_f64_host(ctx->h_csr_stats->min_key);
+    ctx->v_max = order_key_to_f64_host(ctx->h_csr_stats->max_key);
+    ctx->first_value = ctx->h_partial[0];
+    ctx->dev_sign = 1;
+    ctx->lpr = pick_lpr(nnz, num_rows);
+    ctx->has_csr = true;
+    ctx->has_solution = false;
+    return SLA_OK;
+}
+
+int check_shape(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz) {
+    // reference src/solver.rs:192-193 (init) and 232-240 (validate_input), for I = u32
+    if (!(num_rows <= num_cols)) return fail(ctx, SLA_ERR_INVALID, "num_rows must be <= num_cols");
+    if (!(num_rows < 0xFFFFFFFFu)) return fail(ctx, SLA_ERR_INVALID, "num_rows must be < u32::MAX");
+    if (!(nnz > 0)) return fail(ctx, SLA_ERR_INVALID, "no arcs");
+    if (!(num_rows > 0 && num_cols > 0)) return fail(ctx, SLA_ERR_INVALID, "num_rows and num_cols must be positive");
+    if (!(nnz < 0xFFFFFFFFull)) return fail(ctx, SLA_ERR_INVALID, "number of arcs must be < u32::MAX");
+    return SLA_OK;
+}
+
+}  // namespace
+
+// =============================================================================================================
+// extern "C" boundary
+// =============================================================================================================
+extern "C" {
+
+const char* sla_version(void) { return "sla_b200 0.1.0 (sm_100a)"; }
+
+int sla_ctx_create(int device, size_t row_capacity, size_t col_capacity, size_t arc_capacity, sla_ctx** out) {
+    if (!out) return SLA_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return SLA_ERR_NO_DEVICE;
+    }
+    if (device < 0) device = 0;
+    if (device >= count) { g_create_error = "device index out of range"; return SLA_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return SLA_ERR_NO_DEVICE;
+    }
+    if (prop.major != 10) {
+        g_create_error = "this library contains sm_100a code only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        return SLA_ERR_NO_DEVICE;
+    }
+    sla_ctx* ctx = new sla_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (const char* t = getenv("SLA_TIMEOUT_S")) ctx->opt_timeout_s = atof(t);
+    auto bail = [&](const char* what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        sla_ctx_destroy(ctx);
+        return SLA_ERR_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (auto& ev : ctx->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_state, sizeof(DevState))) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_csr_stats, sizeof(DevCsrStats))) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_scratch, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMallocHost", e);
+    // blocks per SM of the widest kernel decide the persistent grid
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bid_wide_kernel<4>, kWideThreads, 0);
+    if (occ < 1) occ = 1;
+    if (occ > 8) occ = 8;
+    ctx->grid_wide = ctx->num_sms * occ;
+    if ((e = cudaMallocHost((void**)&ctx->h_partial, (size_t)ctx->grid_wide * sizeof(double))) != cudaSuccess)
+        return bail("cudaMallocHost", e);
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_state, 1)) || (rc = dev_alloc(ctx, &ctx->d_csr_stats, 1)) ||
+        (rc = dev_alloc(ctx, &ctx->d_scratch, 16)) || (rc = dev_alloc(ctx, &ctx->d_partial, (size_t)ctx->grid_wide)) ||
+        (rc = ensure_capacity(ctx, row_capacity ? row_capacity : 1, col_capacity ? col_capacity : 1,
+                              arc_capacity ? arc_capacity : 1))) {
+        g_create_error = ctx->err;
+        sla_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return SLA_OK;
+}
+
+void sla_batch_free(sla_ctx* ctx);
+void sla_part_free(sla_ctx* ctx);
+
+void sla_ctx_destroy(sla_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    sla_batch_free(ctx);
+    sla_part_free(ctx);
+    drop_graphs(ctx);
+    cudaFree(ctx->d_row_ptr); cudaFree(ctx->d_cols); cudaFree(ctx->d_vals); cudaFree(ctx->d_prices);
+    cudaFree(ctx->d_p2o); cudaFree(ctx->d_o2p); cudaFree(ctx->d_best); cudaFree(ctx->d_queue[0]);
+    cudaFree(ctx->d_queue[1]); cudaFree(ctx->d_slot_obj); cudaFree(ctx->d_slot_bid); cudaFree(ctx->d_state);
+    cudaFree(ctx->d_csr_stats); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial);
+    if (ctx->h_state) cudaFreeHost(ctx->h_state);
+    if (ctx->h_csr_stats) cudaFreeHost(ctx->h_csr_stats);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    if (ctx->h_partial) cudaFreeHost(ctx->h_partial);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* sla_last_error(const sla_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+void* sla_ctx_stream(sla_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int sla_ctx_device(const sla_ctx* ctx) { return ctx ? ctx->device : -1; }
+
+int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return SLA_ERR_INVALID;
+    const std::string k(key);
+    if (k == "tail_max") {
+        if (value < 0 || value > kTailCap) return fail(ctx, SLA_ERR_INVALID, "tail_max must be in [0, 2048]");
+        ctx->opt_tail_max = (int)value;
+    } else if (k == "graph") {
+        ctx->opt_graph = value ? 1 : 0;
+    } else if (k == "zero_price_skip") {
+        ctx->opt_skip_zero = value ? 1 : 0;
+    } else if (k == "profile") {
+        ctx->opt_profile = value ? 1 : 0;
+    } else if (k == "timeout_s") {
+        ctx->opt_timeout_s = (double)value;
+    } else if (k == "super_rounds") {
+        if (value < 1 || value > 64) return fail(ctx, SLA_ERR_INVALID, "super_rounds must be in [1, 64]");
+        ctx->opt_super_rounds = (int)value;
+    } else {
+        return fail(ctx, SLA_ERR_INVALID, "unknown option: " + k);
+    }
+    return SLA_OK;
+}
+
+int sla_upload_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* row_ptr,
+                   const uint32_t* column_indices, const double* values, uint64_t nnz) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (!row_ptr || !column_indices || !values) return fail(ctx, SLA_ERR_INVALID, "null input array");
+    int rc = check_shape(ctx, num_rows, num_cols, nnz);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_cols, column_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_vals, values, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return finish_csr(ctx, num_rows, num_cols, nnz);
+}
+
+int sla_upload_csr_device(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* d_row_ptr,
+                          const uint32_t* d_column_indices, const double* d_values, uint64_t nnz) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (!d_row_ptr || !d_column_indices || !d_values) return fail(ctx, SLA_ERR_INVALID, "null input array");
+    int rc = check_shape(ctx, num_rows, num_cols, nnz);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_row_ptr, d_row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_cols, d_column_indices, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_vals, d_values, (size_t)nnz * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return finish_csr(ctx, num_rows, num_cols, nnz);
+}
+
+static int make_spec(sla_ctx* ctx, sla_synth::Spec* s, uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed,
+                     uint32_t value_lo, uint32_t value_hi, int planted) {
+    if (k == 0 || k > num_cols || (planted && num_cols < 2 && k > 1))
+        return fail(ctx, SLA_ERR_INVALID, "k must be in [1, num_cols]");
+    if (!(value_hi > value_lo)) return fail(ctx, SLA_ERR_INVALID, "value_hi must be > value_lo");
+    if ((uint64_t)num_rows * k >= 0xFFFFFFFFull) return fail(ctx, SLA_ERR_INVALID, "num_rows * k must be < u32::MAX");
+    s->num_rows = num_rows; s->num_cols = num_cols; s->k = k; s->seed = seed;
+    s->value_lo = value_lo; s->value_hi = value_hi; s->planted = planted ? 1u : 0u;
+    sla_synth::finish_spec(*s);
+    return SLA_OK;
+}
+
+int sla_generate_device(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed,
+                        uint32_t value_lo, uint32_t value_hi, int planted) {
+    if (!ctx) return SLA_ERR_INVALID;
+    const uint64_t nnz = (uint64_t)num_rows * k;
+    int rc = check_shape(ctx, num_rows, num_cols, nnz);
+    if (rc) return rc;
+    sla_synth::Spec s;
+    if ((rc = make_spec(ctx, &s, num_rows, num_cols, k, seed, value_lo, value_hi, planted))) return rc;
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
+    generate_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(s, 0u, num_rows, ctx->d_row_ptr, ctx->d_cols, ctx->d_vals);
+    return finish_csr(ctx, num_rows, num_cols, nnz);
+}
+
+int sla_generate_host(uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed, uint32_t value_lo,
+                      uint32_t value_hi, int planted, uint32_t* row_ptr, uint32_t* column_indices, double* values) {
+    if (!row_ptr || !column_indices || !values) return SLA_ERR_INVALID;
+    sla_synth::Spec s;
+    int rc = make_spec(nullptr, &s, num_rows, num_cols, k, seed, value_lo, value_hi, planted);
+    if (rc) return rc;
+    for (uint32_t r = 0; r < num_rows; ++r) {
+        const size_t off = (size_t)r * k;
+        sla_synth::make_row(s, r, column_indices + off, values + off);
+        row_ptr[r] = (uint32_t)off;
+    }
+    row_ptr[num_rows] = num_rows * k;
+    return SLA_OK;
+}
+
+int sla_khosla_solve(sla_ctx* ctx, int maximize, double eps, uint32_t* person_to_object, uint32_t* object_to_person,
+                     double* prices, sla_stats* stats) {
+    return solve_common(ctx, SLA_ALGO_KHOSLA, maximize, eps, NAN, 0, person_to_object, object_to_person, prices, stats);
+}
+
+int sla_forward_solve(sla_ctx* ctx, int maximize, double eps, double start_eps, uint32_t max_iterations,
+                      uint32_t* person_to_object, uint32_t* object_to_person, double* prices, sla_stats* stats) {
+    return solve_common(ctx, SLA_ALGO_FORWARD, maximize, eps, start_eps, max_iterations, person_to_object,
+                        object_to_person, prices, stats);
+}
+
+int sla_download_solution(sla_ctx* ctx, uint32_t* person_to_object, uint32_t* object_to_person, double* prices) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (!ctx->has_solution) return fail(ctx, SLA_ERR_STATE, "no resident solution");
+    CU(cudaSetDevice(ctx->device));
+    if (person_to_object)
+        CU(cudaMemcpyAsync(person_to_object, ctx->d_p2o, (size_t)ctx->n_rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (object_to_person)
+        CU(cudaMemcpyAsync(object_to_person, ctx->d_o2p, (size_t)ctx->n_cols * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (prices) CU(cudaMemcpyAsync(prices, ctx->d_prices, (size_t)ctx->n_cols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SLA_OK;
+}
+
+int sla_get_objective(sla_ctx* ctx, double* objective) {
+    if (!ctx || !objective) return SLA_ERR_INVALID;
+    if (!ctx->has_solution) return fail(ctx, SLA_ERR_STATE, "no resident solution");
+    CU(cudaSetDevice(ctx->device));
+    const Params p = make_params(ctx);
+    const uint32_t flip = ctx->dev_sign < 0 ? 0x80000000u : 0u;
+    objective_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, ctx->n_rows, flip, ctx->d_partial);
+    CU(cudaMemcpyAsync(ctx->h_partial, ctx->d_partial, (size_t)ctx->grid_wide * sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    double sum = 0.0;
+    for (int b = 0; b < ctx->grid_wide; ++b) sum += ctx->h_partial[b];
+    // reference src/solver.rs:111-137: the sign is taken from the (current, possibly negated) first value
+    const double first_eff = ctx->dev_sign > 0 ? ctx->first_value : -ctx->first_value;
+    *objective = (first_eff >= 0.0) ? sum : -sum;
+    return SLA_OK;
+}
+
+int sla_ecs_satisfied(sla_ctx* ctx, double eps, double toleration, int* satisfied) {
+    if (!ctx || !satisfied) return SLA_ERR_INVALID;
+    if (!ctx->has_solution) return fail(ctx, SLA_ERR_STATE, "no resident solution");
+    CU(cudaSetDevice(ctx->device));
+    const Params p = make_params(ctx);
+    const uint32_t flip = ctx->dev_sign < 0 ? 0x80000000u : 0u;
+    CU(cudaMemsetAsync(ctx->d_scratch, 0, 16 * sizeof(uint32_t), ctx->stream));
+    ecs_check_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, ctx->n_rows, ctx->n_cols, flip, eps, toleration,
+                                                                      ctx->d_scratch);
+    CU(cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    *satisfied = ctx->h_scratch[0] ? 0 : 1;
+    return SLA_OK;
+}
+
+int sla_validate_matching(sla_ctx* ctx, uint32_t* num_unassigned, int* consistent) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (!ctx->has_solution) return fail(ctx, SLA_ERR_STATE, "no resident solution");
+    CU(cudaSetDevice(ctx->device));
+    const Params p = make_params(ctx);
+    CU(cudaMemsetAsync(ctx->d_scratch, 0, 16 * sizeof(uint32_t), ctx->stream));
+    validate_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, ctx->n_rows, ctx->n_cols, ctx->d_scratch);
+    CU(cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    if (num_unassigned) *num_unassigned = ctx->h_scratch[0];
+    if (consistent) *consistent = ctx->h_scratch[1] ? 0 : 1;
+    return SLA_OK;
+}
+
+int sla_get_round_profile(sla_ctx* ctx, sla_round_profile* out, size_t capacity, size_t* count) {
+    if (!ctx || !count) return SLA_ERR_INVALID;
+    *count = ctx->profile.size();
+    if (out) {
+        const size_t n = ctx->profile.size() < capacity ? ctx->profile.size() : capacity;
+        if (n) memcpy(out, ctx->profile.data(), n * sizeof(sla_round_profile));
+    }
+    return SLA_OK;
+}
+
+}  // extern "C"
+
+#include "sla_batch.cuh"
+#include "sla_part.cuh"

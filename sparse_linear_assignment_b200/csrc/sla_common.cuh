@@ -1,0 +1,234 @@
+// sla_common.cuh -- shared device-side definitions of the B200 auction path.
+//
+// Round semantics: a synchronous Jacobi auction.  Every queued (unassigned) person scans its CSR
+// row against frozen prices (the reference's choice rule, src/ksparse.rs:199-214 == src/symmetric.rs:361-376),
+// submits one bid, the per-object winner is the maximum packed (bid key, person) word, the winner installs its
+// own exact f64 bid as the new price, and evicted owners plus losers form the next queue.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define SLA_DEV_NONE 0xFFFFFFFFu
+
+namespace sla {
+
+constexpr int kTailCap = 2048;       // max bidders the single-CTA tail engine accepts (smem-resident queue)
+constexpr int kWideThreads = 256;    // block size of the grid-wide kernels
+constexpr int kTailThreads = 1024;   // block size of the tail engine
+
+enum : uint32_t { ALGO_KHOSLA = 0, ALGO_FORWARD = 1 };
+enum : uint32_t { ACTION_NONE = 0, ACTION_RESET = 1 };
+
+// Device-resident control block of one solve.  Only single threads write it (see the kernels).
+struct DevState {
+    uint32_t qlen[2];        // lengths of the two queue buffers
+    uint32_t cur;            // which queue buffer holds the current bidders
+    uint32_t done;           // solve finished
+    uint32_t identity;       // current queue is the implicit [0, qlen)
+    uint32_t zero_prices;    // every price is exactly 0.0 (first round after init_solve): gather may be skipped
+    uint32_t algo;
+    uint32_t pbits;          // bits of the person field of a packed bid word
+    uint32_t nits;           // Forward: rounds (symmetric.rs:277); Khosla: filled from `bids` at the end
+    uint32_t nreductions;
+    uint32_t optimal;
+    uint32_t ecs_violated;
+    uint32_t ecs_ticket;
+    uint32_t action;
+    uint32_t dropped;
+    uint32_t max_iterations;
+    uint32_t start_opt;      // start_from_optimal_eps (symmetric.rs:251-266)
+    uint32_t tail_max;
+    uint32_t skip_zero;      // option zero_price_skip
+    uint32_t sign_flip;      // 0x80000000 when the effective values are the negated uploaded values, else 0
+    uint32_t n_rows, n_cols;
+    uint32_t tail_round_cap; // rounds one tail launch may run before handing control back to the host
+    double eps;
+    double target_eps;
+    double tol;
+    double threshold;        // Khosla price threshold (ksparse.rs:181)
+    unsigned long long rounds, bids, bid_arcs, wide_rounds, tail_rounds;
+    unsigned long long safety_rounds_left;
+};
+
+// Value statistics of the uploaded CSR (computed once per upload).
+struct DevCsrStats {
+    unsigned long long min_key, max_key;   // order-preserving u64 keys of min / max value
+    unsigned long long bad_cols;           // arcs whose column index is >= num_cols
+    unsigned long long bad_rows;           // rows whose extents are not monotone / exceed nnz
+};
+
+// Every buffer a kernel needs, passed by value.  Pointers only: sizes, sign and all per-solve scalars live in
+// the device-resident DevState, so a captured graph stays valid across uploads and solves until a buffer is
+// reallocated.
+struct Params {
+    const uint32_t* __restrict__ row_ptr;
+    const uint32_t* __restrict__ cols;
+    const double* __restrict__ vals;
+    double* prices;
+    uint32_t* p2o;
+    uint32_t* o2p;
+    unsigned long long* best;   // packed best-bid word per object, 0 = no bid
+    uint32_t* queue[2];
+    uint32_t* slot_obj;         // per queue slot: object bid on (SLA_DEV_NONE = dropped)
+    double* slot_bid;           // per queue slot: exact f64 bid
+    DevState* st;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f64_order_key(double x) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return u ^ ((u >> 63) ? ~0ull : (1ull << 63));
+}
+__host__ __device__ __forceinline__ double order_key_to_f64_host(unsigned long long k) {
+    unsigned long long u = (k >> 63) ? (k ^ (1ull << 63)) : ~k;
+    double d;
+#ifdef __CUDA_ARCH__
+    d = __longlong_as_double((long long)u);
+#else
+    __builtin_memcpy(&d, &u, 8);
+#endif
+    return d;
+}
+
+// Packed bid word: [63] = 0, then the top (63 - pbits) bits of the order key of the bid, then (pmask - person)
+// so that on equal keys the LOWER person id wins.  Matches oracle/jacobi_model.c:jm_pack_bid bit for bit.
+__device__ __forceinline__ unsigned long long pack_bid(double bid, uint32_t person, uint32_t pbits) {
+    unsigned long long key = f64_order_key(bid);
+    unsigned long long pmask = (1ull << pbits) - 1ull;
+    return ((key >> (pbits + 1)) << pbits) | (pmask - (unsigned long long)person);
+}
+
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xFFF0000000000000ll); }
+__device__ __forceinline__ bool is_finite_f64(double x) {
+    return (((unsigned long long)__double_as_longlong(x) >> 52) & 0x7FFull) != 0x7FFull;
+}
+
+// ---- loads ------------------------------------------------------------------------------------------------
+// CSR arcs are streamed once per round: read-only path, do not allocate in L1.
+__device__ __forceinline__ uint4 ld_stream_u4(const uint32_t* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ld_stream_d2(const double* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+enum PriceMode : int {
+    PRICE_ZERO = 0,   // all prices are exactly 0.0: no gather
+    PRICE_LDG = 1,    // prices immutable during this kernel: read-only path
+    PRICE_CG = 2      // prices mutated by this kernel (tail / batch engines): L2-coherent loads
+};
+
+template <int MODE>
+__device__ __forceinline__ double ld_price(const double* prices, uint32_t j) {
+    if (MODE == PRICE_ZERO) return 0.0;
+    if (MODE == PRICE_LDG) return __ldg(prices + j);
+    return __ldcg(prices + j);
+}
+
+// ---- the choice rule ---------------------------------------------------------------------------------------
+struct Choice {
+    double best;     // max profit
+    double second;   // second max profit (multiset sense)
+    double value;    // edge value of the best arc
+    uint32_t pos;    // global arc index of the best arc (lowest index wins ties) or SLA_DEV_NONE
+    uint32_t col;    // its column
+};
+
+__device__ __forceinline__ void choice_init(Choice& c) {
+    c.best = neg_inf(); c.second = neg_inf(); c.value = neg_inf(); c.pos = SLA_DEV_NONE; c.col = 0u;
+}
+
+// Sequential update with one arc: exactly the reference's if / else-if (strict '>').
+__device__ __forceinline__ void choice_update(Choice& c, double profit, double value, uint32_t pos, uint32_t col) {
+    if (profit > c.best) {
+        c.second = c.best; c.best = profit; c.value = value; c.pos = pos; c.col = col;
+    } else if (profit > c.second) {
+        c.second = profit;
+    }
+}
+
+// Merge of two partial scans over disjoint arc sets; equals the sequential scan over their union in
+// position order: max profit, lowest position among the maxima, second = second largest of the multiset.
+__device__ __forceinline__ void choice_merge(Choice& c, double ob, double os, double ov, uint32_t opos, uint32_t ocol) {
+    const bool take = (ob > c.best) || (ob == c.best && opos < c.pos);
+    const double loser_best = take ? c.best : ob;
+    double s = (c.second > os) ? c.second : os;
+    s = (loser_best > s) ? loser_best : s;
+    if (take) { c.best = ob; c.value = ov; c.pos = opos; c.col = ocol; }
+    c.second = s;
+}
+
+template <int LPR>
+__device__ __forceinline__ void choice_group_reduce(Choice& c) {
+#pragma unroll
+    for (int m = LPR / 2; m >= 1; m >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, c.best, m);
+        const double os = __shfl_xor_sync(0xffffffffu, c.second, m);
+        const double ov = __shfl_xor_sync(0xffffffffu, c.value, m);
+        const uint32_t op = __shfl_xor_sync(0xffffffffu, c.pos, m);
+        const uint32_t oc = __shfl_xor_sync(0xffffffffu, c.col, m);
+        choice_merge(c, ob, os, ov, op, oc);
+    }
+}
+
+// Scan of row [a, b) by a group of LPR lanes; each lane takes aligned chunks of 4 arcs (one 128-bit load of
+// column indices, two 128-bit loads of values).  Arrays are padded so that the aligned chunk is always
+// in bounds.  `flip` is 0 or 0x80000000 (sign normalisation of solver.rs:209-216 applied on the fly).
+template <int LPR, int MODE>
+__device__ __forceinline__ void scan_row(Choice& c, const uint32_t* __restrict__ cols, const double* __restrict__ vals,
+                                         const double* prices, uint32_t a, uint32_t b, uint32_t flip, int lane) {
+    for (uint32_t base = (a & ~3u) + 4u * (uint32_t)lane; base < b; base += 4u * LPR) {
+        const uint4 cj = ld_stream_u4(cols + base);
+        const double2 v01 = ld_stream_d2(vals + base);
+        const double2 v23 = ld_stream_d2(vals + base + 2);
+        const uint32_t jj[4] = {cj.x, cj.y, cj.z, cj.w};
+        double vv[4] = {v01.x, v01.y, v23.x, v23.y};
+        double pr[4];
+        bool ok[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t g = base + t;
+            ok[t] = (g >= a) && (g < b);
+            pr[t] = ok[t] ? ld_price<MODE>(prices, jj[t]) : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (ok[t]) {
+                const double v = __hiloint2double(__double2hiint(vv[t]) ^ (int)flip, __double2loint(vv[t]));
+                choice_update(c, v - pr[t], v, base + t, jj[t]);
+            }
+        }
+    }
+}
+
+// Outcome of one person's bid: object (SLA_DEV_NONE = dropped by the Khosla threshold) and exact bid.
+struct Bid {
+    uint32_t obj;
+    double bid;
+    bool dropped;
+};
+
+// Bid computation from a finished choice (lane 0 of the group).
+//   Khosla : ksparse.rs:218-227 (threshold test on the current price, `+= eps` when no finite second profit)
+//   Forward: symmetric.rs:378
+template <int MODE>
+__device__ __forceinline__ Bid make_bid(const Choice& c, uint32_t algo, double eps, double threshold, const double* prices) {
+    Bid r;
+    r.obj = (c.pos == SLA_DEV_NONE) ? 0u : c.col;   // the reference starts from object 0 (ksparse.rs:196, symmetric.rs:355)
+    r.dropped = false;
+    if (algo == ALGO_KHOSLA) {
+        const double pj = ld_price<MODE>(prices, r.obj);
+        if (pj > threshold) { r.dropped = true; r.bid = 0.0; return r; }
+        r.bid = is_finite_f64(c.second) ? (c.value - c.second + eps) : (pj + eps);
+    } else {
+        r.bid = c.value - c.second + eps;
+    }
+    return r;
+}
+
+}  // namespace sla

@@ -1,0 +1,569 @@
+// sla_kernels.cuh -- the auction kernels: grid-wide bid scan / assign, the single-CTA tail engine, the
+// Forward phase kernels (eps-CS check, reset), and the small utility kernels around them.
+//
+// Kernel order of one "super-round" (captured into a CUDA graph, DESIGN.md "Control flow"):
+//     bid_wide -> assign_wide -> tail (control step A + tail rounds) -> [Forward only: ecs -> phase_apply]
+// Every kernel decides from the device-resident DevState whether it has work, so the same sequence can be
+// replayed without host involvement until DevState::done is set.
+#pragma once
+#include "sla_common.cuh"
+#include "synth.h"
+
+namespace sla {
+
+// =============================================================================================================
+// Grid-wide bid scan  (reference hot loops src/ksparse.rs:199-227, src/symmetric.rs:343-384)
+// One group of LPR lanes per bidder; coalesced 128-bit loads of the CSR row; shuffle reduction of
+// (best, second best, best value, best position); one 64-bit atomicMax per bid for conflict resolution.
+// =============================================================================================================
+template <int LPR, int MODE>
+__device__ __forceinline__ void bid_wide_body(const Params& p, const uint32_t qlen, const bool identity,
+                                              const uint32_t* __restrict__ queue, const uint32_t algo, const double eps,
+                                              const double threshold, const uint32_t pbits, const uint32_t sign_flip) {
+    constexpr int GROUPS_PER_BLOCK = kWideThreads / LPR;
+    const int lane = threadIdx.x % LPR;
+    const uint32_t group = blockIdx.x * GROUPS_PER_BLOCK + threadIdx.x / LPR;
+    const uint32_t ngroups = gridDim.x * GROUPS_PER_BLOCK;
+    unsigned long long my_arcs = 0;
+    uint32_t my_dropped = 0;
+
+    for (uint32_t base = 0; base < qlen; base += ngroups) {   // grid-uniform trip count (full-mask shuffles inside)
+        const uint32_t q = base + group;
+        const bool valid = q < qlen;
+        uint32_t i = 0, a = 0, b = 0;
+        if (valid) {
+            i = identity ? q : __ldg(queue + q);
+            a = __ldg(p.row_ptr + i);
+            b = __ldg(p.row_ptr + i + 1);
+        }
+        Choice c;
+        choice_init(c);
+        scan_row<LPR, MODE>(c, p.cols, p.vals, p.prices, a, b, sign_flip, lane);
+        choice_group_reduce<LPR>(c);
+        if (valid && lane == 0) {
+            const Bid r = make_bid<MODE>(c, algo, eps, threshold, p.prices);
+            my_arcs += (unsigned long long)(b - a);
+            if (r.dropped) {
+                p.slot_obj[q] = SLA_DEV_NONE;
+                my_dropped += 1;
+            } else {
+                p.slot_obj[q] = r.obj;
+                p.slot_bid[q] = r.bid;
+                if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));   // NaN never bids
+            }
+        }
+    }
+
+    // per-block accumulation of the instrumentation counters
+    __shared__ unsigned long long s_arcs;
+    __shared__ uint32_t s_dropped;
+    if (threadIdx.x == 0) { s_arcs = 0; s_dropped = 0; }
+    __syncthreads();
+    if (my_arcs) atomicAdd(&s_arcs, my_arcs);
+    if (my_dropped) atomicAdd(&s_dropped, my_dropped);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_arcs) atomicAdd(&p.st->bid_arcs, s_arcs);
+        if (s_dropped) atomicAdd(&p.st->dropped, s_dropped);
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(kWideThreads) bid_wide_kernel(const Params p) {
+    const DevState* st = p.st;
+    const uint32_t cur = st->cur;
+    const uint32_t qlen = st->qlen[cur];
+    if (st->done || qlen <= st->tail_max) return;
+    const bool identity = st->identity != 0;
+    const bool zero = (st->zero_prices != 0) && (st->skip_zero != 0);
+    const uint32_t algo = st->algo, pbits = st->pbits;
+    const double eps = st->eps, thr = st->threshold;
+    const uint32_t sf = st->sign_flip;
+    if (zero) bid_wide_body<LPR, PRICE_ZERO>(p, qlen, identity, cur ? p.queue[1] : p.queue[0], algo, eps, thr, pbits, sf);
+    else      bid_wide_body<LPR, PRICE_LDG>(p, qlen, identity, cur ? p.queue[1] : p.queue[0], algo, eps, thr, pbits, sf);
+}
+
+// =============================================================================================================
+// Grid-wide assignment + queue compaction (reference src/symmetric.rs:386-463, src/ksparse.rs:229-244).
+// One thread per old queue slot; each slot yields 0 or 1 entries of the next queue (loser -> itself,
+// winner that evicts -> the evicted owner, winner of a free object or dropped person -> nothing).
+// =============================================================================================================
+__global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params p) {
+    DevState* st = p.st;
+    const uint32_t cur = st->cur;
+    const uint32_t qlen = st->qlen[cur];
+    if (st->done || qlen <= st->tail_max) return;
+    const bool identity = st->identity != 0;
+    const uint32_t pbits = st->pbits;
+    const uint32_t* __restrict__ queue = cur ? p.queue[1] : p.queue[0];
+    uint32_t* __restrict__ next_queue = cur ? p.queue[0] : p.queue[1];
+    uint32_t* next_len = &st->qlen[cur ^ 1u];
+
+    __shared__ uint32_t s_warp_off[kWideThreads / 32];
+    __shared__ uint32_t s_block_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (uint32_t base = blockIdx.x * kWideThreads; base < qlen; base += gridDim.x * kWideThreads) {
+        const uint32_t q = base + threadIdx.x;
+        uint32_t emit = SLA_DEV_NONE;
+        if (q < qlen) {
+            const uint32_t j = p.slot_obj[q];
+            if (j != SLA_DEV_NONE) {
+                const uint32_t i = identity ? q : __ldg(queue + q);
+                const double bid = p.slot_bid[q];
+                const bool won = (bid == bid) && (__ldcg(p.best + j) == pack_bid(bid, i, pbits));
+                if (won) {
+                    const uint32_t prev = p.o2p[j];
+                    p.prices[j] = bid;
+                    p.o2p[j] = i;
+                    p.p2o[i] = j;
+                    p.best[j] = 0ull;
+                    if (prev != SLA_DEV_NONE) { p.p2o[prev] = SLA_DEV_NONE; emit = prev; }
+                } else {
+                    emit = i;
+                }
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
+        const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) s_warp_off[warp] = __popc(ballot);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < kWideThreads / 32; ++w) { const uint32_t c = s_warp_off[w]; s_warp_off[w] = run; run += c; }
+            s_block_base = run ? atomicAdd(next_len, run) : 0u;
+        }
+        __syncthreads();
+        if (emit != SLA_DEV_NONE) next_queue[s_block_base + s_warp_off[warp] + rank] = emit;
+        __syncthreads();
+    }
+}
+
+// =============================================================================================================
+// Control helpers (executed by exactly one thread)
+// =============================================================================================================
+// Queue ran empty: Khosla is finished (ksparse.rs:186 loop exit); Forward is finished without an eps-CS check
+// when start_from_optimal_eps holds (symmetric.rs:279-288).  Otherwise the ecs kernel decides.
+__device__ __forceinline__ void finish_if_possible(DevState* st) {
+    if (st->algo == ALGO_KHOSLA) {
+        st->done = 1;
+    } else if (st->start_opt) {
+        st->optimal = 1;
+        st->done = 1;
+    }
+}
+
+// Control step A: account for the wide round of this super-round (if one ran) and flip the queues.
+// Returns the current queue length afterwards.
+__device__ __forceinline__ uint32_t control_after_wide(DevState* st) {
+    uint32_t cur = st->cur;
+    uint32_t qlen = st->qlen[cur];
+    st->action = ACTION_NONE;
+    if (!st->done && qlen > st->tail_max) {
+        st->rounds += 1;
+        st->wide_rounds += 1;
+        st->bids += qlen;
+        st->qlen[cur] = 0;
+        cur ^= 1u;
+        st->cur = cur;
+        qlen = st->qlen[cur];
+        st->identity = 0;
+        st->zero_prices = 0;
+        if (st->algo == ALGO_FORWARD) {
+            st->nits += 1;
+            if (qlen > 0 && st->nits >= st->max_iterations) st->done = 1;   // symmetric.rs:326-328
+        }
+        if (st->safety_rounds_left <= 1) st->done = 1; else st->safety_rounds_left -= 1;
+        if (!st->done && qlen == 0) finish_if_possible(st);
+    }
+    return qlen;
+}
+
+// =============================================================================================================
+// Tail engine: one persistent CTA runs whole Jacobi rounds (bid -> barrier -> assign/compact -> barrier) while
+// the queue is short; queue and per-slot bids live in shared memory, object state stays in L2.
+// Also hosts control step A (it is the first single-CTA kernel after the wide pair).
+// =============================================================================================================
+template <int LPR>
+__global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
+    __shared__ uint32_t s_queue[2][kTailCap];
+    __shared__ uint32_t s_obj[kTailCap];
+    __shared__ double s_bid[kTailCap];
+    __shared__ uint32_t s_warp_cnt[kTailThreads / 32];
+    __shared__ uint32_t s_ctl[2];
+    __shared__ unsigned long long s_arcs;
+    __shared__ uint32_t s_dropped;
+
+    DevState* st = p.st;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane32 = tid & 31;
+
+    if (tid == 0) {
+        const uint32_t qlen0 = control_after_wide(st);
+        const uint32_t run = (!st->done && qlen0 > 0 && qlen0 <= st->tail_max) ? 1u : 0u;
+        s_ctl[0] = run;
+        s_ctl[1] = qlen0;
+        s_arcs = 0;
+        s_dropped = 0;
+    }
+    __syncthreads();
+    if (!s_ctl[0]) return;
+
+    uint32_t qlen = s_ctl[1];
+    const uint32_t cur = st->cur;
+    const bool identity = st->identity != 0;
+    const uint32_t algo = st->algo, pbits = st->pbits, max_it = st->max_iterations, sign_flip = st->sign_flip;
+    const double eps = st->eps, thr = st->threshold;
+    bool zero = (st->zero_prices != 0) && (st->skip_zero != 0);
+    uint32_t nits = st->nits;
+    unsigned long long safety = st->safety_rounds_left;
+    const uint32_t round_cap = st->tail_round_cap;
+
+    uint32_t* gqueue = cur ? p.queue[1] : p.queue[0];
+    for (uint32_t q = tid; q < qlen; q += kTailThreads) s_queue[0][q] = identity ? q : gqueue[q];
+    __syncthreads();
+
+    constexpr int NGROUPS = kTailThreads / LPR;
+    const int lane = tid % LPR;
+    const uint32_t group = tid / LPR;
+    uint32_t buf = 0;
+    unsigned long long my_arcs = 0, rounds_done = 0, bids_done = 0;
+    uint32_t my_dropped = 0;
+    bool hit_limit = false;
+
+    while (true) {
+        // ---- bidding phase ----
+        const uint32_t* sq = s_queue[buf];
+        for (uint32_t base = 0; base < qlen; base += NGROUPS) {
+            const uint32_t q = base + group;
+            const bool valid = q < qlen;
+            uint32_t i = 0, a = 0, b = 0;
+            if (valid) {
+                i = sq[q];
+                a = __ldg(p.row_ptr + i);
+                b = __ldg(p.row_ptr + i + 1);
+            }
+            Choice c;
+            choice_init(c);
+            if (zero) scan_row<LPR, PRICE_ZERO>(c, p.cols, p.vals, p.prices, a, b, sign_flip, lane);
+            else      scan_row<LPR, PRICE_CG>(c, p.cols, p.vals, p.prices, a, b, sign_flip, lane);
+            choice_group_reduce<LPR>(c);
+            if (valid && lane == 0) {
+                const Bid r = zero ? make_bid<PRICE_ZERO>(c, algo, eps, thr, p.prices)
+                                   : make_bid<PRICE_CG>(c, algo, eps, thr, p.prices);
+                my_arcs += (unsigned long long)(b - a);
+                if (r.dropped) {
+                    s_obj[q] = SLA_DEV_NONE;
+                    my_dropped += 1;
+                } else {
+                    s_obj[q] = r.obj;
+                    s_bid[q] = r.bid;
+                    if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- assignment phase + deterministic compaction into the other smem queue ----
+        uint32_t* nq = s_queue[buf ^ 1u];
+        uint32_t out = 0;
+        for (uint32_t base = 0; base < qlen; base += kTailThreads) {
+            const uint32_t q = base + tid;
+            uint32_t emit = SLA_DEV_NONE;
+            if (q < qlen) {
+                const uint32_t j = s_obj[q];
+                if (j != SLA_DEV_NONE) {
+                    const uint32_t i = sq[q];
+                    const double bid = s_bid[q];
+                    const bool won = (bid == bid) && (__ldcg(p.best + j) == pack_bid(bid, i, pbits));
+                    if (won) {
+                        const uint32_t prev = __ldcg(p.o2p + j);
+                        __stcg(p.prices + j, bid);
+                        __stcg(p.o2p + j, i);
+                        __stcg(p.p2o + i, j);
+                        atomicExch(p.best + j, 0ull);
+                        if (prev != SLA_DEV_NONE) { __stcg(p.p2o + prev, SLA_DEV_NONE); emit = prev; }
+                    } else {
+                        emit = i;
+                    }
+                }
+            }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
+            if (lane32 == 0) s_warp_cnt[warp] = __popc(ballot);
+            __syncthreads();
+            uint32_t off = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kTailThreads / 32; ++w) {
+                const uint32_t cnt = s_warp_cnt[w];
+                off += (w < warp) ? cnt : 0u;
+                total += cnt;
+            }
+            if (emit != SLA_DEV_NONE) nq[out + off + __popc(ballot & ((1u << lane32) - 1u))] = emit;
+            out += total;
+            __syncthreads();
+        }
+
+        bids_done += qlen;
+        rounds_done += 1;
+        qlen = out;
+        buf ^= 1u;
+        zero = false;
+        if (algo == ALGO_FORWARD) nits += 1;
+        if (qlen == 0) break;
+        if (algo == ALGO_FORWARD && nits >= max_it) { hit_limit = true; break; }   // symmetric.rs:326-328
+        if (safety <= 1) { hit_limit = true; break; }
+        safety -= 1;
+        if (rounds_done >= round_cap) break;   // hand control back; the next super-round continues
+    }
+
+    // ---- write the state back ----
+    if (my_arcs) atomicAdd(&s_arcs, my_arcs);
+    if (my_dropped) atomicAdd(&s_dropped, my_dropped);
+    for (uint32_t q = tid; q < qlen; q += kTailThreads) gqueue[q] = s_queue[buf][q];
+    __syncthreads();
+    if (tid == 0) {
+        st->rounds += rounds_done;
+        st->tail_rounds += rounds_done;
+        st->bids += bids_done;
+        atomicAdd(&st->bid_arcs, s_arcs);
+        st->dropped += s_dropped;
+        st->qlen[cur] = qlen;
+        st->identity = 0;
+        st->zero_prices = 0;
+        st->nits = nits;
+        st->safety_rounds_left = safety;
+        if (hit_limit) st->done = 1;
+        else if (qlen == 0) finish_if_possible(st);
+    }
+}
+
+// =============================================================================================================
+// Forward: eps-complementary-slackness check (reference src/solver.rs:154-189), then control step B in the
+// last block to finish (reference src/symmetric.rs:278-328): optimal / give up / start the next eps phase.
+// =============================================================================================================
+template <int LPR>
+__global__ void __launch_bounds__(kWideThreads) ecs_kernel(const Params p) {
+    DevState* st = p.st;
+    if (st->done || st->algo != ALGO_FORWARD || st->start_opt || st->qlen[st->cur] != 0) return;
+    const double eps = st->target_eps, tol = st->tol;
+    const uint32_t n_rows = st->n_rows, n_cols = st->n_cols, sign_flip = st->sign_flip;
+
+    constexpr int GROUPS_PER_BLOCK = kWideThreads / LPR;
+    const int lane = threadIdx.x % LPR;
+    const uint32_t group = blockIdx.x * GROUPS_PER_BLOCK + threadIdx.x / LPR;
+    const uint32_t ngroups = gridDim.x * GROUPS_PER_BLOCK;
+    bool violated = false;
+
+    for (uint32_t base = 0; base < n_rows; base += ngroups) {
+        const uint32_t i = base + group;
+        const bool valid = i < n_rows;
+        uint32_t a = 0, b = 0, j = 0;
+        if (valid) {
+            a = __ldg(p.row_ptr + i);
+            b = __ldg(p.row_ptr + i + 1);
+            j = p.p2o[i];
+        }
+        // pass 1: value of the LAST arc of the row that points at the chosen object (solver.rs:163-169)
+        uint32_t cpos = 0;   // position + 1, 0 = none
+        double cval = neg_inf();
+        for (uint32_t g = a + lane; g < b; g += LPR) {
+            if (__ldg(p.cols + g) == j) { cpos = g + 1u; cval = __ldg(p.vals + g); }
+        }
+#pragma unroll
+        for (int m = LPR / 2; m >= 1; m >>= 1) {
+            const uint32_t op = __shfl_xor_sync(0xffffffffu, cpos, m);
+            const double ov = __shfl_xor_sync(0xffffffffu, cval, m);
+            if (op > cpos) { cpos = op; cval = ov; }
+        }
+        if (valid) {
+            if (j >= n_cols) {
+                violated = true;   // unassigned person: cannot be a complete eps-CS solution
+            } else {
+                const double chosen = (cpos == 0u) ? neg_inf()
+                                                   : __hiloint2double(__double2hiint(cval) ^ (int)sign_flip, __double2loint(cval));
+                const double lhs = chosen - __ldg(p.prices + j) + tol;
+                // pass 2 (solver.rs:177-186)
+                for (uint32_t g = a + lane; g < b; g += LPR) {
+                    const double raw = __ldg(p.vals + g);
+                    const double v = __hiloint2double(__double2hiint(raw) ^ (int)sign_flip, __double2loint(raw));
+                    const double pk = __ldg(p.prices + __ldg(p.cols + g));
+                    if (lhs < v - pk - eps) violated = true;
+                }
+            }
+        }
+    }
+    if (violated) st->ecs_violated = 1;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t ticket = atomicAdd(&st->ecs_ticket, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            const uint32_t bad = *((volatile uint32_t*)&st->ecs_violated);
+            if (!bad) {
+                st->optimal = 1;
+                st->done = 1;
+            } else if (st->eps < st->target_eps) {
+                st->done = 1;                                   // symmetric.rs:291-294
+            } else {
+                st->eps *= 0.15;                                // REDUCTION_FACTOR, symmetric.rs:189, 296
+                st->nreductions += 1;
+                st->action = ACTION_RESET;
+                st->qlen[st->cur] = n_rows;
+                st->identity = 1;
+                if (st->nits >= st->max_iterations) st->done = 1;   // symmetric.rs:326-328 (after the reset)
+            }
+            st->ecs_violated = 0;
+            st->ecs_ticket = 0;
+        }
+    }
+}
+
+// Forward phase restart: wipe both assignment vectors, keep prices (reference src/symmetric.rs:299-321).
+__global__ void __launch_bounds__(kWideThreads) phase_apply_kernel(const Params p) {
+    if (p.st->action != ACTION_RESET) return;
+    const uint32_t n_rows = p.st->n_rows, n_cols = p.st->n_cols;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < n_rows; i += stride) p.p2o[i] = SLA_DEV_NONE;
+    for (uint32_t j = tid; j < n_cols; j += stride) p.o2p[j] = SLA_DEV_NONE;
+}
+
+// =============================================================================================================
+// Utility kernels
+// =============================================================================================================
+// init_solve (reference src/solver.rs:218-229): prices = 0, both assignment vectors = NONE.
+__global__ void __launch_bounds__(kWideThreads) init_solve_kernel(const Params p, const uint32_t n_rows, const uint32_t n_cols,
+                                                                  const int clear_best) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t j = tid; j < n_cols; j += stride) {
+        p.prices[j] = 0.0;
+        p.o2p[j] = SLA_DEV_NONE;
+        if (clear_best) p.best[j] = 0ull;
+    }
+    for (uint32_t i = tid; i < n_rows; i += stride) p.p2o[i] = SLA_DEV_NONE;
+}
+
+// Value range + structural validation of an uploaded CSR (ksparse.rs:171-179, symmetric.rs:246, solver.rs:241).
+__global__ void __launch_bounds__(kWideThreads) csr_stats_kernel(const uint32_t* __restrict__ row_ptr,
+                                                                 const uint32_t* __restrict__ cols,
+                                                                 const double* __restrict__ vals, const uint32_t n_rows,
+                                                                 const uint32_t n_cols, const unsigned long long nnz,
+                                                                 DevCsrStats* out) {
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long kmin = ~0ull, kmax = 0ull, bad_c = 0, bad_r = 0;
+    for (unsigned long long g = tid; g < nnz; g += stride) {
+        const unsigned long long k = f64_order_key(vals[g]);
+        kmin = k < kmin ? k : kmin;
+        kmax = k > kmax ? k : kmax;
+        bad_c += (cols[g] >= n_cols) ? 1u : 0u;
+    }
+    for (unsigned long long i = tid; i < n_rows; i += stride) {
+        const uint32_t a = row_ptr[i], b = row_ptr[i + 1];
+        bad_r += (b < a || (unsigned long long)b > nnz) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const unsigned long long omin = __shfl_xor_sync(0xffffffffu, kmin, m);
+        const unsigned long long omax = __shfl_xor_sync(0xffffffffu, kmax, m);
+        kmin = omin < kmin ? omin : kmin;
+        kmax = omax > kmax ? omax : kmax;
+        bad_c += __shfl_xor_sync(0xffffffffu, bad_c, m);
+        bad_r += __shfl_xor_sync(0xffffffffu, bad_r, m);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out->min_key, kmin);
+        atomicMax(&out->max_key, kmax);
+        if (bad_c) atomicAdd(&out->bad_cols, bad_c);
+        if (bad_r) atomicAdd(&out->bad_rows, bad_r);
+    }
+}
+
+// get_objective on the resident solution (reference src/solver.rs:110-142): per-block partial sums of the
+// effective values of the chosen arcs; the host adds the partials in block order (deterministic).
+__global__ void __launch_bounds__(kWideThreads) objective_kernel(const Params p, const uint32_t n_rows, const uint32_t sign_flip,
+                                                                 double* __restrict__ partial) {
+    double acc = 0.0;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < n_rows; i += stride) {
+        const uint32_t j = p.p2o[i];
+        if (j == SLA_DEV_NONE) continue;
+        const uint32_t a = p.row_ptr[i], b = p.row_ptr[i + 1];
+        for (uint32_t g = a; g < b; ++g) {
+            if (p.cols[g] == j) {
+                const double raw = p.vals[g];
+                acc += __hiloint2double(__double2hiint(raw) ^ (int)sign_flip, __double2loint(raw));
+            }
+        }
+    }
+    __shared__ double s_part[kWideThreads / 32];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kWideThreads / 32; ++w) t += s_part[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+// Stand-alone eps-CS check on the resident solution (reference src/solver.rs:154-189); out[0] |= violated.
+__global__ void __launch_bounds__(kWideThreads) ecs_check_kernel(const Params p, const uint32_t n_rows, const uint32_t n_cols,
+                                                                 const uint32_t sign_flip, const double eps, const double tol,
+                                                                 uint32_t* out) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    bool violated = false;
+    for (uint32_t i = tid; i < n_rows; i += stride) {
+        const uint32_t j = p.p2o[i];
+        if (j >= n_cols) { violated = true; continue; }
+        const uint32_t a = p.row_ptr[i], b = p.row_ptr[i + 1];
+        double chosen = neg_inf();
+        for (uint32_t g = a; g < b; ++g)
+            if (p.cols[g] == j) {
+                const double raw = p.vals[g];
+                chosen = __hiloint2double(__double2hiint(raw) ^ (int)sign_flip, __double2loint(raw));
+            }
+        const double lhs = chosen - p.prices[j] + tol;
+        for (uint32_t g = a; g < b; ++g) {
+            const double raw = p.vals[g];
+            const double v = __hiloint2double(__double2hiint(raw) ^ (int)sign_flip, __double2loint(raw));
+            if (lhs < v - p.prices[p.cols[g]] - eps) violated = true;
+        }
+    }
+    if (violated) out[0] = 1u;
+}
+
+// Matching validator: out[0] = unassigned persons, out[1] = inconsistencies between the two vectors.
+__global__ void __launch_bounds__(kWideThreads) validate_kernel(const Params p, const uint32_t n_rows, const uint32_t n_cols,
+                                                                uint32_t* out) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    uint32_t unassigned = 0, bad = 0;
+    for (uint32_t i = tid; i < n_rows; i += stride) {
+        const uint32_t j = p.p2o[i];
+        if (j == SLA_DEV_NONE) unassigned += 1;
+        else if (j >= n_cols || p.o2p[j] != i) bad += 1;
+    }
+    for (uint32_t j = tid; j < n_cols; j += stride) {
+        const uint32_t i = p.o2p[j];
+        if (i != SLA_DEV_NONE && (i >= n_rows || p.p2o[i] != j)) bad += 1;
+    }
+    if (unassigned) atomicAdd(out + 0, unassigned);
+    if (bad) atomicAdd(out + 1, bad);
+}
+
+// Synthetic instance generator (synth.h), one thread per row.
+__global__ void __launch_bounds__(kWideThreads) generate_kernel(const sla_synth::Spec spec, const uint32_t row_begin,
+                                                                const uint32_t row_count, uint32_t* __restrict__ row_ptr,
+                                                                uint32_t* __restrict__ cols, double* __restrict__ vals) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t r = tid; r < row_count; r += stride) {
+        const size_t off = (size_t)r * spec.k;
+        sla_synth::make_row(spec, row_begin + r, cols + off, vals + off);
+        row_ptr[r] = (uint32_t)off;
+    }
+    if (tid == 0) row_ptr[row_count] = row_count * spec.k;
+}
+
+}  // namespace sla

@@ -1,0 +1,340 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI (libsla_b200.so) via the
+host-side mirror of the reference API; the CPU oracle and the CPU model of the device algorithm are the checkers.
+
+Bars (BASELINE.json north_star): valid matching with the reference's num_unassigned; bit-exact objective for
+integer weights with eps < 1/n; within n * eps_final otherwise; and -- stronger, our own bar -- bit-exact equality
+of prices / assignment vectors / counters with the sequential CPU model of the Jacobi rounds.
+"""
+import numpy as np
+import pytest
+
+from helpers import (U32_MAX, check_matching, dense_csr, fixtures, goldens, objective_of, random_sparse_instance,
+                     scipy_optimum)
+
+pytestmark = pytest.mark.gpu
+
+SOLVERS = (("khosla", "KhoslaSolver"), ("forward", "ForwardAuctionSolver"))
+
+
+def gpu_solve(sla, cls_name, n, m, rp, c, v, maximize=False, eps=None, options=None, index_dtype=np.uint32, **kw):
+    solver, z = getattr(sla, cls_name).new(n, m, len(c), index_dtype=index_dtype)
+    solver.load_csr(n, m, rp, c, v)
+    for k_, v_ in (options or {}).items():
+        solver.set_option(k_, v_)
+    if kw:
+        solver.solve_with_params(z, maximize, eps, kw.get("start_eps"), kw.get("max_iterations"))
+    else:
+        solver.solve(z, maximize, eps)
+    return solver, z
+
+
+def assert_equals_model(O, kind, solver, z, n, m, rp, c, v, maximize=False, eps=None, **kw):
+    r = O.jacobi_model(kind, n, m, rp, c, v, maximize=maximize, eps=eps, **kw)
+    st = solver.last_stats
+    assert np.array_equal(z.person_to_object.astype(np.uint32), r["p2o"]), "person_to_object differs from the model"
+    assert np.array_equal(z.object_to_person.astype(np.uint32), r["o2p"]), "object_to_person differs from the model"
+    assert np.array_equal(solver.prices(), r["prices"]), "prices differ from the model (bit-exact f64)"
+    for key in ("num_unassigned", "nits", "nreductions", "optimal_soln_found", "rounds", "bids", "bid_arcs", "dropped",
+                "values_negated"):
+        assert st[key] == r["stats"][key], f"{key}: gpu {st[key]} != model {r['stats'][key]}"
+    assert st["eps"] == r["stats"]["eps"]
+    return r
+
+
+# ---- the reference's own test-suite, instantiated for both solvers (src/solver.rs:246-445) ------------------------
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_random_solve_small(sla, oracle, kind, cls_name):
+    g = goldens()["random_solve_small"]
+    fx = fixtures()
+    rp, c, v = fx["small_row_ptr"], fx["small_cols"], fx["small_vals"]
+    solver, z = getattr(sla, cls_name).new(5, 5, 10)
+    for maximize, key in ((False, "minimize"), (True, "maximize")):
+        solver.load_csr(5, 5, rp, c, v)                       # the reference re-populates before each solve
+        solver.solve(z, maximize, None)
+        assert solver.get_objective(z) == g[key]              # assert_eq! on f64
+        assert z.num_unassigned == 0
+        assert_equals_model(oracle, kind, solver, z, 5, 5, rp, c, v, maximize=maximize)
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_random_no_perfect_matching(sla, oracle, kind, cls_name):
+    g = goldens()["random_no_perfect_matching"]
+    fx = fixtures()
+    rp, c, v = fx["no_perfect_row_ptr"], fx["no_perfect_cols"], fx["no_perfect_vals"]
+    solver, z = gpu_solve(sla, cls_name, 9, 9, rp, c, v)
+    assert z.num_unassigned == 1
+    assert solver.get_objective(z) in g["accepted_objectives"]
+    check_matching(9, 9, rp, c, z.person_to_object, z.object_to_person, z.num_unassigned)
+    assert_equals_model(oracle, kind, solver, z, 9, 9, rp, c, v)
+    if kind == "forward":
+        assert solver.nits == 100000 and not solver.optimal_soln_found      # runs into MAX_ITERATIONS like the reference
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_random_large(sla, oracle, kind, cls_name):
+    g = goldens()["random_large"]
+    fx = fixtures()
+    rp, c, v = fx["large_row_ptr"], fx["large_cols"], fx["large_vals"]
+    solver, z = gpu_solve(sla, cls_name, 90, 900, rp, c, v)
+    assert solver.get_objective(z) == g["minimize"]
+    assert z.num_unassigned == 0
+    assert_equals_model(oracle, kind, solver, z, 90, 900, rp, c, v)
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_fixed_cases_reusing_one_solver(sla, oracle, kind, cls_name):
+    solver, z = getattr(sla, cls_name).new(10, 10, 100)
+    for case in goldens()["fixed_cases"]["cases"]:
+        n, m, rp, c, v = dense_csr(case["costs"])
+        solver.init(n, m)
+        for i in range(n):
+            solver.extend_from_values(i, np.arange(m, dtype=np.uint32), np.asarray(case["costs"][i], dtype=np.float64))
+        solver.solve(z, False, None)
+        assert z.num_unassigned == 0
+        assert solver.get_objective(z) == case["objective"]
+        check_matching(n, m, rp, c, z.person_to_object, z.object_to_person, 0)
+        assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v)
+        if kind == "forward":      # same Jacobi order as the reference and no ties: the exact vectors of solver.rs:361-386
+            assert list(z.person_to_object) == case["person_to_object"]
+            assert list(z.object_to_person) == case["object_to_person"]
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_doctest_ragged(sla, oracle, kind, cls_name):
+    g = goldens()["doctest"]
+    solver, z = getattr(sla, cls_name).new(10, 10, 100)
+    solver.init(2, 4)
+    for i, row in enumerate(g["rows"]):
+        solver.extend_from_values(i, np.arange(len(row), dtype=np.uint32), np.asarray(row, dtype=np.float64))
+    solver.solve(z, False, None)
+    assert z.num_unassigned == 0
+    assert solver.get_objective(z) == g["objective"]
+    assert list(z.person_to_object) == g["person_to_object"]
+    assert list(z.object_to_person) == g["object_to_person"]
+
+
+# ---- seeded instances: GPU == model bit for bit, and objective parity with the reference oracle ------------------
+def ragged_instance(rng, n, m, kmin, kmax, integer):
+    """Rows of different lengths (unaligned row starts exercise the masked 128-bit chunk loads)."""
+    counts = rng.integers(kmin, kmax + 1, size=n)
+    rp = np.zeros(n + 1, dtype=np.uint32)
+    rp[1:] = np.cumsum(counts)
+    cols = np.empty(rp[-1], dtype=np.uint32)
+    perm = rng.permutation(m)[:n]
+    for i in range(n):
+        k = int(counts[i])
+        others = rng.choice(m - 1, size=k - 1, replace=False)
+        others = others + (others >= perm[i])
+        cols[rp[i]:rp[i + 1]] = np.sort(np.concatenate([[perm[i]], others]))
+    vals = rng.integers(0, 1000, size=rp[-1]).astype(np.float64) if integer else rng.uniform(0, 10, size=rp[-1])
+    return rp, cols, vals
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+@pytest.mark.parametrize("seed", range(8))
+def test_seeded_instances_match_model_and_oracle(sla, oracle, kind, cls_name, seed):
+    rng = np.random.default_rng(1000 + seed)
+    integer = seed % 2 == 0
+    n = int(rng.integers(20, 400))
+    m = n if (kind == "forward" and seed % 4 < 2) else n + int(rng.integers(0, 200))
+    kmax = int(rng.integers(3, 40))
+    rp, c, v = ragged_instance(rng, n, m, 1 if seed == 3 else 2, min(kmax, m), integer)
+    maximize = seed % 3 == 0
+    eps = 1.0 / (m + 1) if integer else None
+    solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v, maximize=maximize, eps=eps)
+    assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v, maximize=maximize, eps=eps)
+    check_matching(n, m, rp, c, z.person_to_object, z.object_to_person, z.num_unassigned)
+    o = oracle.OracleSolver(kind, n, m, len(c))
+    o.load_csr(n, m, rp, c, v)
+    o.solve(maximize=maximize, eps=eps)
+    if seed == 3 and kind == "forward":
+        return   # single-arc rows make Forward bid +inf (symmetric.rs:378): both sides only need to stay valid
+    assert z.num_unassigned == o.num_unassigned
+    if z.num_unassigned == 0:
+        got, ref = solver.get_objective(z), o.get_objective()
+        if integer:
+            assert got == ref                                  # bit-exact: integer weights, eps < 1/n
+            assert objective_of(rp, c, v, z.person_to_object) == scipy_optimum(n, m, rp, c, v, maximize)
+        else:
+            assert abs(got - ref) <= n * max(z.eps, o.eps) + 1e-9      # tolerance n * eps_final (north_star)
+    assert np.array_equal(solver.values(), o.values)           # in-place sign normalisation is observable
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_engine_options_do_not_change_results(sla, oracle, kind, cls_name):
+    """Wide kernels only / tail engine only / host loop / CUDA graph / gather skipped or not: identical bits."""
+    rng = np.random.default_rng(7)
+    n, m, k = 3000, (3000 if kind == "forward" else 5000), 12
+    rp, c, v = random_sparse_instance(rng, n, m, k, integer=True, lo=0, hi=200)
+    ref = oracle.jacobi_model(kind, n, m, rp, c, v, eps=1.0 / (m + 1))
+    combos = [
+        dict(graph=1, tail_max=1024, zero_price_skip=1),
+        dict(graph=0, tail_max=1024, zero_price_skip=1),
+        dict(graph=1, tail_max=0, zero_price_skip=0),
+        dict(graph=0, tail_max=0, zero_price_skip=1, profile=1),
+        dict(graph=1, tail_max=2048, zero_price_skip=0, super_rounds=2),
+        dict(graph=1, tail_max=64, zero_price_skip=1, super_rounds=16),
+    ]
+    for opt in combos:
+        solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v, eps=1.0 / (m + 1), options=opt)
+        assert np.array_equal(z.person_to_object, ref["p2o"]), opt
+        assert np.array_equal(z.object_to_person, ref["o2p"]), opt
+        assert np.array_equal(solver.prices(), ref["prices"]), opt
+        for key in ("num_unassigned", "nits", "nreductions", "rounds", "bids", "bid_arcs"):
+            assert solver.last_stats[key] == ref["stats"][key], (opt, key)
+        if opt.get("profile"):
+            prof = solver.round_profile()
+            assert prof and prof[0]["bidders"] == n and prof[0]["arcs"] == n * k
+            assert sum(p["arcs"] for p in prof) == ref["stats"]["bid_arcs"]
+        if opt["tail_max"] == 0:
+            assert solver.last_stats["tail_rounds"] == 0
+        if opt["tail_max"] == 2048 and n <= 2048:
+            assert solver.last_stats["wide_rounds"] == 0
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_u16_index_type(sla, oracle, kind, cls_name):
+    rng = np.random.default_rng(3)
+    n, m, k = 300, 300 if kind == "forward" else 400, 6
+    rp, c, v = random_sparse_instance(rng, n, m, k, integer=True)
+    solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v, eps=1.0 / (m + 1), index_dtype=np.uint16)
+    assert z.person_to_object.dtype == np.uint16 and z.object_to_person.dtype == np.uint16
+    r = oracle.jacobi_model(kind, n, m, rp, c, v, eps=1.0 / (m + 1))
+    assert np.array_equal(z.person_to_object, r["p2o"].astype(np.uint16))    # u32::MAX truncates to u16::MAX
+    assert np.array_equal(z.object_to_person, r["o2p"].astype(np.uint16))
+    if m > n:
+        assert np.any(z.object_to_person == 0xFFFF)
+
+
+def test_sign_handling_across_repeated_solves(sla, oracle):
+    """solver.rs:207-216 is stateful: values are negated in place and the next solve sees the negated values."""
+    rng = np.random.default_rng(11)
+    n, m, k = 200, 300, 8
+    rp, c, v = random_sparse_instance(rng, n, m, k, integer=True, lo=1, hi=500)
+    solver, z = sla.KhoslaSolver.new(n, m, n * k)
+    solver.load_csr(n, m, rp, c, v)
+    o = oracle.OracleSolver("khosla", n, m, n * k)
+    o.load_csr(n, m, rp, c, v)
+    for maximize in (False, False, True, False, True, True):
+        solver.solve(z, maximize, 1.0 / (m + 1))
+        o.solve(maximize=maximize, eps=1.0 / (m + 1))
+        assert np.array_equal(solver.values(), o.values)
+        assert solver.get_objective(z) == o.get_objective()
+        assert z.num_unassigned == o.num_unassigned == 0
+        assert solver.device_objective() == o.get_objective()      # device-side sum, exact on integer weights
+        un, ok = solver.device_validate_matching()
+        assert (un, ok) == (0, True)
+
+
+def test_forward_params_and_eps_scaling(sla, oracle):
+    """solve_with_params (symmetric.rs:217-332): start_eps, max_iterations, nreductions, optimal_soln_found, eps."""
+    rng = np.random.default_rng(5)
+    n, k = 500, 10
+    rp, c, v = random_sparse_instance(rng, n, n, k, integer=True, lo=0, hi=1000)
+    for kw in (dict(), dict(start_eps=50.0), dict(start_eps=1e-4), dict(max_iterations=7), dict(max_iterations=1),
+               dict(start_eps=5.0, max_iterations=100)):
+        solver, z = gpu_solve(sla, "ForwardAuctionSolver", n, n, rp, c, v, eps=1.0 / (n + 1), **(kw or {"start_eps": None}))
+        o = oracle.OracleSolver("forward", n, n, n * k)
+        o.load_csr(n, n, rp, c, v)
+        o.solve(eps=1.0 / (n + 1), **kw)
+        r = assert_equals_model(oracle, "forward", solver, z, n, n, rp, c, v, eps=1.0 / (n + 1), **kw)
+        assert solver.optimal_soln_found == o.optimal_soln_found, kw
+        assert z.num_unassigned == o.num_unassigned, kw
+        if o.optimal_soln_found:
+            assert solver.get_objective(z) == o.get_objective()
+            assert solver.nreductions == o.nreductions and z.eps == o.eps
+            tol = solver.get_toleration(float(np.max(np.abs(v))))
+            assert solver.ecs_satisfied(z.person_to_object, 1.0 / (n + 1), tol)
+            assert solver.device_ecs_satisfied(1.0 / (n + 1), tol)
+        del r
+
+
+def test_invalid_inputs_fail_loudly(sla):
+    solver, z = sla.KhoslaSolver.new(4, 4, 16)
+    solver.init(2, 3)
+    solver.extend_from_values(0, [0, 7], [1.0, 2.0])          # column 7 >= num_cols (reference: debug_assert only)
+    solver.extend_from_values(1, [1], [1.0])
+    with pytest.raises(sla.SlaError) as e:
+        solver.solve(z, False, None)
+    assert e.value.code == 1 and "column" in e.value.message
+    with pytest.raises(sla.SlaError):
+        solver.set_option("no_such_option", 1)
+    with pytest.raises(sla.SlaError):
+        solver.set_option("tail_max", 4096)
+
+
+# ---- BASELINE.json configurations -----------------------------------------------------------------------------------
+def test_cfg1_khosla_1000x10000_k32(sla, oracle):
+    from sparse_linear_assignment_b200 import generators as G
+    n, m, k, _ = G.CONFIGS["cfg1"]
+    rp, c, v = G.kregular_host(n, m, k, seed=1)
+    solver, z = gpu_solve(sla, "KhoslaSolver", n, m, rp, c, v)                 # (1a) integer costs, eps=None
+    o = oracle.OracleSolver("khosla", n, m, n * k)
+    o.load_csr(n, m, rp, c, v)
+    o.solve()
+    assert z.num_unassigned == o.num_unassigned == 0
+    assert solver.get_objective(z) == o.get_objective()                        # eps = 1/M < 1/N: exact regime
+    assert_equals_model(oracle, "khosla", solver, z, n, m, rp, c, v)
+    rng = np.random.default_rng(1)
+    vf = rng.uniform(0, 10, size=n * k)                                       # (1b) non-integer weights
+    solver, z = gpu_solve(sla, "KhoslaSolver", n, m, rp, c, vf)
+    o.load_csr(n, m, rp, c, vf)
+    o.solve()
+    assert z.num_unassigned == o.num_unassigned == 0
+    assert abs(solver.get_objective(z) - o.get_objective()) <= n * z.eps      # n * eps_final
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_device_generator_equals_host_generator(sla, oracle, kind, cls_name):
+    from sparse_linear_assignment_b200 import generators as G
+    n, m, k = 2048, (2048 if kind == "forward" else 6000), 16
+    planted = kind == "forward"
+    rp, c, v = G.kregular_host(n, m, k, seed=5, planted=planted)
+    assert np.all(np.diff(c.reshape(n, k), axis=1) > 0) and c.max() < m and v.min() >= 300 and v.max() < 1000
+    host, zh = gpu_solve(sla, cls_name, n, m, rp, c, v, eps=1.0 / (m + 1))
+    dev, zd = getattr(sla, cls_name).new(n, m, n * k)
+    G.kregular_device(dev, n, m, k, seed=5, planted=planted)
+    dev.solve(zd, False, 1.0 / (m + 1))
+    assert np.array_equal(zh.person_to_object, zd.person_to_object)
+    assert np.array_equal(host.prices(), dev.prices())
+    assert host.last_stats["bid_arcs"] == dev.last_stats["bid_arcs"]
+    assert zd.num_unassigned == 0
+    assert dev.device_objective() == host.get_objective(zh)
+
+
+def test_cfg2_forward_20000x20000_k64(sla, oracle):
+    from sparse_linear_assignment_b200 import generators as G
+    n, m, k, planted = G.CONFIGS["cfg2"]
+    rp, c, v = G.kregular_host(n, m, k, seed=1, planted=planted)
+    eps = 1.0 / (n + 1)                                                        # strict < 1/n: bit-exact parity run
+    solver, z = gpu_solve(sla, "ForwardAuctionSolver", n, m, rp, c, v, eps=eps)
+    o = oracle.OracleSolver("forward", n, m, n * k)
+    o.load_csr(n, m, rp, c, v)
+    o.solve(eps=eps)
+    assert z.num_unassigned == o.num_unassigned == 0
+    assert solver.optimal_soln_found and o.optimal_soln_found
+    assert solver.get_objective(z) == o.get_objective()
+    check_matching(n, m, rp, c, z.person_to_object, z.object_to_person, 0)
+    assert_equals_model(oracle, "forward", solver, z, n, m, rp, c, v, eps=eps)
+
+
+def test_cfg3_khosla_1Mx4M_k16(sla, oracle):
+    from sparse_linear_assignment_b200 import generators as G
+    n, m, k, _ = G.CONFIGS["cfg3"]
+    rp, c, v = G.kregular_host(n, m, k, seed=1)
+    solver, z = gpu_solve(sla, "KhoslaSolver", n, m, rp, c, v)                 # eps=None -> 1/M < 1/N
+    o = oracle.OracleSolver("khosla", n, m, n * k)
+    o.load_csr(n, m, rp, c, v)
+    o.solve()
+    assert z.num_unassigned == o.num_unassigned == 0
+    assert solver.get_objective(z) == o.get_objective()
+    check_matching(n, m, rp, c, z.person_to_object, z.object_to_person, 0)
+    assert solver.device_objective() == o.get_objective()
+    assert solver.device_validate_matching() == (0, True)
+    assert_equals_model(oracle, "khosla", solver, z, n, m, rp, c, v)
+    # the same instance generated in HBM, solved without any host copy
+    dev, zd = sla.KhoslaSolver.new(n, m, n * k)
+    G.kregular_device(dev, n, m, k, seed=1)
+    st = dev.solve_resident(False, None)
+    assert st["bid_arcs"] == solver.last_stats["bid_arcs"] and st["num_unassigned"] == 0
+    assert dev.device_objective() == o.get_objective()

@@ -1,0 +1,139 @@
+"""CPU-only: the host-side mirror of the reference API (CSR builder, validation, objective, eps-CS, clone) and the
+C-ABI library's exported symbols.  No compute call is made here (there is no GPU in this container)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import fixtures, goldens
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(sla):
+    from sparse_linear_assignment_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "sla.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(sla_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/sla.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes signatures out of sync with include/sla.h"
+    lib.sla_version.restype = C.c_char_p
+    assert b"sm_100a" in lib.sla_version()
+
+
+def test_no_gpu_means_loud_failure(sla):
+    """Without a device the product path must fail, never fall back to a CPU solve."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    solver, solution = sla.KhoslaSolver.new(4, 4, 16)
+    solver.init(2, 2)
+    solver.extend_from_values(0, [0, 1], [1.0, 2.0])
+    solver.extend_from_values(1, [0, 1], [3.0, 1.0])
+    with pytest.raises(sla.SlaError) as e:
+        solver.solve(solution, False, None)
+    assert e.value.code == 3   # SLA_ERR_NO_DEVICE
+
+
+@pytest.mark.parametrize("cls_name", ["KhoslaSolver", "ForwardAuctionSolver"])
+def test_cumulative_idx_diff_u16(sla, cls_name):
+    g = goldens()["cumulative_idx_diff"]                      # src/symmetric.rs:525-534
+    solver, _ = getattr(sla, cls_name).new(7, 7, 7, index_dtype=np.uint16)
+    solver.init(7, 7)
+    for r in g["rows"]:
+        solver.add_value(r, 0, 0.0)
+    assert list(solver.i_starts_stops()) == g["i_starts_stops"]
+    assert list(solver.j_counts()) == g["j_counts"]
+    assert solver.i_starts_stops().dtype == np.uint16
+    assert solver.num_of_arcs() == 7
+
+
+def test_builder_matches_oracle_builder(sla, oracle):
+    fx = fixtures()
+    rp, c, v = fx["large_row_ptr"], fx["large_cols"], fx["large_vals"]
+    solver, _ = sla.ForwardAuctionSolver.new(90, 900, 90 * 32)
+    solver.init(90, 900)
+    o = oracle.OracleSolver("forward", 90, 900, 90 * 32)
+    o.init(90, 900)
+    for i in range(90):
+        a, b = rp[i], rp[i + 1]
+        if i % 2:
+            solver.extend_from_values(i, c[a:b], v[a:b])
+        else:
+            for g in range(a, b):
+                solver.add_value(i, c[g], v[g])
+        o.extend_from_values(i, c[a:b], v[a:b])
+    assert np.array_equal(solver.i_starts_stops(), o.i_starts_stops)
+    assert np.array_equal(solver.j_counts(), o.j_counts)
+    assert np.array_equal(solver.column_indices(), c)
+    assert np.array_equal(solver.values(), v)
+    bulk, _ = sla.KhoslaSolver.new(1, 1, 1)
+    bulk.load_csr(90, 900, rp, c, v)
+    assert np.array_equal(bulk.i_starts_stops(), solver.i_starts_stops())
+    assert np.array_equal(bulk.j_counts(), solver.j_counts())
+
+
+def test_builder_errors(sla):
+    solver, _ = sla.KhoslaSolver.new(4, 4, 16)
+    with pytest.raises(sla.SlaError):
+        solver.init(5, 4)                                     # solver.rs:192
+    solver.init(2, 4)
+    with pytest.raises(sla.SlaError):
+        solver.add_value(1, 0, 1.0)                           # solver.rs:55
+    solver.add_value(0, 0, 1.0)
+    with pytest.raises(sla.SlaError):
+        solver.add_value(2, 0, 1.0)                           # solver.rs:44
+    with pytest.raises(sla.SlaError):
+        solver.extend_from_values(0, [1, 2], [1.0])           # solver.rs:75
+    s16, _ = sla.KhoslaSolver.new(4, 4, 16, index_dtype=np.uint16)
+    with pytest.raises(sla.SlaError):
+        s16.init(0xFFFF, 0xFFFF)                              # solver.rs:193
+    s16.init(2, 70000)
+    with pytest.raises(sla.SlaError):
+        s16.extend_from_values(0, np.zeros(70000), np.zeros(70000))   # I::from_usize, solver.rs:80-81
+    empty, sol = sla.ForwardAuctionSolver.new(4, 4, 16)
+    empty.init(2, 2)
+    with pytest.raises(sla.SlaError):
+        empty.solve(sol, False, None)                         # validate_input before any device work, solver.rs:234
+
+
+def test_solution_new_and_clone(sla):
+    _, z = sla.KhoslaSolver.new(3, 5, 9)
+    assert z.person_to_object.size == 0 and z.object_to_person.size == 0    # solution.rs:46-53
+    assert np.isnan(z.eps) and z.num_unassigned == 0xFFFFFFFF
+    _, z16 = sla.KhoslaSolver.new(3, 5, 9, index_dtype=np.uint16)
+    assert z16.num_unassigned == 0xFFFF
+    solver, _ = sla.ForwardAuctionSolver.new(2, 2, 4)
+    solver.init(2, 2)
+    solver.extend_from_values(0, [0, 1], [1.0, 2.0])
+    twin = solver.clone()
+    twin.extend_from_values(1, [0], [5.0])
+    assert solver.num_of_arcs() == 2 and twin.num_of_arcs() == 3
+
+
+def test_get_objective_ecs_and_toleration_match_oracle(sla, oracle):
+    """Host post-processing (solver.rs:110-189) against the oracle's, on a solved oracle state."""
+    fx = fixtures()
+    rp, c, v = fx["large_row_ptr"], fx["large_cols"], fx["large_vals"]
+    o = oracle.OracleSolver("forward", 90, 900, 90 * 32)
+    o.load_csr(90, 900, rp, c, v)
+    o.solve(maximize=False)
+    solver, z = sla.ForwardAuctionSolver.new(90, 900, 90 * 32)
+    solver.load_csr(90, 900, rp, c, v)
+    solver.init_solve(z, False)                               # host-side sign normalisation, solver.rs:207-230
+    assert np.array_equal(solver.values(), o.values)
+    assert z.num_unassigned == 90 and np.all(z.person_to_object == 0xFFFFFFFF)
+    z.person_to_object = o.person_to_object
+    solver.prices_mut()[:] = o.prices
+    assert solver.get_objective(z) == o.get_objective() == goldens()["random_large"]["minimize"]
+    tol = solver.get_toleration(10.0)
+    assert tol == oracle.get_toleration(10.0)
+    for eps in (1.0 / 90, 1e-9, 0.0):
+        assert solver.ecs_satisfied(z.person_to_object, eps, tol) == o.ecs_satisfied(eps, tol)
+    for cost in (0.0, 0.5, 1.0, 999.0, 1000.0, 1e6):
+        assert solver.get_toleration(cost) == oracle.get_toleration(cost)
