@@ -239,8 +239,8 @@ def test_forward_params_and_eps_scaling(sla, oracle):
         o.solve(eps=1.0 / (n + 1), **kw)
         r = assert_equals_model(oracle, "forward", solver, z, n, n, rp, c, v, eps=1.0 / (n + 1), **kw)
         assert solver.optimal_soln_found == o.optimal_soln_found, kw
-        assert z.num_unassigned == o.num_unassigned, kw
-        if o.optimal_soln_found:
+        if o.optimal_soln_found:      # a solve cut short by max_iterations stops mid-auction: only the model is comparable
+            assert z.num_unassigned == o.num_unassigned == 0, kw
             assert solver.get_objective(z) == o.get_objective()
             assert solver.nreductions == o.nreductions and z.eps == o.eps
             tol = solver.get_toleration(float(np.max(np.abs(v))))
