@@ -34,6 +34,8 @@ if __name__ == "__main__":
         s = run("cfg3 khosla", S.KhoslaSolver, 1_000_000, 4_000_000, 16, False)
         run("cfg3 khosla", S.KhoslaSolver, 1_000_000, 4_000_000, 16, False, options=dict(zero_price_skip=0))
         run("cfg3 khosla", S.KhoslaSolver, 1_000_000, 4_000_000, 16, False, options=dict(graph=0))
+        run("cfg3 khosla", S.KhoslaSolver, 1_000_000, 4_000_000, 16, False, options=dict(regular=0))
+        run("cfg3 khosla", S.KhoslaSolver, 1_000_000, 4_000_000, 16, False, options=dict(tail_max=2048))
         for skip in (1, 0):
             s.set_option("profile", 1)
             s.set_option("zero_price_skip", skip)

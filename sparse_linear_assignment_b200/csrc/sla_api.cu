@@ -23,6 +23,7 @@ struct GraphSlot {
     uint64_t generation = 0;
     int lpr = 0;
     int super_rounds = 0;
+    uint32_t regular_k = 0;
 };
 
 }  // namespace
@@ -68,12 +69,15 @@ struct sla_ctx {
     double v_min = 0, v_max = 0, first_value = 0;
     int dev_sign = 1;   // effective values = dev_sign * uploaded values (in-place negation of solver.rs:214-216)
     int lpr = 4;
+    uint32_t regular_k = 0;   // all rows have this many arcs (multiple of 8): the regular bid kernel is used
+    int lpr8 = 1;
+    int opt_regular = 1;
 
     // options
     int opt_graph = 1, opt_tail_max = 1024, opt_skip_zero = 1, opt_profile = 0, opt_super_rounds = 6;
     double opt_timeout_s = 900.0;   // wall-clock guard of one solve ("timeout_s" option / SLA_TIMEOUT_S)
     uint64_t generation = 1;   // bumped whenever a device buffer is reallocated
-    GraphSlot graphs[2];
+    GraphSlot graphs[4];   // [forward * 2 + first-launch-of-a-solve]
     int grid_wide = 0;
 
     std::vector<sla_round_profile> profile;
@@ -175,54 +179,68 @@ int pick_lpr(uint64_t nnz, uint32_t n_rows) {
 }
 
 // ---- kernel dispatch on lanes-per-row -----------------------------------------------------------------
-template <int LPR>
-void launch_super_round_t(sla_ctx* c, const Params& p, bool forward) {
-    bid_wide_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
-    assign_wide_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
-    tail_kernel<LPR><<<1, kTailThreads, 0, c->stream>>>(p);
-    if (forward) {
-        ecs_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
-        phase_apply_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
+template <int MODE>
+void launch_bid_regular_m(sla_ctx* c, const Params& p) {
+    switch (c->lpr8) {
+        case 1: bid_regular_kernel<1, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 2: bid_regular_kernel<2, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 4: bid_regular_kernel<4, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 8: bid_regular_kernel<8, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 16: bid_regular_kernel<16, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        default: bid_regular_kernel<32, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
     }
 }
 
-void launch_super_round(sla_ctx* c, const Params& p, bool forward) {
-    switch (c->lpr) {
-        case 1: launch_super_round_t<1>(c, p, forward); break;
-        case 2: launch_super_round_t<2>(c, p, forward); break;
-        case 4: launch_super_round_t<4>(c, p, forward); break;
-        case 8: launch_super_round_t<8>(c, p, forward); break;
-        case 16: launch_super_round_t<16>(c, p, forward); break;
-        default: launch_super_round_t<32>(c, p, forward); break;
-    }
-}
+bool use_regular(const sla_ctx* c) { return c->regular_k != 0 && c->opt_regular; }
 
+// which: 0 bid, 1 assign, 2 tail, 3 ecs, 4 phase_apply.  zero_first: this bid launch is the first round of a
+// solve and all prices are known to be exactly 0 (only meaningful for the regular bid kernel; the generic one
+// reads the flag from the device state).
 template <int LPR>
-void launch_one_t(sla_ctx* c, const Params& p, int which) {
+void launch_one_t(sla_ctx* c, const Params& p, int which, bool zero_first) {
     switch (which) {
-        case 0: bid_wide_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 0:
+            if (use_regular(c)) {
+                if (zero_first) launch_bid_regular_m<PRICE_ZERO>(c, p);
+                else launch_bid_regular_m<PRICE_LDG>(c, p);
+            } else {
+                bid_wide_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
+            }
+            break;
         case 1: assign_wide_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
         case 2: tail_kernel<LPR><<<1, kTailThreads, 0, c->stream>>>(p); break;
         case 3: ecs_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
         default: phase_apply_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
     }
 }
-void launch_one(sla_ctx* c, const Params& p, int which) {
+void launch_one(sla_ctx* c, const Params& p, int which, bool zero_first = false) {
     switch (c->lpr) {
-        case 1: launch_one_t<1>(c, p, which); break;
-        case 2: launch_one_t<2>(c, p, which); break;
-        case 4: launch_one_t<4>(c, p, which); break;
-        case 8: launch_one_t<8>(c, p, which); break;
-        case 16: launch_one_t<16>(c, p, which); break;
-        default: launch_one_t<32>(c, p, which); break;
+        case 1: launch_one_t<1>(c, p, which, zero_first); break;
+        case 2: launch_one_t<2>(c, p, which, zero_first); break;
+        case 4: launch_one_t<4>(c, p, which, zero_first); break;
+        case 8: launch_one_t<8>(c, p, which, zero_first); break;
+        case 16: launch_one_t<16>(c, p, which, zero_first); break;
+        default: launch_one_t<32>(c, p, which, zero_first); break;
+    }
+}
+
+void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_first) {
+    launch_one(c, p, 0, zero_first);
+    launch_one(c, p, 1);
+    launch_one(c, p, 2);
+    if (forward) {
+        launch_one(c, p, 3);
+        launch_one(c, p, 4);
     }
 }
 
 int kernels_per_super_round(bool forward) { return forward ? 5 : 3; }
 
-int get_graph(sla_ctx* ctx, bool forward, cudaGraphExec_t* out) {
-    GraphSlot& g = ctx->graphs[forward ? 1 : 0];
-    if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == ctx->opt_super_rounds) {
+int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out) {
+    GraphSlot& g = ctx->graphs[(forward ? 2 : 0) + (zero_first ? 1 : 0)];
+    const uint32_t reg_key = use_regular(ctx) ? ctx->regular_k : 0u;
+    if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == ctx->opt_super_rounds &&
+        g.regular_k == reg_key) {
         *out = g.exec;
         return SLA_OK;
     }
@@ -230,7 +248,7 @@ int get_graph(sla_ctx* ctx, bool forward, cudaGraphExec_t* out) {
     const Params p = make_params(ctx);
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    for (int r = 0; r < ctx->opt_super_rounds; ++r) launch_super_round(ctx, p, forward);
+    for (int r = 0; r < ctx->opt_super_rounds; ++r) launch_super_round(ctx, p, forward, zero_first && r == 0);
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (e != cudaSuccess) return fail(ctx, SLA_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
     e = cudaGraphInstantiate(&g.exec, graph, 0);
@@ -242,6 +260,7 @@ int get_graph(sla_ctx* ctx, bool forward, cudaGraphExec_t* out) {
     g.generation = ctx->generation;
     g.lpr = ctx->lpr;
     g.super_rounds = ctx->opt_super_rounds;
+    g.regular_k = reg_key;
     *out = g.exec;
     return SLA_OK;
 }
@@ -302,6 +321,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
     s.n_cols = M;
     s.safety_rounds_left = 1ull << 40;
     s.tail_round_cap = 1u << 19;
+    s.regular_k = use_regular(ctx) ? ctx->regular_k : 0u;
     if (!forward) {
         // reference src/ksparse.rs:160-181
         const double m = (double)M;
@@ -344,10 +364,17 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > ctx->opt_timeout_s;
     };
     if (use_graph) {
-        cudaGraphExec_t exec = nullptr;
-        int rc = get_graph(ctx, forward, &exec);
+        cudaGraphExec_t exec_first = nullptr, exec_next = nullptr;
+        int rc = get_graph(ctx, forward, ctx->opt_skip_zero != 0, &exec_first);
         if (rc) return rc;
+        bool first = true;
         while (!done) {
+            cudaGraphExec_t exec = exec_first;
+            if (!first) {
+                if (!exec_next && (rc = get_graph(ctx, forward, false, &exec_next))) return rc;
+                exec = exec_next;
+            }
+            first = false;
             CU(cudaGraphLaunch(exec, ctx->stream));
             graph_launches += 1;
             launches += (uint32_t)(ctx->opt_super_rounds * kernels_per_super_round(forward));
@@ -359,10 +386,12 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
         // Host-driven loop: one super-round per iteration, state polled after each.  With "profile" the wide
         // kernels and the tail engine are bracketed by CUDA events on the solve stream.
         DevState prev = s;
+        bool first = true;
         while (!done) {
             const bool wide = !prev.done && prev.qlen[prev.cur] > prev.tail_max;
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-            launch_one(ctx, p, 0);
+            launch_one(ctx, p, 0, first && ctx->opt_skip_zero != 0);
+            first = false;
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
             launch_one(ctx, p, 1);
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -458,7 +487,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
 // After the three CSR arrays are resident: statistics + validation (solver.rs:232-243).
 int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz) {
     DevCsrStats init;
-    init.min_key = ~0ull; init.max_key = 0ull; init.bad_cols = 0; init.bad_rows = 0;
+    init.min_key = ~0ull; init.max_key = 0ull; init.bad_cols = 0; init.bad_rows = 0; init.irregular_rows = 0;
     *ctx->h_csr_stats = init;
     CU(cudaMemcpyAsync(ctx->d_csr_stats, ctx->h_csr_stats, sizeof(DevCsrStats), cudaMemcpyHostToDevice, ctx->stream));
     csr_stats_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(ctx->d_row_ptr, ctx->d_cols, ctx->d_vals, num_rows,
@@ -482,6 +511,13 @@ int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz)
     ctx->first_value = ctx->h_partial[0];
     ctx->dev_sign = 1;
     ctx->lpr = pick_lpr(nnz, num_rows);
+    ctx->regular_k = 0;
+    if (ctx->h_csr_stats->irregular_rows == 0 && nnz == (uint64_t)num_rows * (nnz / num_rows) && (nnz / num_rows) % 8 == 0) {
+        ctx->regular_k = (uint32_t)(nnz / num_rows);
+        int l = 1;
+        while (l < 32 && (uint32_t)(l * 8) < ctx->regular_k) l *= 2;
+        ctx->lpr8 = l;
+    }
     ctx->has_csr = true;
     ctx->has_solution = false;
     return SLA_OK;
@@ -601,6 +637,8 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
         ctx->opt_skip_zero = value ? 1 : 0;
     } else if (k == "profile") {
         ctx->opt_profile = value ? 1 : 0;
+    } else if (k == "regular") {
+        ctx->opt_regular = value ? 1 : 0;
     } else if (k == "timeout_s") {
         ctx->opt_timeout_s = (double)value;
     } else if (k == "super_rounds") {

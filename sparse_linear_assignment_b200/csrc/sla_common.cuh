@@ -42,6 +42,8 @@ struct DevState {
     uint32_t sign_flip;      // 0x80000000 when the effective values are the negated uploaded values, else 0
     uint32_t n_rows, n_cols;
     uint32_t tail_round_cap; // rounds one tail launch may run before handing control back to the host
+    uint32_t regular_k;      // every row has exactly this many arcs and it is a multiple of 8 (0 = ragged CSR)
+    uint32_t pad1;
     double eps;
     double target_eps;
     double tol;
@@ -55,6 +57,7 @@ struct DevCsrStats {
     unsigned long long min_key, max_key;   // order-preserving u64 keys of min / max value
     unsigned long long bad_cols;           // arcs whose column index is >= num_cols
     unsigned long long bad_rows;           // rows whose extents are not monotone / exceed nnz
+    unsigned long long irregular_rows;     // rows whose degree differs from row 0's
 };
 
 // Every buffer a kernel needs, passed by value.  Pointers only: sizes, sign and all per-solve scalars live in
@@ -117,16 +120,44 @@ __device__ __forceinline__ double2 ld_stream_d2(const double* p) {
     return r;
 }
 
+// Coherent, L1-allocating loads for state that the SAME CTA mutates between barriers (single-CTA engines):
+// within one SM the L1 is kept coherent with that SM's own stores, so after __syncthreads() these see them.
+// (Never used for words that are the target of L2 atomics.)
+__device__ __forceinline__ double ld_ca_f64(const double* p) {
+    double r;
+    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_ca_u32(const uint32_t* p) {
+    uint32_t r;
+    asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+
+// 256-bit streaming loads (sm_100): one LDG.256 per 8 column indices / 4 values, evict-first in L2 so that the
+// once-per-round CSR stream does not push the object state (prices, owners, bid words) out of the L2.
+__device__ __forceinline__ void ld_stream_u8(const uint32_t* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ld_stream_d4(const double* p, double* r) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
+}
+
 enum PriceMode : int {
     PRICE_ZERO = 0,   // all prices are exactly 0.0: no gather
     PRICE_LDG = 1,    // prices immutable during this kernel: read-only path
-    PRICE_CG = 2      // prices mutated by this kernel (tail / batch engines): L2-coherent loads
+    PRICE_CG = 2,     // L2-coherent loads
+    PRICE_CA = 3      // prices mutated by this very CTA (tail / batch engines): coherent L1-cached loads
 };
 
 template <int MODE>
 __device__ __forceinline__ double ld_price(const double* prices, uint32_t j) {
     if (MODE == PRICE_ZERO) return 0.0;
     if (MODE == PRICE_LDG) return __ldg(prices + j);
+    if (MODE == PRICE_CA) return ld_ca_f64(prices + j);
     return __ldcg(prices + j);
 }
 
@@ -179,13 +210,23 @@ __device__ __forceinline__ void choice_group_reduce(Choice& c) {
 // Scan of row [a, b) by a group of LPR lanes; each lane takes aligned chunks of 4 arcs (one 128-bit load of
 // column indices, two 128-bit loads of values).  Arrays are padded so that the aligned chunk is always
 // in bounds.  `flip` is 0 or 0x80000000 (sign normalisation of solver.rs:209-216 applied on the fly).
-template <int LPR, int MODE>
+// STREAM: the CSR is read once per kernel (wide rounds) -> do not allocate in L1; otherwise (persistent single-CTA
+// engines, where the same persons bid again and again) let the rows live in L1.
+template <int LPR, int MODE, bool STREAM = true>
 __device__ __forceinline__ void scan_row(Choice& c, const uint32_t* __restrict__ cols, const double* __restrict__ vals,
                                          const double* prices, uint32_t a, uint32_t b, uint32_t flip, int lane) {
     for (uint32_t base = (a & ~3u) + 4u * (uint32_t)lane; base < b; base += 4u * LPR) {
-        const uint4 cj = ld_stream_u4(cols + base);
-        const double2 v01 = ld_stream_d2(vals + base);
-        const double2 v23 = ld_stream_d2(vals + base + 2);
+        uint4 cj;
+        double2 v01, v23;
+        if (STREAM) {
+            cj = ld_stream_u4(cols + base);
+            v01 = ld_stream_d2(vals + base);
+            v23 = ld_stream_d2(vals + base + 2);
+        } else {
+            cj = __ldg(reinterpret_cast<const uint4*>(cols + base));
+            v01 = __ldg(reinterpret_cast<const double2*>(vals + base));
+            v23 = __ldg(reinterpret_cast<const double2*>(vals + base + 2));
+        }
         const uint32_t jj[4] = {cj.x, cj.y, cj.z, cj.w};
         double vv[4] = {v01.x, v01.y, v23.x, v23.y};
         double pr[4];
@@ -203,6 +244,24 @@ __device__ __forceinline__ void scan_row(Choice& c, const uint32_t* __restrict__
                 choice_update(c, v - pr[t], v, base + t, jj[t]);
             }
         }
+    }
+}
+
+// Regular CSR fast path: 8 consecutive arcs starting at the 8-aligned arc index g, no masking.
+template <int MODE>
+__device__ __forceinline__ void scan8(Choice& c, const uint32_t* __restrict__ cols, const double* __restrict__ vals,
+                                      const double* prices, uint32_t g, uint32_t flip) {
+    uint32_t cj[8];
+    double vv[8], pr[8];
+    ld_stream_u8(cols + g, cj);
+    ld_stream_d4(vals + g, vv);
+    ld_stream_d4(vals + g + 4, vv + 4);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) pr[t] = ld_price<MODE>(prices, cj[t]);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const double v = __hiloint2double(__double2hiint(vv[t]) ^ (int)flip, __double2loint(vv[t]));
+        choice_update(c, (MODE == PRICE_ZERO) ? v : (v - pr[t]), v, g + t, cj[t]);
     }
 }
 

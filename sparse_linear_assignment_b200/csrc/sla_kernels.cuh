@@ -83,11 +83,71 @@ __global__ void __launch_bounds__(kWideThreads) bid_wide_kernel(const Params p) 
     else      bid_wide_body<LPR, PRICE_LDG>(p, qlen, identity, cur ? p.queue[1] : p.queue[0], algo, eps, thr, pbits, sf);
 }
 
+// Regular-CSR variant (every row has exactly K arcs, K % 8 == 0: all of BASELINE.json's configs): no row-extent
+// loads (a = i * K), no masking, 8 arcs per lane per step through 256-bit loads.  LPR8 lanes share one row.
+template <int LPR8, int MODE>
+__device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t qlen, const bool identity,
+                                                 const uint32_t* __restrict__ queue, const uint32_t algo, const double eps,
+                                                 const double threshold, const uint32_t pbits, const uint32_t sign_flip,
+                                                 const uint32_t K) {
+    constexpr int GROUPS_PER_BLOCK = kWideThreads / LPR8;
+    const int lane = threadIdx.x % LPR8;
+    const uint32_t group = blockIdx.x * GROUPS_PER_BLOCK + threadIdx.x / LPR8;
+    const uint32_t ngroups = gridDim.x * GROUPS_PER_BLOCK;
+    uint32_t my_dropped = 0;
+
+    for (uint32_t base = 0; base < qlen; base += ngroups) {
+        const uint32_t q = base + group;
+        const bool valid = q < qlen;
+        Choice c;
+        choice_init(c);
+        uint32_t i = 0;
+        if (valid) {
+            i = identity ? q : __ldg(queue + q);
+            const uint32_t a = i * K;
+            for (uint32_t off = 8u * (uint32_t)lane; off < K; off += 8u * LPR8)
+                scan8<MODE>(c, p.cols, p.vals, p.prices, a + off, sign_flip);
+        }
+        choice_group_reduce<LPR8>(c);
+        if (valid && lane == 0) {
+            const Bid r = make_bid<MODE>(c, algo, eps, threshold, p.prices);
+            if (r.dropped) {
+                p.slot_obj[q] = SLA_DEV_NONE;
+                my_dropped += 1;
+            } else {
+                p.slot_obj[q] = r.obj;
+                p.slot_bid[q] = r.bid;
+                if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));
+            }
+        }
+    }
+    if (my_dropped) atomicAdd(&p.st->dropped, my_dropped);
+    // arcs of a regular round = bidders * K: accounted in control step A
+}
+
+// MODE is a launch-time decision of the host: PRICE_ZERO only for the very first round of a solve (prices are
+// exactly 0 after init_solve, solver.rs:218-219, and the option zero_price_skip is on), PRICE_LDG otherwise.
+template <int LPR8, int MODE>
+__global__ void __launch_bounds__(kWideThreads, (MODE == PRICE_ZERO) ? 6 : 4) bid_regular_kernel(const Params p) {
+    const DevState* st = p.st;
+    const uint32_t cur = st->cur;
+    const uint32_t qlen = st->qlen[cur];
+    if (st->done || qlen <= st->tail_max) return;
+    const bool identity = st->identity != 0;
+    const uint32_t algo = st->algo, pbits = st->pbits, sf = st->sign_flip, K = st->regular_k;
+    const double eps = st->eps, thr = st->threshold;
+    const uint32_t* queue = cur ? p.queue[1] : p.queue[0];
+    bid_regular_body<LPR8, MODE>(p, qlen, identity, queue, algo, eps, thr, pbits, sf, K);
+}
+
 // =============================================================================================================
 // Grid-wide assignment + queue compaction (reference src/symmetric.rs:386-463, src/ksparse.rs:229-244).
 // One thread per old queue slot; each slot yields 0 or 1 entries of the next queue (loser -> itself,
 // winner that evicts -> the evicted owner, winner of a free object or dropped person -> nothing).
 // =============================================================================================================
+constexpr int kAssignChunk = 2048;   // queue slots one block stages before it reserves output space
+constexpr int kAssignUnroll = 4;     // slots per thread whose dependent loads are issued together
+
 __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params p) {
     DevState* st = p.st;
     const uint32_t cur = st->cur;
@@ -99,43 +159,70 @@ __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params 
     uint32_t* __restrict__ next_queue = cur ? p.queue[0] : p.queue[1];
     uint32_t* next_len = &st->qlen[cur ^ 1u];
 
-    __shared__ uint32_t s_warp_off[kWideThreads / 32];
-    __shared__ uint32_t s_block_base;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ uint32_t s_emit[kAssignChunk];
+    __shared__ uint32_t s_cnt, s_base;
+    const int lane = threadIdx.x & 31;
 
-    for (uint32_t base = blockIdx.x * kWideThreads; base < qlen; base += gridDim.x * kWideThreads) {
-        const uint32_t q = base + threadIdx.x;
-        uint32_t emit = SLA_DEV_NONE;
-        if (q < qlen) {
-            const uint32_t j = p.slot_obj[q];
-            if (j != SLA_DEV_NONE) {
-                const uint32_t i = identity ? q : __ldg(queue + q);
-                const double bid = p.slot_bid[q];
-                const bool won = (bid == bid) && (__ldcg(p.best + j) == pack_bid(bid, i, pbits));
-                if (won) {
-                    const uint32_t prev = p.o2p[j];
-                    p.prices[j] = bid;
-                    p.o2p[j] = i;
-                    p.p2o[i] = j;
-                    p.best[j] = 0ull;
-                    if (prev != SLA_DEV_NONE) { p.p2o[prev] = SLA_DEV_NONE; emit = prev; }
-                } else {
-                    emit = i;
+    // contiguous chunk per block: one global atomicAdd per chunk instead of one per 256 slots
+    uint32_t per = (qlen + gridDim.x - 1) / gridDim.x;
+    per = ((per + kWideThreads - 1) / kWideThreads) * kWideThreads;
+    if (per > (uint32_t)kAssignChunk) per = kAssignChunk;
+
+    for (uint32_t start = blockIdx.x * per; start < qlen; start += gridDim.x * per) {
+        const uint32_t stop = (start + per < qlen) ? start + per : qlen;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        for (uint32_t t0 = start; t0 < stop; t0 += kWideThreads * kAssignUnroll) {
+            uint32_t j[kAssignUnroll], i[kAssignUnroll], prev[kAssignUnroll];
+            double bid[kAssignUnroll];
+            unsigned long long word[kAssignUnroll];
+#pragma unroll
+            for (int u = 0; u < kAssignUnroll; ++u) {
+                const uint32_t q = t0 + u * kWideThreads + threadIdx.x;
+                j[u] = SLA_DEV_NONE; i[u] = 0; bid[u] = 0.0;
+                if (q < stop) {
+                    j[u] = p.slot_obj[q];
+                    bid[u] = p.slot_bid[q];
+                    i[u] = identity ? q : __ldg(queue + q);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kAssignUnroll; ++u) {
+                word[u] = 0ull; prev[u] = SLA_DEV_NONE;
+                if (j[u] != SLA_DEV_NONE) {
+                    word[u] = __ldcg(p.best + j[u]);
+                    prev[u] = __ldcg(p.o2p + j[u]);   // speculative: only the winner uses it
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kAssignUnroll; ++u) {
+                uint32_t emit = SLA_DEV_NONE;
+                if (j[u] != SLA_DEV_NONE) {
+                    const bool won = (bid[u] == bid[u]) && (word[u] == pack_bid(bid[u], i[u], pbits));
+                    if (won) {
+                        p.prices[j[u]] = bid[u];
+                        p.o2p[j[u]] = i[u];
+                        p.p2o[i[u]] = j[u];
+                        p.best[j[u]] = 0ull;
+                        if (prev[u] != SLA_DEV_NONE) { p.p2o[prev[u]] = SLA_DEV_NONE; emit = prev[u]; }
+                    } else {
+                        emit = i[u];
+                    }
+                }
+                const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
+                if (ballot) {
+                    uint32_t wbase = 0;
+                    if (lane == 0) wbase = atomicAdd(&s_cnt, (uint32_t)__popc(ballot));
+                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    if (emit != SLA_DEV_NONE) s_emit[wbase + __popc(ballot & ((1u << lane) - 1u))] = emit;
                 }
             }
         }
-        const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
-        const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) s_warp_off[warp] = __popc(ballot);
         __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t run = 0;
-#pragma unroll
-            for (int w = 0; w < kWideThreads / 32; ++w) { const uint32_t c = s_warp_off[w]; s_warp_off[w] = run; run += c; }
-            s_block_base = run ? atomicAdd(next_len, run) : 0u;
-        }
+        if (threadIdx.x == 0) s_base = s_cnt ? atomicAdd(next_len, s_cnt) : 0u;
         __syncthreads();
-        if (emit != SLA_DEV_NONE) next_queue[s_block_base + s_warp_off[warp] + rank] = emit;
+        const uint32_t cnt = s_cnt, gbase = s_base;
+        for (uint32_t e = threadIdx.x; e < cnt; e += kWideThreads) next_queue[gbase + e] = s_emit[e];
         __syncthreads();
     }
 }
@@ -164,6 +251,7 @@ __device__ __forceinline__ uint32_t control_after_wide(DevState* st) {
         st->rounds += 1;
         st->wide_rounds += 1;
         st->bids += qlen;
+        if (st->regular_k) st->bid_arcs += (unsigned long long)qlen * st->regular_k;
         st->qlen[cur] = 0;
         cur ^= 1u;
         st->cur = cur;
@@ -182,7 +270,10 @@ __device__ __forceinline__ uint32_t control_after_wide(DevState* st) {
 
 // =============================================================================================================
 // Tail engine: one persistent CTA runs whole Jacobi rounds (bid -> barrier -> assign/compact -> barrier) while
-// the queue is short; queue and per-slot bids live in shared memory, object state stays in L2.
+// the queue is short.  Queue and per-slot bids live in shared memory; prices / owners are read through the L1
+// (coherent for this CTA's own stores), CSR rows of repeat bidders stay L1-resident.  Conflict resolution:
+//   * <= 32 bidders: entirely in shared memory by one warp (no global atomics, no L2 round trips);
+//   * more bidders : the same packed-word atomicMax on best[] as the wide kernels.
 // Also hosts control step A (it is the first single-CTA kernel after the wide pair).
 // =============================================================================================================
 template <int LPR>
@@ -190,8 +281,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     __shared__ uint32_t s_queue[2][kTailCap];
     __shared__ uint32_t s_obj[kTailCap];
     __shared__ double s_bid[kTailCap];
+    __shared__ unsigned long long s_word[32];
+    __shared__ uint32_t s_prev[32];
     __shared__ uint32_t s_warp_cnt[kTailThreads / 32];
     __shared__ uint32_t s_ctl[2];
+    __shared__ uint32_t s_next_len;
     __shared__ unsigned long long s_arcs;
     __shared__ uint32_t s_dropped;
 
@@ -233,6 +327,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     bool hit_limit = false;
 
     while (true) {
+        const bool small = qlen <= 32u;
         // ---- bidding phase ----
         const uint32_t* sq = s_queue[buf];
         for (uint32_t base = 0; base < qlen; base += NGROUPS) {
@@ -246,12 +341,12 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
             }
             Choice c;
             choice_init(c);
-            if (zero) scan_row<LPR, PRICE_ZERO>(c, p.cols, p.vals, p.prices, a, b, sign_flip, lane);
-            else      scan_row<LPR, PRICE_CG>(c, p.cols, p.vals, p.prices, a, b, sign_flip, lane);
+            if (zero) scan_row<LPR, PRICE_ZERO, false>(c, p.cols, p.vals, p.prices, a, b, sign_flip, lane);
+            else      scan_row<LPR, PRICE_CA, false>(c, p.cols, p.vals, p.prices, a, b, sign_flip, lane);
             choice_group_reduce<LPR>(c);
             if (valid && lane == 0) {
                 const Bid r = zero ? make_bid<PRICE_ZERO>(c, algo, eps, thr, p.prices)
-                                   : make_bid<PRICE_CG>(c, algo, eps, thr, p.prices);
+                                   : make_bid<PRICE_CA>(c, algo, eps, thr, p.prices);
                 my_arcs += (unsigned long long)(b - a);
                 if (r.dropped) {
                     s_obj[q] = SLA_DEV_NONE;
@@ -259,7 +354,13 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                 } else {
                     s_obj[q] = r.obj;
                     s_bid[q] = r.bid;
-                    if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));
+                    const bool is_bid = (r.bid == r.bid);   // NaN never bids
+                    if (small) {
+                        s_word[q] = is_bid ? pack_bid(r.bid, i, pbits) : 0ull;
+                        s_prev[q] = ld_ca_u32(p.o2p + r.obj);   // speculative: only the winner uses it
+                    } else if (is_bid) {
+                        atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));
+                    }
                 }
             }
         }
@@ -268,40 +369,70 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
         // ---- assignment phase + deterministic compaction into the other smem queue ----
         uint32_t* nq = s_queue[buf ^ 1u];
         uint32_t out = 0;
-        for (uint32_t base = 0; base < qlen; base += kTailThreads) {
-            const uint32_t q = base + tid;
-            uint32_t emit = SLA_DEV_NONE;
-            if (q < qlen) {
-                const uint32_t j = s_obj[q];
-                if (j != SLA_DEV_NONE) {
-                    const uint32_t i = sq[q];
-                    const double bid = s_bid[q];
-                    const bool won = (bid == bid) && (__ldcg(p.best + j) == pack_bid(bid, i, pbits));
-                    if (won) {
-                        const uint32_t prev = __ldcg(p.o2p + j);
-                        __stcg(p.prices + j, bid);
-                        __stcg(p.o2p + j, i);
-                        __stcg(p.p2o + i, j);
-                        atomicExch(p.best + j, 0ull);
-                        if (prev != SLA_DEV_NONE) { __stcg(p.p2o + prev, SLA_DEV_NONE); emit = prev; }
-                    } else {
-                        emit = i;
+        if (small) {
+            if (warp == 0) {
+                const uint32_t q = (uint32_t)lane32;
+                uint32_t emit = SLA_DEV_NONE;
+                if (q < qlen) {
+                    const uint32_t j = s_obj[q];
+                    if (j != SLA_DEV_NONE) {
+                        const uint32_t i = sq[q];
+                        const unsigned long long w = s_word[q];
+                        bool won = (w != 0ull);
+                        for (uint32_t r = 0; r < qlen; ++r) won = won && !(s_obj[r] == j && s_word[r] > w);
+                        if (won) {
+                            const uint32_t prev = s_prev[q];
+                            p.prices[j] = s_bid[q];
+                            p.o2p[j] = i;
+                            p.p2o[i] = j;
+                            if (prev != SLA_DEV_NONE) { p.p2o[prev] = SLA_DEV_NONE; emit = prev; }
+                        } else {
+                            emit = i;
+                        }
                     }
                 }
+                const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
+                if (emit != SLA_DEV_NONE) nq[__popc(ballot & ((1u << lane32) - 1u))] = emit;
+                if (lane32 == 0) s_next_len = __popc(ballot);
             }
-            const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
-            if (lane32 == 0) s_warp_cnt[warp] = __popc(ballot);
             __syncthreads();
-            uint32_t off = 0, total = 0;
+            out = s_next_len;
+        } else {
+            for (uint32_t base = 0; base < qlen; base += kTailThreads) {
+                const uint32_t q = base + tid;
+                uint32_t emit = SLA_DEV_NONE;
+                if (q < qlen) {
+                    const uint32_t j = s_obj[q];
+                    if (j != SLA_DEV_NONE) {
+                        const uint32_t i = sq[q];
+                        const double bid = s_bid[q];
+                        const uint32_t prev = ld_ca_u32(p.o2p + j);   // issued together with the best-word load
+                        const bool won = (bid == bid) && (__ldcg(p.best + j) == pack_bid(bid, i, pbits));
+                        if (won) {
+                            p.prices[j] = bid;
+                            p.o2p[j] = i;
+                            p.p2o[i] = j;
+                            atomicExch(p.best + j, 0ull);
+                            if (prev != SLA_DEV_NONE) { p.p2o[prev] = SLA_DEV_NONE; emit = prev; }
+                        } else {
+                            emit = i;
+                        }
+                    }
+                }
+                const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
+                if (lane32 == 0) s_warp_cnt[warp] = __popc(ballot);
+                __syncthreads();
+                uint32_t off = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < kTailThreads / 32; ++w) {
-                const uint32_t cnt = s_warp_cnt[w];
-                off += (w < warp) ? cnt : 0u;
-                total += cnt;
+                for (int w = 0; w < kTailThreads / 32; ++w) {
+                    const uint32_t cnt = s_warp_cnt[w];
+                    off += (w < warp) ? cnt : 0u;
+                    total += cnt;
+                }
+                if (emit != SLA_DEV_NONE) nq[out + off + __popc(ballot & ((1u << lane32) - 1u))] = emit;
+                out += total;
+                __syncthreads();
             }
-            if (emit != SLA_DEV_NONE) nq[out + off + __popc(ballot & ((1u << lane32) - 1u))] = emit;
-            out += total;
-            __syncthreads();
         }
 
         bids_done += qlen;
@@ -452,7 +583,8 @@ __global__ void __launch_bounds__(kWideThreads) csr_stats_kernel(const uint32_t*
                                                                  DevCsrStats* out) {
     const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long kmin = ~0ull, kmax = 0ull, bad_c = 0, bad_r = 0;
+    unsigned long long kmin = ~0ull, kmax = 0ull, bad_c = 0, bad_r = 0, irr = 0;
+    const uint32_t k0 = row_ptr[1] - row_ptr[0];
     for (unsigned long long g = tid; g < nnz; g += stride) {
         const unsigned long long k = f64_order_key(vals[g]);
         kmin = k < kmin ? k : kmin;
@@ -462,6 +594,7 @@ __global__ void __launch_bounds__(kWideThreads) csr_stats_kernel(const uint32_t*
     for (unsigned long long i = tid; i < n_rows; i += stride) {
         const uint32_t a = row_ptr[i], b = row_ptr[i + 1];
         bad_r += (b < a || (unsigned long long)b > nnz) ? 1u : 0u;
+        irr += (b - a != k0) ? 1u : 0u;
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
@@ -471,12 +604,14 @@ __global__ void __launch_bounds__(kWideThreads) csr_stats_kernel(const uint32_t*
         kmax = omax > kmax ? omax : kmax;
         bad_c += __shfl_xor_sync(0xffffffffu, bad_c, m);
         bad_r += __shfl_xor_sync(0xffffffffu, bad_r, m);
+        irr += __shfl_xor_sync(0xffffffffu, irr, m);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMin(&out->min_key, kmin);
         atomicMax(&out->max_key, kmax);
         if (bad_c) atomicAdd(&out->bad_cols, bad_c);
         if (bad_r) atomicAdd(&out->bad_rows, bad_r);
+        if (irr) atomicAdd(&out->irregular_rows, irr);
     }
 }
 

@@ -164,7 +164,7 @@ def test_seeded_instances_match_model_and_oracle(sla, oracle, kind, cls_name, se
 def test_engine_options_do_not_change_results(sla, oracle, kind, cls_name):
     """Wide kernels only / tail engine only / host loop / CUDA graph / gather skipped or not: identical bits."""
     rng = np.random.default_rng(7)
-    n, m, k = 3000, (3000 if kind == "forward" else 5000), 12
+    n, m, k = 3000, (3000 if kind == "forward" else 5000), 16      # k % 8 == 0: the regular-CSR bid kernel applies
     rp, c, v = random_sparse_instance(rng, n, m, k, integer=True, lo=0, hi=200)
     ref = oracle.jacobi_model(kind, n, m, rp, c, v, eps=1.0 / (m + 1))
     combos = [
@@ -174,6 +174,8 @@ def test_engine_options_do_not_change_results(sla, oracle, kind, cls_name):
         dict(graph=0, tail_max=0, zero_price_skip=1, profile=1),
         dict(graph=1, tail_max=2048, zero_price_skip=0, super_rounds=2),
         dict(graph=1, tail_max=64, zero_price_skip=1, super_rounds=16),
+        dict(graph=1, tail_max=1024, zero_price_skip=1, regular=0),
+        dict(graph=0, tail_max=16, zero_price_skip=0, regular=0),
     ]
     for opt in combos:
         solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v, eps=1.0 / (m + 1), options=opt)
