@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for the auction hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1]
+
+A "step" is one complete solve of one synthetic instance (BASELINE.json configs; default cfg3 = KhoslaSolver
+1M x 4M, k=16, the configuration the north star quotes its roofline target on).  Metric: bid-arcs/s, where a
+bid-arc is one (column, value) pair examined for one bidding person in one round.
+
+  value     device-resident throughput: CSR already in HBM, results stay in HBM; CUDA events on the solve stream
+            around exactly K steps, max over ranks.
+  e2e       the same metric through the public API (KhoslaSolver.solve): every step uploads the CSR from pinned
+            host memory, solves, and copies person_to_object / object_to_person / prices back to the host.
+  roofline  the dominant kernel (round-1 bid scan) timed with CUDA events inside the library ("profile" option):
+            algorithmic bytes 12*A + 8*B over the launch duration, against the measured HBM copy bandwidth.
+  cpu_baseline   the CPU oracle (C restatement of the reference, goldens verified) on one host core.
+
+With N > 1 (torchrun, one rank per GPU) every rank solves its own independent instance (seed = 1 + rank): the
+path shards over independent instances with no data-path collective, so scaling is "weak".
+`--impl reference` times the reference's CPU algorithm (the oracle port; the Rust crate cannot be built here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bid_arcs_per_sec"
+UNIT = "bid-arcs/s"
+
+WORKLOADS = {
+    # name: (solver, rows, cols, k, planted, eps)
+    "cfg1": ("khosla", 1_000, 10_000, 32, False, None),
+    "cfg2": ("forward", 20_000, 20_000, 64, True, None),
+    "cfg3": ("khosla", 1_000_000, 4_000_000, 16, False, None),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def describe(workload):
+    kind, n, m, k, planted, eps = WORKLOADS[workload]
+    return {
+        "workload": f"{workload}: {'KhoslaSolver' if kind == 'khosla' else 'ForwardAuctionSolver'} {n}x{m} k={k} "
+                    f"integer costs [300,1000){' planted perfect matching' if planted else ''}, minimize, eps=None",
+        "rows": n, "cols": m, "k": k, "arcs": n * k,
+        "csr_bytes": n * k * 12 + (n + 1) * 4,
+        "l2": "inputs larger than the 126 MB L2" if n * k * 12 > 126e6 else "L2 flushed between timed steps",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.device_index = device_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.device_index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=3)
+        sm, smax, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                smax = max(smax, float(s[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+def flush_l2(torch, device):
+    if not hasattr(flush_l2, "buf"):
+        flush_l2.buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    flush_l2.buf.add_(1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def host_instance(workload, seed, pinned=True):
+    """The synthetic instance in (pinned) host memory, generated by the library's counter-based generator."""
+    import numpy as np
+    import torch
+    from sparse_linear_assignment_b200 import generators as G
+    kind, n, m, k, planted, eps = WORKLOADS[workload]
+    pin = pinned and torch.cuda.is_available()
+    t_rp = torch.empty(n + 1, dtype=torch.int32, pin_memory=pin)
+    t_c = torch.empty(n * k, dtype=torch.int32, pin_memory=pin)
+    t_v = torch.empty(n * k, dtype=torch.float64, pin_memory=pin)
+    rp, c, v = t_rp.numpy().view(np.uint32), t_c.numpy().view(np.uint32), t_v.numpy()
+    G.kregular_host(n, m, k, seed=seed, planted=planted, out=(rp, c, v))
+    return (rp, c, v), (t_rp, t_c, t_v)
+
+
+def run_oracle(workload, csr, reps):
+    """The reference's CPU algorithm (oracle port) on the host instance: best-of-reps solve time, bid-arcs."""
+    from oracle import oracle as O
+    kind, n, m, k, planted, eps = WORKLOADS[workload]
+    rp, c, v = csr
+    times, arcs, obj = [], 0, None
+    for _ in range(reps):
+        s = O.OracleSolver(kind, n, m, n * k)
+        s.load_csr(n, m, rp, c, v)          # the oracle negates its own copy of the values in place
+        t = time.perf_counter()
+        s.solve(maximize=False, eps=eps)
+        times.append(time.perf_counter() - t)
+        arcs, obj = s.bid_arcs, s.get_objective()
+        del s
+    return times, arcs, obj
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    csr, _keep = host_instance(args.workload, args.seed, pinned=False)
+    for _ in range(max(args.warmup, 0)):
+        run_oracle(args.workload, csr, 1)
+    t0 = time.perf_counter()
+    total_arcs, total_t = 0, 0.0
+    for _ in range(args.steps):
+        times, arcs, obj = run_oracle(args.workload, csr, 1)
+        total_arcs += arcs
+        total_t += times[0]
+    wall = time.perf_counter() - t0
+    value = total_arcs / total_t
+    cfg = describe(args.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"full {args.workload} instance, {args.steps} solves, solve() only (the reference is "
+                                   f"single-threaded; C restatement of src/ksparse.rs / src/symmetric.rs, goldens verified)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "objective": obj, "wall_s": wall,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main_ours(args):
+    import numpy as np
+    import torch
+    import sparse_linear_assignment_b200 as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
+        return 2
+    S.build_library()
+    kind, n, m, k, planted, eps = WORKLOADS[args.workload]
+    cls = S.KhoslaSolver if kind == "khosla" else S.ForwardAuctionSolver
+    device = torch.device("cuda", local_rank)
+    seed = args.seed + rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(device)
+
+    # ---- inputs --------------------------------------------------------------------------------------------------
+    csr, keep = host_instance(args.workload, seed, pinned=True)
+    rp, c, v = csr
+    resident, _ = cls.new(n, m, n * k, device=local_rank)
+    resident.load_csr(n, m, rp, c, v)
+    resident._sync_device()                       # CSR now resident in HBM; the host copy is not touched again
+    stream = torch.cuda.ExternalStream(resident._context_stream(), device=device)
+    small_inputs = n * k * 12 <= 126e6
+
+    # ---- value: device-resident solves ---------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        resident.solve_resident(False, eps)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    arcs = launches = 0
+    ms_solve_sum = 0.0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        if small_inputs:
+            flush_l2(torch, device)
+        st = resident.solve_resident(False, eps)
+        arcs += st["bid_arcs"]
+        launches += st["kernel_launches"]
+        ms_solve_sum += st["ms_solve"]
+    ev1.record(stream)
+    barrier()
+    ms_value = ev0.elapsed_time(ev1)
+    if small_inputs:
+        ms_value = ms_solve_sum                    # the L2 flush runs on another stream: count the solves only
+    clocks = sampler.summary()
+    stats = dict(st)
+
+    # ---- e2e: public API with host buffers ------------------------------------------------------------------------
+    solver, solution = cls.new(n, m, n * k, device=local_rank)
+    solver.load_csr(n, m, rp.copy(), c.copy(), v.copy())
+    # back the host-side CSR storage of the solver by the pinned buffers so that the H2D copies run at PCIe speed
+    solver._i_starts_stops.a, solver._column_indices.a, solver._values.a = rp, c, v
+    e2e_warm = max(min(args.warmup, 3), 1)
+    for _ in range(e2e_warm):
+        solver._dirty = True
+        solver.solve(solution, False, eps)
+    barrier()
+    e2e_arcs, e2e_s = 0, 0.0
+    for _ in range(args.steps):
+        if v[0] < 0:
+            np.negative(v, out=v)                  # untimed: hand the solver the caller's original (positive) costs again
+        solver._dirty = True                       # a fresh problem every step: upload + solve + download
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        solver.solve(solution, False, eps)         # includes the in-place sign normalisation of values (solver.rs:214-216)
+        torch.cuda.synchronize(device)
+        e2e_s += time.perf_counter() - t0
+        e2e_arcs += solver.last_stats["bid_arcs"]
+    h2d = 4 * (n + 1) + 12 * n * k
+    d2h = 4 * n + 12 * m
+    objective = solver.get_objective(solution)
+
+    # ---- reduce over ranks ---------------------------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms_value, e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        a = torch.tensor([float(arcs), float(e2e_arcs), float(launches)], dtype=torch.float64, device=device)
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+        ms_value, e2e_s = t.tolist()
+        arcs, e2e_arcs, launches = a.tolist()
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (round-1 bid scan), CUDA events inside the library -------------------------
+        peak, peak_src = measured_peak_gbs()
+        roof = {}
+        for skip, key in ((1, "roofline"), (0, "roofline_general_gather")):
+            resident.set_option("profile", 1)
+            resident.set_option("zero_price_skip", skip)
+            ts, rec = [], None
+            for _ in range(5):
+                resident.solve_resident(False, eps)
+                prof = [p for p in resident.round_profile() if p["engine"] == 0]
+                if prof:
+                    rec = prof[0]
+                    ts.append(rec["bid_ms"])
+            resident.set_option("profile", 0)
+            resident.set_option("zero_price_skip", 1)
+            if rec:
+                t_ms = sorted(ts)[len(ts) // 2]
+                alg = 12 * rec["arcs"] + 8 * rec["bidders"]
+                ach = alg / (t_ms * 1e-3) / 1e9
+                kname = "bid_regular_kernel<PRICE_ZERO>" if skip else "bid_regular_kernel<PRICE_LDG>"
+                roof[key] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": ncu_traffic(kname), "kernel": kname, "launch": "round 1 (all persons bid)",
+                             "bidders": rec["bidders"], "arcs": rec["arcs"], "algorithmic_bytes": alg,
+                             "launch_us": t_ms * 1e3, "peak_source": peak_src}
+        whole = (12 * stats["bid_arcs"] + 8 * stats["bids"]) / (stats["ms_solve"] * 1e-3) / 1e9
+
+        cpu = None
+        if not args.no_cpu_baseline:
+            if v[0] < 0:
+                np.negative(v, out=v)
+            times, o_arcs, o_obj = run_oracle(args.workload, csr, 3)
+            cpu = {"value": o_arcs / min(times), "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"full {args.workload} instance, solve() only, best of 3 "
+                             f"({min(times) * 1e3:.1f} ms, {o_arcs} bid-arcs; the reference is single-threaded)",
+                   "ms": min(times) * 1e3, "objective": o_obj, "objective_matches_gpu": bool(o_obj == objective)}
+        cfg = describe(args.workload)
+        cfg["parallelism"] = "1 GPU" if world == 1 else f"{world} independent instances, one per GPU (no collective)"
+        line = {
+            "metric": METRIC, "value": arcs / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_value / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "clocks": clocks,
+            "e2e": {"value": e2e_arcs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof.get("roofline"),
+            "roofline_general_gather": roof.get("roofline_general_gather"),
+            "roofline_whole_solve": {"achieved": whole, "unit": "GB/s", "frac": whole / peak,
+                                     "note": "sum over rounds of 12*A + 8*B over the whole solve time (tail rounds included)"},
+            "cpu_baseline": cpu,
+            "solve": {k_: stats[k_] for k_ in ("rounds", "wide_rounds", "tail_rounds", "bids", "bid_arcs", "num_unassigned",
+                                               "kernel_launches", "graph_launches", "ms_solve")},
+            "objective": objective,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

@@ -87,7 +87,7 @@ void *sla_ctx_stream(sla_ctx *ctx);             /* the context's cudaStream_t, f
 int sla_ctx_device(const sla_ctx *ctx);
 const char *sla_version(void);
 
-/* Options: "tail_max" (bidders at or below which the tail engine runs, <= 2048), "graph" (1: CUDA-graph
+/* Options: "tail_max" (bidders at or below which the tail engine runs, <= 1024), "graph" (1: CUDA-graph
  * super-rounds, 0: host-driven loop), "zero_price_skip" (1: skip the price gather while all prices are
  * exactly 0, i.e. the first round after init_solve), "profile" (1: record sla_round_profile entries),
  * "super_rounds" (rounds captured per graph). */

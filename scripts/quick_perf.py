@@ -35,7 +35,7 @@ if __name__ == "__main__":
         run("cfg3 khosla", S.KhoslaSolver, 1_000_000, 4_000_000, 16, False, options=dict(zero_price_skip=0))
         run("cfg3 khosla", S.KhoslaSolver, 1_000_000, 4_000_000, 16, False, options=dict(graph=0))
         run("cfg3 khosla", S.KhoslaSolver, 1_000_000, 4_000_000, 16, False, options=dict(regular=0))
-        run("cfg3 khosla", S.KhoslaSolver, 1_000_000, 4_000_000, 16, False, options=dict(tail_max=2048))
+        run("cfg3 khosla", S.KhoslaSolver, 1_000_000, 4_000_000, 16, False, options=dict(tail_max=512))
         for skip in (1, 0):
             s.set_option("profile", 1)
             s.set_option("zero_price_skip", skip)
@@ -46,5 +46,5 @@ if __name__ == "__main__":
     if "cfg2" in which:
         run("cfg2 forward", S.ForwardAuctionSolver, 20000, 20000, 64, True, reps=3)
         run("cfg2 forward", S.ForwardAuctionSolver, 20000, 20000, 64, True, reps=2, options=dict(tail_max=256))
-        run("cfg2 forward", S.ForwardAuctionSolver, 20000, 20000, 64, True, reps=2, options=dict(tail_max=2048))
+        run("cfg2 forward", S.ForwardAuctionSolver, 20000, 20000, 64, True, reps=2, options=dict(tail_max=512))
         run("cfg2 khosla", S.KhoslaSolver, 20000, 20000, 64, True, reps=2)

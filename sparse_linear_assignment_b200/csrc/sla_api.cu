@@ -24,6 +24,7 @@ struct GraphSlot {
     int lpr = 0;
     int super_rounds = 0;
     uint32_t regular_k = 0;
+    bool smem_prices = false;
 };
 
 }  // namespace
@@ -72,6 +73,8 @@ struct sla_ctx {
     uint32_t regular_k = 0;   // all rows have this many arcs (multiple of 8): the regular bid kernel is used
     int lpr8 = 1;
     int opt_regular = 1;
+    int opt_smem_prices = 1;
+    bool tail_smem_prices = false;   // n_cols small enough for the tail engine's shared-memory price mirror
 
     // options
     int opt_graph = 1, opt_tail_max = 1024, opt_skip_zero = 1, opt_profile = 0, opt_super_rounds = 6;
@@ -208,7 +211,10 @@ void launch_one_t(sla_ctx* c, const Params& p, int which, bool zero_first) {
             }
             break;
         case 1: assign_wide_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
-        case 2: tail_kernel<LPR><<<1, kTailThreads, 0, c->stream>>>(p); break;
+        case 2:
+            if (c->tail_smem_prices) tail_kernel<LPR, true><<<1, kTailThreads, kTailSmemPriceCols * sizeof(double), c->stream>>>(p);
+            else tail_kernel<LPR, false><<<1, kTailThreads, 0, c->stream>>>(p);
+            break;
         case 3: ecs_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
         default: phase_apply_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
     }
@@ -240,7 +246,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     GraphSlot& g = ctx->graphs[(forward ? 2 : 0) + (zero_first ? 1 : 0)];
     const uint32_t reg_key = use_regular(ctx) ? ctx->regular_k : 0u;
     if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == ctx->opt_super_rounds &&
-        g.regular_k == reg_key) {
+        g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices) {
         *out = g.exec;
         return SLA_OK;
     }
@@ -261,6 +267,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     g.lpr = ctx->lpr;
     g.super_rounds = ctx->opt_super_rounds;
     g.regular_k = reg_key;
+    g.smem_prices = ctx->tail_smem_prices;
     *out = g.exec;
     return SLA_OK;
 }
@@ -406,7 +413,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
                     r.engine = 0;
                     r.bidders = prev.qlen[prev.cur];
                     r.rounds_covered = 1;
-                    r.arcs = ctx->h_state->bid_arcs - prev.bid_arcs;
+                    r.arcs = prev.regular_k ? (uint64_t)r.bidders * prev.regular_k : ctx->h_state->bid_arcs - prev.bid_arcs;
                     cudaEventElapsedTime(&r.bid_ms, ctx->ev[1], ctx->ev[2]);
                     cudaEventElapsedTime(&r.assign_ms, ctx->ev[2], ctx->ev[3]);
                     ctx->profile.push_back(r);
@@ -518,6 +525,7 @@ int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz)
         while (l < 32 && (uint32_t)(l * 8) < ctx->regular_k) l *= 2;
         ctx->lpr8 = l;
     }
+    ctx->tail_smem_prices = ctx->opt_smem_prices && num_cols <= (uint32_t)kTailSmemPriceCols;
     ctx->has_csr = true;
     ctx->has_solution = false;
     return SLA_OK;
@@ -577,6 +585,16 @@ int sla_ctx_create(int device, size_t row_capacity, size_t col_capacity, size_t 
     if ((e = cudaMallocHost((void**)&ctx->h_state, sizeof(DevState))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_csr_stats, sizeof(DevCsrStats))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_scratch, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMallocHost", e);
+    {
+        const int dyn = kTailSmemPriceCols * (int)sizeof(double);
+        cudaFuncSetAttribute(tail_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaFuncSetAttribute(tail_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaFuncSetAttribute(tail_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaFuncSetAttribute(tail_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        cudaFuncSetAttribute(tail_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        if ((e = cudaFuncSetAttribute(tail_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess)
+            return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
+    }
     // blocks per SM of the widest kernel decide the persistent grid
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bid_wide_kernel<4>, kWideThreads, 0);
@@ -629,7 +647,7 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return SLA_ERR_INVALID;
     const std::string k(key);
     if (k == "tail_max") {
-        if (value < 0 || value > kTailCap) return fail(ctx, SLA_ERR_INVALID, "tail_max must be in [0, 2048]");
+        if (value < 0 || value > kTailCap) return fail(ctx, SLA_ERR_INVALID, "tail_max must be in [0, 1024]");
         ctx->opt_tail_max = (int)value;
     } else if (k == "graph") {
         ctx->opt_graph = value ? 1 : 0;
@@ -637,6 +655,9 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
         ctx->opt_skip_zero = value ? 1 : 0;
     } else if (k == "profile") {
         ctx->opt_profile = value ? 1 : 0;
+    } else if (k == "smem_prices") {
+        ctx->opt_smem_prices = value ? 1 : 0;
+        ctx->tail_smem_prices = ctx->opt_smem_prices && ctx->has_csr && ctx->n_cols <= (uint32_t)kTailSmemPriceCols;
     } else if (k == "regular") {
         ctx->opt_regular = value ? 1 : 0;
     } else if (k == "timeout_s") {
@@ -790,6 +811,13 @@ int sla_validate_matching(sla_ctx* ctx, uint32_t* num_unassigned, int* consisten
     CU(cudaGetLastError());
     if (num_unassigned) *num_unassigned = ctx->h_scratch[0];
     if (consistent) *consistent = ctx->h_scratch[1] ? 0 : 1;
+    return SLA_OK;
+}
+
+// Development aid (not part of include/sla.h): raw tail-engine cycle counters of the last solve.
+int sla_debug_counters(sla_ctx* ctx, uint64_t* out8) {
+    if (!ctx || !out8) return SLA_ERR_INVALID;
+    for (int i = 0; i < 8; ++i) out8[i] = ctx->h_state->dbg[i];
     return SLA_OK;
 }
 

@@ -12,9 +12,10 @@
 
 namespace sla {
 
-constexpr int kTailCap = 2048;       // max bidders the single-CTA tail engine accepts (smem-resident queue)
+constexpr int kTailCap = 1024;       // max bidders the single-CTA tail engine accepts (smem-resident queue)
 constexpr int kWideThreads = 256;    // block size of the grid-wide kernels
 constexpr int kTailThreads = 1024;   // block size of the tail engine
+constexpr int kTailSmemPriceCols = 20480;   // objects whose prices the tail engine can mirror in shared memory (160 KB)
 
 enum : uint32_t { ALGO_KHOSLA = 0, ALGO_FORWARD = 1 };
 enum : uint32_t { ACTION_NONE = 0, ACTION_RESET = 1 };
@@ -50,6 +51,7 @@ struct DevState {
     double threshold;        // Khosla price threshold (ksparse.rs:181)
     unsigned long long rounds, bids, bid_arcs, wide_rounds, tail_rounds;
     unsigned long long safety_rounds_left;
+    unsigned long long dbg[8];   // cycle counters of the tail engine when built with -DSLA_TAIL_TIMING
 };
 
 // Value statistics of the uploaded CSR (computed once per upload).
@@ -150,7 +152,8 @@ enum PriceMode : int {
     PRICE_ZERO = 0,   // all prices are exactly 0.0: no gather
     PRICE_LDG = 1,    // prices immutable during this kernel: read-only path
     PRICE_CG = 2,     // L2-coherent loads
-    PRICE_CA = 3      // prices mutated by this very CTA (tail / batch engines): coherent L1-cached loads
+    PRICE_CA = 3,     // prices mutated by this very CTA (tail / batch engines): coherent L1-cached loads
+    PRICE_SMEM = 4    // `prices` points at a shared-memory copy kept by a single-CTA engine
 };
 
 template <int MODE>
@@ -158,6 +161,7 @@ __device__ __forceinline__ double ld_price(const double* prices, uint32_t j) {
     if (MODE == PRICE_ZERO) return 0.0;
     if (MODE == PRICE_LDG) return __ldg(prices + j);
     if (MODE == PRICE_CA) return ld_ca_f64(prices + j);
+    if (MODE == PRICE_SMEM) return prices[j];
     return __ldcg(prices + j);
 }
 
@@ -168,29 +172,40 @@ struct Choice {
     double value;    // edge value of the best arc
     uint32_t pos;    // global arc index of the best arc (lowest index wins ties) or SLA_DEV_NONE
     uint32_t col;    // its column
+    uint32_t aux;    // single-CTA engines: current owner of that column, gathered together with its price
 };
 
 __device__ __forceinline__ void choice_init(Choice& c) {
-    c.best = neg_inf(); c.second = neg_inf(); c.value = neg_inf(); c.pos = SLA_DEV_NONE; c.col = 0u;
+    c.best = neg_inf(); c.second = neg_inf(); c.value = neg_inf(); c.pos = SLA_DEV_NONE; c.col = 0u; c.aux = SLA_DEV_NONE;
 }
 
-// Sequential update with one arc: exactly the reference's if / else-if (strict '>').
-__device__ __forceinline__ void choice_update(Choice& c, double profit, double value, uint32_t pos, uint32_t col) {
-    if (profit > c.best) {
-        c.second = c.best; c.best = profit; c.value = value; c.pos = pos; c.col = col;
-    } else if (profit > c.second) {
-        c.second = profit;
-    }
+// Sequential update with one arc: exactly the reference's if / else-if (strict '>'), written with selects so that
+// it compiles to straight-line code (the branchy form costs a divergence region per arc).
+__device__ __forceinline__ void choice_update(Choice& c, double profit, double value, uint32_t pos, uint32_t col,
+                                              uint32_t aux = SLA_DEV_NONE) {
+    const bool gt = profit > c.best;
+    const bool gs = profit > c.second;
+    c.second = gt ? c.best : (gs ? profit : c.second);
+    c.best = gt ? profit : c.best;
+    c.value = gt ? value : c.value;
+    c.pos = gt ? pos : c.pos;
+    c.col = gt ? col : c.col;
+    c.aux = gt ? aux : c.aux;
 }
 
 // Merge of two partial scans over disjoint arc sets; equals the sequential scan over their union in
 // position order: max profit, lowest position among the maxima, second = second largest of the multiset.
-__device__ __forceinline__ void choice_merge(Choice& c, double ob, double os, double ov, uint32_t opos, uint32_t ocol) {
+__device__ __forceinline__ void choice_merge(Choice& c, double ob, double os, double ov, uint32_t opos, uint32_t ocol,
+                                             uint32_t oaux) {
     const bool take = (ob > c.best) || (ob == c.best && opos < c.pos);
     const double loser_best = take ? c.best : ob;
     double s = (c.second > os) ? c.second : os;
     s = (loser_best > s) ? loser_best : s;
-    if (take) { c.best = ob; c.value = ov; c.pos = opos; c.col = ocol; }
+    c.best = take ? ob : c.best;
+    c.value = take ? ov : c.value;
+    c.pos = take ? opos : c.pos;
+    c.col = take ? ocol : c.col;
+    c.aux = take ? oaux : c.aux;
     c.second = s;
 }
 
@@ -203,7 +218,8 @@ __device__ __forceinline__ void choice_group_reduce(Choice& c) {
         const double ov = __shfl_xor_sync(0xffffffffu, c.value, m);
         const uint32_t op = __shfl_xor_sync(0xffffffffu, c.pos, m);
         const uint32_t oc = __shfl_xor_sync(0xffffffffu, c.col, m);
-        choice_merge(c, ob, os, ov, op, oc);
+        const uint32_t oa = __shfl_xor_sync(0xffffffffu, c.aux, m);   // dead code where aux is never consumed
+        choice_merge(c, ob, os, ov, op, oc, oa);
     }
 }
 
@@ -212,9 +228,12 @@ __device__ __forceinline__ void choice_group_reduce(Choice& c) {
 // in bounds.  `flip` is 0 or 0x80000000 (sign normalisation of solver.rs:209-216 applied on the fly).
 // STREAM: the CSR is read once per kernel (wide rounds) -> do not allocate in L1; otherwise (persistent single-CTA
 // engines, where the same persons bid again and again) let the rows live in L1.
-template <int LPR, int MODE, bool STREAM = true>
+// OWNER: also gather the current owner of every scanned column (o2p, coherent L1 loads) so that the eviction
+// victim of the best column is known without a further dependent memory round trip.
+template <int LPR, int MODE, bool STREAM = true, bool OWNER = false>
 __device__ __forceinline__ void scan_row(Choice& c, const uint32_t* __restrict__ cols, const double* __restrict__ vals,
-                                         const double* prices, uint32_t a, uint32_t b, uint32_t flip, int lane) {
+                                         const double* prices, uint32_t a, uint32_t b, uint32_t flip, int lane,
+                                         const uint32_t* o2p = nullptr) {
     for (uint32_t base = (a & ~3u) + 4u * (uint32_t)lane; base < b; base += 4u * LPR) {
         uint4 cj;
         double2 v01, v23;
@@ -230,19 +249,20 @@ __device__ __forceinline__ void scan_row(Choice& c, const uint32_t* __restrict__
         const uint32_t jj[4] = {cj.x, cj.y, cj.z, cj.w};
         double vv[4] = {v01.x, v01.y, v23.x, v23.y};
         double pr[4];
+        uint32_t ow[4];
         bool ok[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const uint32_t g = base + t;
             ok[t] = (g >= a) && (g < b);
             pr[t] = ok[t] ? ld_price<MODE>(prices, jj[t]) : 0.0;
+            ow[t] = (OWNER && MODE != PRICE_ZERO && ok[t]) ? ld_ca_u32(o2p + jj[t]) : SLA_DEV_NONE;
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            if (ok[t]) {
-                const double v = __hiloint2double(__double2hiint(vv[t]) ^ (int)flip, __double2loint(vv[t]));
-                choice_update(c, v - pr[t], v, base + t, jj[t]);
-            }
+            const double v = __hiloint2double(__double2hiint(vv[t]) ^ (int)flip, __double2loint(vv[t]));
+            // arcs outside [a, b) get profit -inf, which never passes the strict '>' tests
+            choice_update(c, ok[t] ? (v - pr[t]) : neg_inf(), v, base + t, jj[t], ow[t]);
         }
     }
 }

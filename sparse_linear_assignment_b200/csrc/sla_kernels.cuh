@@ -27,7 +27,9 @@ __device__ __forceinline__ void bid_wide_body(const Params& p, const uint32_t ql
     unsigned long long my_arcs = 0;
     uint32_t my_dropped = 0;
 
-    for (uint32_t base = 0; base < qlen; base += ngroups) {   // grid-uniform trip count (full-mask shuffles inside)
+    const uint32_t warp_group0 = group - (uint32_t)((threadIdx.x & 31) / LPR);   // first group of this warp
+    for (uint32_t base = 0; base < qlen; base += ngroups) {
+        if (base + warp_group0 >= qlen) break;   // warp-uniform: the whole warp is past the end of the queue
         const uint32_t q = base + group;
         const bool valid = q < qlen;
         uint32_t i = 0, a = 0, b = 0;
@@ -96,7 +98,9 @@ __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t
     const uint32_t ngroups = gridDim.x * GROUPS_PER_BLOCK;
     uint32_t my_dropped = 0;
 
+    const uint32_t warp_group0 = group - (uint32_t)((threadIdx.x & 31) / LPR8);   // first group of this warp
     for (uint32_t base = 0; base < qlen; base += ngroups) {
+        if (base + warp_group0 >= qlen) break;   // warp-uniform: the whole warp is past the end of the queue
         const uint32_t q = base + group;
         const bool valid = q < qlen;
         Choice c;
@@ -276,13 +280,18 @@ __device__ __forceinline__ uint32_t control_after_wide(DevState* st) {
 //   * more bidders : the same packed-word atomicMax on best[] as the wide kernels.
 // Also hosts control step A (it is the first single-CTA kernel after the wide pair).
 // =============================================================================================================
-template <int LPR>
+// SPRICES: the object prices are mirrored in dynamic shared memory for the lifetime of the launch (write-through to
+// global), which removes k scattered L1 misses per bidder -- the single SM's miss throughput, not latency, is
+// what bounds a tail round otherwise (profiles/README.md).
+template <int LPR, bool SPRICES>
 __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    double* s_prices = reinterpret_cast<double*>(s_dyn);
     __shared__ uint32_t s_queue[2][kTailCap];
     __shared__ uint32_t s_obj[kTailCap];
     __shared__ double s_bid[kTailCap];
     __shared__ unsigned long long s_word[32];
-    __shared__ uint32_t s_prev[32];
+    __shared__ uint32_t s_prev[kTailCap];
     __shared__ uint32_t s_warp_cnt[kTailThreads / 32];
     __shared__ uint32_t s_ctl[2];
     __shared__ uint32_t s_next_len;
@@ -308,6 +317,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     const uint32_t cur = st->cur;
     const bool identity = st->identity != 0;
     const uint32_t algo = st->algo, pbits = st->pbits, max_it = st->max_iterations, sign_flip = st->sign_flip;
+    const uint32_t regK = st->regular_k;
     const double eps = st->eps, thr = st->threshold;
     bool zero = (st->zero_prices != 0) && (st->skip_zero != 0);
     uint32_t nits = st->nits;
@@ -316,7 +326,13 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
 
     uint32_t* gqueue = cur ? p.queue[1] : p.queue[0];
     for (uint32_t q = tid; q < qlen; q += kTailThreads) s_queue[0][q] = identity ? q : gqueue[q];
+    if (SPRICES) {
+        const uint32_t n_cols = st->n_cols;
+        for (uint32_t j = tid; j < n_cols; j += kTailThreads) s_prices[j] = zero ? 0.0 : p.prices[j];
+    }
     __syncthreads();
+    constexpr int kPriceMode = SPRICES ? PRICE_SMEM : PRICE_CA;
+    const double* price_src = SPRICES ? s_prices : p.prices;
 
     constexpr int NGROUPS = kTailThreads / LPR;
     const int lane = tid % LPR;
@@ -326,27 +342,43 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     uint32_t my_dropped = 0;
     bool hit_limit = false;
 
+#ifdef SLA_TAIL_TIMING
+    long long tk0 = clock64(), tk_scan = 0, tk_red = 0, tk_bid = 0, tk_bar1 = 0, tk_asg = 0, tk_bar2 = 0, tk1, tk2;
+#define TK(acc) do { tk2 = clock64(); acc += tk2 - tk1; tk1 = tk2; } while (0)
+#else
+#define TK(acc) do { } while (0)
+#endif
     while (true) {
         const bool small = qlen <= 32u;
+#ifdef SLA_TAIL_TIMING
+        tk1 = clock64();
+#endif
         // ---- bidding phase ----
         const uint32_t* sq = s_queue[buf];
         for (uint32_t base = 0; base < qlen; base += NGROUPS) {
+            // warps none of whose groups has a bidder leave (warp-uniform, so the full-mask shuffles stay legal):
+            // idle warps must not burn issue slots on the reduction while one or two warps do the real work
+            if (base + (uint32_t)(warp * 32) / LPR >= qlen) break;
             const uint32_t q = base + group;
             const bool valid = q < qlen;
             uint32_t i = 0, a = 0, b = 0;
             if (valid) {
                 i = sq[q];
-                a = __ldg(p.row_ptr + i);
-                b = __ldg(p.row_ptr + i + 1);
+                if (regK) { a = i * regK; b = a + regK; }
+                else { a = __ldg(p.row_ptr + i); b = __ldg(p.row_ptr + i + 1); }
             }
             Choice c;
             choice_init(c);
-            if (zero) scan_row<LPR, PRICE_ZERO, false>(c, p.cols, p.vals, p.prices, a, b, sign_flip, lane);
-            else      scan_row<LPR, PRICE_CA, false>(c, p.cols, p.vals, p.prices, a, b, sign_flip, lane);
+            if (zero) scan_row<LPR, PRICE_ZERO, false>(c, p.cols, p.vals, price_src, a, b, sign_flip, lane);
+            else      scan_row<LPR, kPriceMode, false>(c, p.cols, p.vals, price_src, a, b, sign_flip, lane);
+            TK(tk_scan);
             choice_group_reduce<LPR>(c);
+            // current owner of the chosen object (nobody owns anything while all prices are still zero)
+            if (valid && lane == 0 && !zero) c.aux = ld_ca_u32(p.o2p + ((c.pos == SLA_DEV_NONE) ? 0u : c.col));
+            TK(tk_red);
             if (valid && lane == 0) {
-                const Bid r = zero ? make_bid<PRICE_ZERO>(c, algo, eps, thr, p.prices)
-                                   : make_bid<PRICE_CA>(c, algo, eps, thr, p.prices);
+                const Bid r = zero ? make_bid<PRICE_ZERO>(c, algo, eps, thr, price_src)
+                                   : make_bid<kPriceMode>(c, algo, eps, thr, price_src);
                 my_arcs += (unsigned long long)(b - a);
                 if (r.dropped) {
                     s_obj[q] = SLA_DEV_NONE;
@@ -355,16 +387,18 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                     s_obj[q] = r.obj;
                     s_bid[q] = r.bid;
                     const bool is_bid = (r.bid == r.bid);   // NaN never bids
+                    s_prev[q] = c.aux;                      // owner of r.obj (only the winner uses it)
                     if (small) {
                         s_word[q] = is_bid ? pack_bid(r.bid, i, pbits) : 0ull;
-                        s_prev[q] = ld_ca_u32(p.o2p + r.obj);   // speculative: only the winner uses it
                     } else if (is_bid) {
                         atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));
                     }
                 }
             }
         }
+        TK(tk_bid);
         __syncthreads();
+        TK(tk_bar1);
 
         // ---- assignment phase + deterministic compaction into the other smem queue ----
         uint32_t* nq = s_queue[buf ^ 1u];
@@ -372,30 +406,42 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
         if (small) {
             if (warp == 0) {
                 const uint32_t q = (uint32_t)lane32;
+                const bool live = q < qlen;
+                uint32_t j = live ? s_obj[q] : SLA_DEV_NONE;
+                const bool bidding = j != SLA_DEV_NONE;            // not dropped by the Khosla threshold
+                const uint32_t i = live ? sq[q] : 0u;
+                const unsigned long long w = bidding ? s_word[q] : 0ull;
+                const double bid = bidding ? s_bid[q] : 0.0;
+                const uint32_t prev = bidding ? s_prev[q] : SLA_DEV_NONE;
+                // lanes that bid on the same object; idle lanes get unique keys so that they match nobody
+                const uint32_t peers = __match_any_sync(0xffffffffu, bidding ? j : (0xFFFFFF00u + (uint32_t)lane32));
+                bool won = bidding && (w != 0ull);                  // word 0 == NaN bid: never wins
+                if (__any_sync(0xffffffffu, bidding && (peers & (peers - 1u)) != 0u)) {
+                    // rare: at least two bidders share an object -> compare words lane by lane (warp-uniform loop)
+                    for (uint32_t r = 0; r < qlen; ++r) {
+                        const unsigned long long ow = __shfl_sync(0xffffffffu, w, (int)r);
+                        won = won && !(((peers >> r) & 1u) && ow > w);
+                    }
+                }
                 uint32_t emit = SLA_DEV_NONE;
-                if (q < qlen) {
-                    const uint32_t j = s_obj[q];
-                    if (j != SLA_DEV_NONE) {
-                        const uint32_t i = sq[q];
-                        const unsigned long long w = s_word[q];
-                        bool won = (w != 0ull);
-                        for (uint32_t r = 0; r < qlen; ++r) won = won && !(s_obj[r] == j && s_word[r] > w);
-                        if (won) {
-                            const uint32_t prev = s_prev[q];
-                            p.prices[j] = s_bid[q];
-                            p.o2p[j] = i;
-                            p.p2o[i] = j;
-                            if (prev != SLA_DEV_NONE) { p.p2o[prev] = SLA_DEV_NONE; emit = prev; }
-                        } else {
-                            emit = i;
-                        }
+                if (bidding) {
+                    if (won) {
+                        p.prices[j] = bid;
+                        if (SPRICES) s_prices[j] = bid;
+                        p.o2p[j] = i;
+                        p.p2o[i] = j;
+                        if (prev != SLA_DEV_NONE) { p.p2o[prev] = SLA_DEV_NONE; emit = prev; }
+                    } else {
+                        emit = i;
                     }
                 }
                 const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
                 if (emit != SLA_DEV_NONE) nq[__popc(ballot & ((1u << lane32) - 1u))] = emit;
                 if (lane32 == 0) s_next_len = __popc(ballot);
             }
+            TK(tk_asg);
             __syncthreads();
+            TK(tk_bar2);
             out = s_next_len;
         } else {
             for (uint32_t base = 0; base < qlen; base += kTailThreads) {
@@ -406,10 +452,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                     if (j != SLA_DEV_NONE) {
                         const uint32_t i = sq[q];
                         const double bid = s_bid[q];
-                        const uint32_t prev = ld_ca_u32(p.o2p + j);   // issued together with the best-word load
+                        const uint32_t prev = s_prev[q];
                         const bool won = (bid == bid) && (__ldcg(p.best + j) == pack_bid(bid, i, pbits));
                         if (won) {
                             p.prices[j] = bid;
+                            if (SPRICES) s_prices[j] = bid;
                             p.o2p[j] = i;
                             p.p2o[i] = j;
                             atomicExch(p.best + j, 0ull);
@@ -466,7 +513,18 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
         st->safety_rounds_left = safety;
         if (hit_limit) st->done = 1;
         else if (qlen == 0) finish_if_possible(st);
+#ifdef SLA_TAIL_TIMING
+        st->dbg[0] += (unsigned long long)(clock64() - tk0);
+        st->dbg[1] += (unsigned long long)tk_scan;
+        st->dbg[2] += (unsigned long long)tk_red;
+        st->dbg[3] += (unsigned long long)tk_bar1;
+        st->dbg[4] += (unsigned long long)tk_asg;
+        st->dbg[5] += (unsigned long long)tk_bar2;
+        st->dbg[6] += rounds_done;
+        st->dbg[7] += (unsigned long long)tk_bid;
+#endif
     }
+#undef TK
 }
 
 // =============================================================================================================

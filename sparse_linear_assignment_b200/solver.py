@@ -350,6 +350,10 @@ class AuctionSolver:
             self._dirty = True
         return self._ctx
 
+    def _context_stream(self) -> int:
+        """The context's cudaStream_t as an integer (for torch.cuda.ExternalStream / event timing)."""
+        return int(_lib.load().sla_ctx_stream(self._context()) or 0)
+
     def set_option(self, key: str, value: int) -> None:
         ctx = self._context()
         _lib.check(ctx, _lib.load().sla_set_option(ctx, key.encode(), int(value)))
