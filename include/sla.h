@@ -87,6 +87,13 @@ void *sla_ctx_stream(sla_ctx *ctx);             /* the context's cudaStream_t, f
 int sla_ctx_device(const sla_ctx *ctx);
 const char *sla_version(void);
 
+/* Host-memory helpers for the wrappers: page-locked staging buffers (a Rust shim would back its Vecs with these, or
+ * cudaHostRegister them) and the in-place negation of the host copy of `values` that AuctionSolver::init_solve
+ * performs (solver.rs:214-216; stats.values_negated says when), split over `threads` host threads. */
+int sla_host_alloc(size_t bytes, void **out);
+void sla_host_free(void *p);
+void sla_host_negate_f64(double *values, size_t n, int threads);
+
 /* Options: "tail_max" (bidders at or below which the tail engine runs, <= 1024), "graph" (1: CUDA-graph
  * super-rounds, 0: host-driven loop), "zero_price_skip" (1: skip the price gather while all prices are
  * exactly 0, i.e. the first round after init_solve), "profile" (1: record sla_round_profile entries),

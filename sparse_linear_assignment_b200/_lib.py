@@ -89,6 +89,9 @@ SIGNATURES = {
     "sla_ctx_device": (C.c_int, [_vp]),
     "sla_version": (C.c_char_p, []),
     "sla_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+    "sla_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "sla_host_free": (None, [_vp]),
+    "sla_host_negate_f64": (None, [_vp, C.c_size_t, C.c_int]),
     "sla_upload_csr": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint64]),
     "sla_upload_csr_device": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint64]),
     "sla_generate_device": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32,

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sla.h"
@@ -812,6 +813,43 @@ int sla_validate_matching(sla_ctx* ctx, uint32_t* num_unassigned, int* consisten
     if (num_unassigned) *num_unassigned = ctx->h_scratch[0];
     if (consistent) *consistent = ctx->h_scratch[1] ? 0 : 1;
     return SLA_OK;
+}
+
+// ---- host-memory helpers for the wrappers (pinned staging keeps the H2D / D2H copies at PCIe speed) ----
+int sla_host_alloc(size_t bytes, void** out) {
+    if (!out) return SLA_ERR_INVALID;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+        *out = nullptr;
+        return SLA_ERR_ALLOC;
+    }
+    return SLA_OK;
+}
+
+void sla_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// In-place negation of the host copy of `values` (the observable half of solver.rs:214-216), split over threads.
+void sla_host_negate_f64(double* values, size_t n, int threads) {
+    if (!values || !n) return;
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    if (n < (size_t)1 << 16) threads = 1;
+    auto work = [values](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) values[i] = -values[i];
+    };
+    std::vector<std::thread> pool;
+    const size_t chunk = (n + (size_t)threads - 1) / (size_t)threads;
+    for (int t = 1; t < threads; ++t) {
+        const size_t lo = (size_t)t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        if (lo < hi) pool.emplace_back(work, lo, hi);
+    }
+    work(0, chunk < n ? chunk : n);
+    for (auto& th : pool) th.join();
 }
 
 // Development aid (not part of include/sla.h): raw tail-engine cycle counters of the last solve.

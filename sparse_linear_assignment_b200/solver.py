@@ -15,6 +15,9 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
+import threading
+import weakref
 from typing import Optional, Tuple
 
 import numpy as np
@@ -29,11 +32,36 @@ def _imax(dtype) -> int:
     return int(np.iinfo(dtype).max)
 
 
+_PIN_MIN_BYTES = 1 << 16
+_pin_state = {"ok": None}
+
+
+def host_array(n: int, dtype) -> np.ndarray:
+    """An uninitialised host array; large ones are page-locked through the library (sla_host_alloc) so that the
+    H2D / D2H copies of the C ABI run at PCIe speed.  Falls back to pageable memory when no device is usable
+    (storage only -- nothing is ever computed on the host)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(n) * dtype.itemsize
+    if nbytes >= _PIN_MIN_BYTES and _pin_state["ok"] is not False:
+        try:
+            lib = _lib.load()
+            ptr = C.c_void_p()
+            if lib.sla_host_alloc(nbytes, C.byref(ptr)) == _lib.SLA_OK and ptr.value:
+                _pin_state["ok"] = True
+                arr = np.frombuffer((C.c_char * nbytes).from_address(ptr.value), dtype=dtype, count=int(n))
+                weakref.finalize(arr, lib.sla_host_free, ptr.value)
+                return arr
+            _pin_state["ok"] = False
+        except Exception:
+            _pin_state["ok"] = False
+    return np.empty(int(n), dtype=dtype)
+
+
 class _Vec:
     """A growable typed array with Vec semantics (len <= capacity, amortised push)."""
 
     def __init__(self, dtype, capacity: int = 0):
-        self.a = np.empty(max(int(capacity), 1), dtype=dtype)
+        self.a = host_array(max(int(capacity), 1), dtype)
         self.len = 0
 
     def reserve(self, n: int):
@@ -41,7 +69,7 @@ class _Vec:
             cap = self.a.size
             while cap < n:
                 cap *= 2
-            b = np.empty(cap, dtype=self.a.dtype)
+            b = host_array(cap, self.a.dtype)
             b[: self.len] = self.a[: self.len]
             self.a = b
 
@@ -127,6 +155,7 @@ class AuctionSolver:
         self._ctx = None
         self._dirty = True
         self._device_only = False   # CSR was generated in HBM (generators.kregular_device): no host copy exists
+        self._prices_on_device = False
 
     # ---- construction ------------------------------------------------------------------------------------
     @classmethod
@@ -140,6 +169,7 @@ class AuctionSolver:
         """#[derive(Clone)]: deep copy of the host state; the device context is re-created lazily."""
         other = type(self)(*self._caps, index_dtype=self.index_dtype, device=self.device)
         other._num_rows, other._num_cols = self._num_rows, self._num_cols
+        self.prices()    # pull resident prices into the host copy before it is duplicated
         for name in ("_i_starts_stops", "_j_counts", "_prices", "_column_indices", "_values"):
             getattr(other, name).assign(getattr(self, name).view)
         for name in ("nits", "nreductions", "optimal_soln_found", "max_iterations"):
@@ -166,6 +196,12 @@ class AuctionSolver:
         return self._num_cols
 
     def prices(self) -> np.ndarray:
+        """Final prices of the last solve; fetched from HBM on first access (they stay resident otherwise)."""
+        if self._prices_on_device:
+            ctx = self._context()
+            self._prices.resize(self._num_cols, 0.0)
+            _lib.check(ctx, _lib.load().sla_download_solution(ctx, None, None, self._prices.view.ctypes.data))
+            self._prices_on_device = False
         return self._prices.view
 
     def i_starts_stops(self) -> np.ndarray:
@@ -181,7 +217,7 @@ class AuctionSolver:
         return self._values.view
 
     def prices_mut(self) -> np.ndarray:
-        return self._prices.view
+        return self.prices()
 
     def i_starts_stops_mut(self) -> np.ndarray:
         self._dirty = True
@@ -314,7 +350,7 @@ class AuctionSolver:
         p2o = np.asarray(person_to_object)[:n].astype(np.int64)
         cols = self._column_indices.view.astype(np.int64)
         vals = self._values.view
-        prices = self._prices.view
+        prices = self.prices()
         row_of = np.repeat(np.arange(n), counts)
         match = cols == p2o[row_of]
         chosen = np.full(n, -np.inf)
@@ -331,6 +367,7 @@ class AuctionSolver:
         if bool(maximize) ^ bool(positive):
             vals *= -1.0
             self._dirty = True
+        self._prices_on_device = False
         self._prices.clear()
         self._prices.resize(self._num_cols, 0.0)
         solution.person_to_object = np.full(self._num_rows, self.imax, dtype=self.index_dtype)
@@ -371,9 +408,27 @@ class AuctionSolver:
             self._dirty = False
         return ctx
 
-    def _finish(self, solution: AuctionSolution, stats: SlaStats, p2o, o2p):
-        if stats.values_negated and not self._device_only:
-            self._values.view[:] *= -1.0     # solver.rs:214-216, observable through values()
+    def _begin_negation(self, maximize: bool):
+        """solver.rs:209-216 on the host copy: decided by the sign of the first value; runs on helper threads while
+        the GPU solves (the device applies the same sign on the fly).  Returns (thread or None, flip)."""
+        if self._device_only:
+            return None, None
+        vals = self._values.view
+        flip = bool(maximize) ^ bool((vals[0] if vals.size else 0.0) >= 0.0)
+        if not flip:
+            return None, False
+        lib = _lib.load()
+        th = threading.Thread(target=lib.sla_host_negate_f64,
+                              args=(vals.ctypes.data, vals.size, min(8, os.cpu_count() or 1)))
+        th.start()
+        return th, True
+
+    def _finish(self, solution: AuctionSolution, stats: SlaStats, p2o, o2p, negation=(None, None)):
+        th, flip = negation
+        if th is not None:
+            th.join()
+        if flip is not None and bool(stats.values_negated) != flip:
+            raise SlaError(_lib.SLA_ERR_STATE, "host / device disagree on the sign normalisation of values")
         if self.index_dtype == np.dtype(np.uint32):
             solution.person_to_object, solution.object_to_person = p2o, o2p
         else:   # SLA_NONE truncates to u16::MAX
@@ -384,12 +439,17 @@ class AuctionSolver:
         self.nits = int(stats.nits)
         self.last_stats = stats.as_dict()
 
-    def _outputs(self):
-        p2o = np.empty(self._num_rows, dtype=np.uint32)
-        o2p = np.empty(self._num_cols, dtype=np.uint32)
-        self._prices.resize(self._num_cols, 0.0)
-        self._prices.len = self._num_cols
-        return p2o, o2p, self._prices.view
+    def _outputs(self, solution: AuctionSolution):
+        """Output buffers: the caller's solution vectors are reused when they already have the right shape (the
+        reference resizes the caller's Vecs in place, solver.rs:221-228); prices stay in HBM until asked for."""
+        def fit(arr, n):
+            if isinstance(arr, np.ndarray) and arr.dtype == np.uint32 and arr.size == n and arr.flags.c_contiguous \
+                    and arr.flags.writeable:
+                return arr
+            return host_array(n, np.uint32)
+        p2o = fit(solution.person_to_object, self._num_rows)
+        o2p = fit(solution.object_to_person, self._num_cols)
+        return p2o, o2p
 
     def device_objective(self) -> float:
         """sla_get_objective on the resident solution (exact for integer-valued weights)."""
@@ -442,17 +502,17 @@ class AuctionSolver:
                                       C.byref(st))
         _lib.check(ctx, rc)
         if st.values_negated and not self._device_only:
-            self._values.view[:] *= -1.0
+            _lib.load().sla_host_negate_f64(self._values.view.ctypes.data, self._values.view.size, 8)
+        self._prices_on_device = True
         self.nits = int(st.nits)
         self.last_stats = st.as_dict()
         return self.last_stats
 
     def download_solution(self, solution: AuctionSolution) -> None:
         ctx = self._context()
-        p2o, o2p, prices = self._outputs()
-        _lib.check(ctx, _lib.load().sla_download_solution(ctx, p2o.ctypes.data, o2p.ctypes.data, prices.ctypes.data))
+        p2o, o2p = self._outputs(solution)
+        _lib.check(ctx, _lib.load().sla_download_solution(ctx, p2o.ctypes.data, o2p.ctypes.data, None))
         st = SlaStats(**{k: v for k, v in (self.last_stats or {}).items()})
-        st.values_negated = 0
         self._finish(solution, st, p2o, o2p)
 
 
@@ -464,12 +524,16 @@ class KhoslaSolver(AuctionSolver):
         if not self._device_only:
             self.validate_input()
         ctx = self._sync_device()
-        p2o, o2p, prices = self._outputs()
+        p2o, o2p = self._outputs(solution)
         st = SlaStats()
+        neg = self._begin_negation(maximize)
         rc = _lib.load().sla_khosla_solve(ctx, int(bool(maximize)), float("nan") if eps is None else float(eps),
-                                          p2o.ctypes.data, o2p.ctypes.data, prices.ctypes.data, C.byref(st))
+                                          p2o.ctypes.data, o2p.ctypes.data, None, C.byref(st))
+        if neg[0] is not None:
+            neg[0].join()
         _lib.check(ctx, rc)
-        self._finish(solution, st, p2o, o2p)
+        self._prices_on_device = True
+        self._finish(solution, st, p2o, o2p, neg)
 
 
 class ForwardAuctionSolver(AuctionSolver):
@@ -494,15 +558,19 @@ class ForwardAuctionSolver(AuctionSolver):
         if not self._device_only:
             self.validate_input()
         ctx = self._sync_device()
-        p2o, o2p, prices = self._outputs()
+        p2o, o2p = self._outputs(solution)
         # Some(0) behaves like Some(1) in the reference (the check runs after the first round, symmetric.rs:326)
         self.max_iterations = max(int(max_iterations), 1) if max_iterations is not None else self.MAX_ITERATIONS
         st = SlaStats()
         nan = float("nan")
+        neg = self._begin_negation(maximize)
         rc = _lib.load().sla_forward_solve(ctx, int(bool(maximize)), nan if eps is None else float(eps),
                                            nan if start_eps is None else float(start_eps), self.max_iterations,
-                                           p2o.ctypes.data, o2p.ctypes.data, prices.ctypes.data, C.byref(st))
+                                           p2o.ctypes.data, o2p.ctypes.data, None, C.byref(st))
+        if neg[0] is not None:
+            neg[0].join()
         _lib.check(ctx, rc)
-        self._finish(solution, st, p2o, o2p)
+        self._prices_on_device = True
+        self._finish(solution, st, p2o, o2p, neg)
         self.nreductions = int(st.nreductions)
         self.optimal_soln_found = bool(st.optimal_soln_found)
