@@ -21,7 +21,10 @@ enum : uint32_t { ALGO_KHOSLA = 0, ALGO_FORWARD = 1 };
 enum : uint32_t { ACTION_NONE = 0, ACTION_RESET = 1 };
 
 // Device-resident control block of one solve.  Only single threads write it (see the kernels).
+// The first 96 bytes are the fields every kernel needs at start-up; HotState mirrors them so that a kernel can
+// fetch them with six independent 128-bit loads (one L2 round trip instead of a chain of dependent ones).
 struct DevState {
+    // ---- hot (mirrored by HotState) ----
     uint32_t qlen[2];        // lengths of the two queue buffers
     uint32_t cur;            // which queue buffer holds the current bidders
     uint32_t done;           // solve finished
@@ -29,30 +32,51 @@ struct DevState {
     uint32_t zero_prices;    // every price is exactly 0.0 (first round after init_solve): gather may be skipped
     uint32_t algo;
     uint32_t pbits;          // bits of the person field of a packed bid word
+    uint32_t tail_max;
+    uint32_t skip_zero;      // option zero_price_skip
+    uint32_t sign_flip;      // 0x80000000 when the effective values are the negated uploaded values, else 0
+    uint32_t regular_k;      // every row has exactly this many arcs and it is a multiple of 8 (0 = ragged CSR)
+    uint32_t n_rows, n_cols;
+    uint32_t start_opt;      // start_from_optimal_eps (symmetric.rs:251-266)
+    uint32_t action;
+    double eps;
+    double threshold;        // Khosla price threshold (ksparse.rs:181)
+    double target_eps;
+    double tol;
+    // ---- cold ----
     uint32_t nits;           // Forward: rounds (symmetric.rs:277); Khosla: filled from `bids` at the end
     uint32_t nreductions;
     uint32_t optimal;
     uint32_t ecs_violated;
     uint32_t ecs_ticket;
-    uint32_t action;
     uint32_t dropped;
     uint32_t max_iterations;
-    uint32_t start_opt;      // start_from_optimal_eps (symmetric.rs:251-266)
-    uint32_t tail_max;
-    uint32_t skip_zero;      // option zero_price_skip
-    uint32_t sign_flip;      // 0x80000000 when the effective values are the negated uploaded values, else 0
-    uint32_t n_rows, n_cols;
     uint32_t tail_round_cap; // rounds one tail launch may run before handing control back to the host
-    uint32_t regular_k;      // every row has exactly this many arcs and it is a multiple of 8 (0 = ragged CSR)
-    uint32_t pad1;
-    double eps;
-    double target_eps;
-    double tol;
-    double threshold;        // Khosla price threshold (ksparse.rs:181)
     unsigned long long rounds, bids, bid_arcs, wide_rounds, tail_rounds;
     unsigned long long safety_rounds_left;
     unsigned long long dbg[8];   // cycle counters of the tail engine when built with -DSLA_TAIL_TIMING
 };
+
+struct alignas(16) HotState {
+    uint32_t qlen[2], cur, done;
+    uint32_t identity, zero_prices, algo, pbits;
+    uint32_t tail_max, skip_zero, sign_flip, regular_k;
+    uint32_t n_rows, n_cols, start_opt, action;
+    double eps, threshold;
+    double target_eps, tol;
+};
+static_assert(sizeof(HotState) == 96, "HotState must mirror the first 96 bytes of DevState");
+static_assert(sizeof(DevState) % 16 == 0, "DevState is copied as 128-bit words");
+
+__device__ __forceinline__ HotState load_hot(const DevState* st) {
+    HotState h;
+    const uint4* src = reinterpret_cast<const uint4*>(st);
+    uint4* dst = reinterpret_cast<uint4*>(&h);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dst[i] = src[i];   // L1-cached: thousands of warps read the same 96 bytes (the L1 is
+                                                   // invalidated at every launch boundary, so the data is current)
+    return h;
+}
 
 // Value statistics of the uploaded CSR (computed once per upload).
 struct DevCsrStats {

@@ -72,15 +72,15 @@ __device__ __forceinline__ void bid_wide_body(const Params& p, const uint32_t ql
 
 template <int LPR>
 __global__ void __launch_bounds__(kWideThreads) bid_wide_kernel(const Params p) {
-    const DevState* st = p.st;
-    const uint32_t cur = st->cur;
-    const uint32_t qlen = st->qlen[cur];
-    if (st->done || qlen <= st->tail_max) return;
-    const bool identity = st->identity != 0;
-    const bool zero = (st->zero_prices != 0) && (st->skip_zero != 0);
-    const uint32_t algo = st->algo, pbits = st->pbits;
-    const double eps = st->eps, thr = st->threshold;
-    const uint32_t sf = st->sign_flip;
+    const HotState h = load_hot(p.st);
+    const uint32_t cur = h.cur;
+    const uint32_t qlen = h.qlen[cur & 1u];
+    if (h.done || qlen <= h.tail_max) return;
+    const bool identity = h.identity != 0;
+    const bool zero = (h.zero_prices != 0) && (h.skip_zero != 0);
+    const uint32_t algo = h.algo, pbits = h.pbits;
+    const double eps = h.eps, thr = h.threshold;
+    const uint32_t sf = h.sign_flip;
     if (zero) bid_wide_body<LPR, PRICE_ZERO>(p, qlen, identity, cur ? p.queue[1] : p.queue[0], algo, eps, thr, pbits, sf);
     else      bid_wide_body<LPR, PRICE_LDG>(p, qlen, identity, cur ? p.queue[1] : p.queue[0], algo, eps, thr, pbits, sf);
 }
@@ -133,13 +133,13 @@ __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t
 // exactly 0 after init_solve, solver.rs:218-219, and the option zero_price_skip is on), PRICE_LDG otherwise.
 template <int LPR8, int MODE>
 __global__ void __launch_bounds__(kWideThreads, (MODE == PRICE_ZERO) ? 6 : 4) bid_regular_kernel(const Params p) {
-    const DevState* st = p.st;
-    const uint32_t cur = st->cur;
-    const uint32_t qlen = st->qlen[cur];
-    if (st->done || qlen <= st->tail_max) return;
-    const bool identity = st->identity != 0;
-    const uint32_t algo = st->algo, pbits = st->pbits, sf = st->sign_flip, K = st->regular_k;
-    const double eps = st->eps, thr = st->threshold;
+    const HotState h = load_hot(p.st);
+    const uint32_t cur = h.cur;
+    const uint32_t qlen = h.qlen[cur & 1u];
+    if (h.done || qlen <= h.tail_max) return;
+    const bool identity = h.identity != 0;
+    const uint32_t algo = h.algo, pbits = h.pbits, sf = h.sign_flip, K = h.regular_k;
+    const double eps = h.eps, thr = h.threshold;
     const uint32_t* queue = cur ? p.queue[1] : p.queue[0];
     bid_regular_body<LPR8, MODE>(p, qlen, identity, queue, algo, eps, thr, pbits, sf, K);
 }
@@ -154,11 +154,13 @@ constexpr int kAssignUnroll = 4;     // slots per thread whose dependent loads a
 
 __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params p) {
     DevState* st = p.st;
-    const uint32_t cur = st->cur;
-    const uint32_t qlen = st->qlen[cur];
-    if (st->done || qlen <= st->tail_max) return;
-    const bool identity = st->identity != 0;
-    const uint32_t pbits = st->pbits;
+    const HotState h = load_hot(st);
+    const uint32_t cur = h.cur;
+    const uint32_t qlen = h.qlen[cur & 1u];
+    if (h.done || qlen <= h.tail_max) return;
+    const bool identity = h.identity != 0;
+    const bool nobody_owns = h.zero_prices != 0;   // first round after init_solve: every object is still free
+    const uint32_t pbits = h.pbits;
     const uint32_t* __restrict__ queue = cur ? p.queue[1] : p.queue[0];
     uint32_t* __restrict__ next_queue = cur ? p.queue[0] : p.queue[1];
     uint32_t* next_len = &st->qlen[cur ^ 1u];
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params 
                 word[u] = 0ull; prev[u] = SLA_DEV_NONE;
                 if (j[u] != SLA_DEV_NONE) {
                     word[u] = __ldcg(p.best + j[u]);
-                    prev[u] = __ldcg(p.o2p + j[u]);   // speculative: only the winner uses it
+                    if (!nobody_owns) prev[u] = __ldcg(p.o2p + j[u]);   // speculative: only the winner uses it
                 }
             }
 #pragma unroll
@@ -298,9 +300,16 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     __shared__ unsigned long long s_arcs;
     __shared__ uint32_t s_dropped;
 
-    DevState* st = p.st;
+    // The whole control block is fetched with one cooperative copy, mutated in shared memory by thread 0 and written
+    // back at the end: the tail kernel is the only kernel running on the stream, so it owns the block meanwhile.
+    __shared__ DevState s_state;
+    DevState* const gst = p.st;
+    DevState* const st = &s_state;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane32 = tid & 31;
+    constexpr int kStateWords = (int)(sizeof(DevState) / 16);
+    if (tid < kStateWords) reinterpret_cast<uint4*>(st)[tid] = __ldcg(reinterpret_cast<const uint4*>(gst) + tid);
+    __syncthreads();
 
     if (tid == 0) {
         const uint32_t qlen0 = control_after_wide(st);
@@ -311,7 +320,10 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
         s_dropped = 0;
     }
     __syncthreads();
-    if (!s_ctl[0]) return;
+    if (!s_ctl[0]) {
+        if (tid < kStateWords) reinterpret_cast<uint4*>(gst)[tid] = reinterpret_cast<const uint4*>(st)[tid];
+        return;
+    }
 
     uint32_t qlen = s_ctl[1];
     const uint32_t cur = st->cur;
@@ -504,7 +516,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
         st->rounds += rounds_done;
         st->tail_rounds += rounds_done;
         st->bids += bids_done;
-        atomicAdd(&st->bid_arcs, s_arcs);
+        st->bid_arcs += s_arcs;
         st->dropped += s_dropped;
         st->qlen[cur] = qlen;
         st->identity = 0;
@@ -524,6 +536,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
         st->dbg[7] += (unsigned long long)tk_bid;
 #endif
     }
+    __syncthreads();
+    if (tid < kStateWords) reinterpret_cast<uint4*>(gst)[tid] = reinterpret_cast<const uint4*>(st)[tid];
 #undef TK
 }
 
@@ -534,9 +548,10 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
 template <int LPR>
 __global__ void __launch_bounds__(kWideThreads) ecs_kernel(const Params p) {
     DevState* st = p.st;
-    if (st->done || st->algo != ALGO_FORWARD || st->start_opt || st->qlen[st->cur] != 0) return;
-    const double eps = st->target_eps, tol = st->tol;
-    const uint32_t n_rows = st->n_rows, n_cols = st->n_cols, sign_flip = st->sign_flip;
+    const HotState h = load_hot(st);
+    if (h.done || h.algo != ALGO_FORWARD || h.start_opt || h.qlen[h.cur & 1u] != 0) return;
+    const double eps = h.target_eps, tol = h.tol;
+    const uint32_t n_rows = h.n_rows, n_cols = h.n_cols, sign_flip = h.sign_flip;
 
     constexpr int GROUPS_PER_BLOCK = kWideThreads / LPR;
     const int lane = threadIdx.x % LPR;
@@ -611,8 +626,9 @@ __global__ void __launch_bounds__(kWideThreads) ecs_kernel(const Params p) {
 
 // Forward phase restart: wipe both assignment vectors, keep prices (reference src/symmetric.rs:299-321).
 __global__ void __launch_bounds__(kWideThreads) phase_apply_kernel(const Params p) {
-    if (p.st->action != ACTION_RESET) return;
-    const uint32_t n_rows = p.st->n_rows, n_cols = p.st->n_cols;
+    const HotState h = load_hot(p.st);
+    if (h.action != ACTION_RESET) return;
+    const uint32_t n_rows = h.n_rows, n_cols = h.n_cols;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     for (uint32_t i = tid; i < n_rows; i += stride) p.p2o[i] = SLA_DEV_NONE;
     for (uint32_t j = tid; j < n_cols; j += stride) p.o2p[j] = SLA_DEV_NONE;
