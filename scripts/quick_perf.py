@@ -26,6 +26,18 @@ def run(name, cls, n, m, k, planted, eps=None, reps=5, options=None):
     return solver
 
 
+def run_cfg4(kind, count=8192):
+    b = S.BatchSolver(kind)
+    t = time.perf_counter()
+    b.generate_device(count, 0, 512, 512, 32, seed=0, planted=True)
+    gen = time.perf_counter() - t
+    for _ in range(3):
+        res = b.solve(eps=None, download=False, per_instance=False)
+    tot = res["total"]
+    print("cfg4", kind, count, "instances gen_s", round(gen, 3), {k_: tot[k_] for k_ in ("num_unassigned", "rounds", "bids", "bid_arcs",
+          "ms_solve")}, "Garcs/s", round(tot["bid_arcs"] / tot["ms_solve"] / 1e6, 3), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg1", "cfg3", "cfg2"]
     if "cfg1" in which:
@@ -43,6 +55,9 @@ if __name__ == "__main__":
             for p in s.round_profile():
                 b = 12 * p["arcs"] + 8 * p["bidders"]
                 print("  skip", skip, p, "bid GB/s", round(b / max(p["bid_ms"], 1e-6) / 1e6, 1) if p["engine"] == 0 else "-")
+    if "cfg4" in which:
+        run_cfg4("forward")
+        run_cfg4("khosla")
     if "cfg2" in which:
         run("cfg2 forward", S.ForwardAuctionSolver, 20000, 20000, 64, True, reps=3)
         run("cfg2 forward", S.ForwardAuctionSolver, 20000, 20000, 64, True, reps=2, options=dict(tail_max=256))

@@ -6,6 +6,7 @@ the bidding loop runs in hand-written sm_100a CUDA through the C ABI of `libsla_
 from ._lib import SlaError, build_library, load as load_library
 from .solver import AuctionSolution, AuctionSolver, ForwardAuctionSolver, KhoslaSolver
 from . import generators
+from .batch import BatchSolver
 
 __all__ = ["AuctionSolution", "AuctionSolver", "ForwardAuctionSolver", "KhoslaSolver", "SlaError", "build_library",
-           "load_library", "generators"]
+           "load_library", "generators", "BatchSolver"]

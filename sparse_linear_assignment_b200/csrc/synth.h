@@ -79,10 +79,10 @@ SLA_HD void make_row(const Spec& s, uint32_t row, uint32_t* out_cols, double* ou
         out_vals[t] = (double)(s.value_lo + below(draw(s.seed, 2, row, t), span));
 }
 
-inline uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
+SLA_HD uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
-// Host-side: fills perm_a / perm_b from the seed (perm_a coprime to num_rows => a bijection on [0, num_rows)).
-inline void finish_spec(Spec& s) {
+// Fills perm_a / perm_b from the seed (perm_a coprime to num_rows => a bijection on [0, num_rows)).
+SLA_HD void finish_spec(Spec& s) {
     s.perm_a = 1; s.perm_b = 0;
     if (!s.planted || s.num_rows == 0) return;
     uint64_t h = splitmix64(s.seed ^ 0xA5A5A5A5DEADBEEFull);
