@@ -120,6 +120,10 @@ int sla_upload_csr_device(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, co
  * cols/vals: num_rows*k). */
 int sla_generate_device(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed,
                         uint32_t value_lo, uint32_t value_hi, int planted);
+/* Rows [row_begin, row_begin + row_count) of the same global instance, for one rank of a row-partitioned solve. */
+int sla_generate_device_shard(sla_ctx *ctx, uint32_t global_rows, uint32_t num_cols, uint32_t k, uint64_t seed,
+                              uint32_t value_lo, uint32_t value_hi, int planted, uint32_t row_begin,
+                              uint32_t row_count);
 int sla_generate_host(uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed, uint32_t value_lo,
                       uint32_t value_hi, int planted, uint32_t *row_ptr, uint32_t *column_indices, double *values);
 
@@ -156,17 +160,22 @@ int sla_batch_solve(sla_ctx *ctx, int algo, int maximize, double eps, double sta
                     uint32_t *person_to_object, uint32_t *object_to_person, double *prices,
                     sla_stats *per_instance_stats /* num_instances entries or NULL */, sla_stats *total);
 
-/* ---- row-partitioned single instance (BASELINE.json config 5): this context holds persons
- *      [row_begin, row_begin + num_rows) of a global instance with `global_rows` persons; object state
- *      (prices, owners, packed best-bid words) is replicated on every rank.  One round is
- *          sla_part_bid   -> all-reduce(MAX) of the `best` words (and the price candidates) by the caller
- *          sla_part_assign-> applies the winners; returns this rank's next queue length.
- *      The caller (sparse_linear_assignment_b200.distributed) owns the collectives. ---- */
-int sla_part_begin(sla_ctx *ctx, int algo, int maximize, uint32_t row_begin, uint32_t global_rows, double eps,
-                   double global_w_min, double global_w_max);
+/* ---- row-partitioned single KhoslaSolver instance (BASELINE.json config 5): this context holds persons
+ *      [row_begin, row_begin + num_rows) of a global instance with `global_rows` persons (upload the shard with
+ *      sla_upload_csr / sla_generate_device first); object state (prices, owners, packed best-bid words) is
+ *      replicated on every rank.  One synchronous round is
+ *          sla_part_bid    -> all-reduce(MAX) of the best-bid words (uint64, bit 63 clear: valid as int64)
+ *          sla_part_claim  -> all-reduce(MAX) of the price candidates (f64, -inf = no bid)
+ *          sla_part_assign -> applies all winners to this rank's replica; returns this rank's next queue length.
+ *      The caller (sparse_linear_assignment_b200.distributed) owns the collectives and stops when the queue lengths
+ *      sum to zero.  global_w_min / global_w_max / global_first_value: min / max over all ranks of
+ *      sla_part_local_value_range, and rank 0's first value (sign normalisation, solver.rs:207-216). ---- */
 int sla_part_local_value_range(sla_ctx *ctx, double *w_min, double *w_max, double *first_value);
-int sla_part_bid(sla_ctx *ctx);
+int sla_part_begin(sla_ctx *ctx, int algo, int maximize, uint32_t row_begin, uint32_t global_rows, double eps,
+                   double global_w_min, double global_w_max, double global_first_value);
 int sla_part_buffers(sla_ctx *ctx, void **d_best_words, void **d_price_candidates, uint64_t *num_words);
+int sla_part_bid(sla_ctx *ctx);
+int sla_part_claim(sla_ctx *ctx);
 int sla_part_assign(sla_ctx *ctx, uint32_t *local_queue_len, uint32_t *local_dropped);
 int sla_part_finish(sla_ctx *ctx, uint32_t *person_to_object /* local rows */, uint32_t *object_to_person,
                     double *prices, sla_stats *stats);

@@ -96,6 +96,8 @@ SIGNATURES = {
     "sla_upload_csr_device": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint64]),
     "sla_generate_device": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32,
                                       C.c_int]),
+    "sla_generate_device_shard": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32,
+                                            C.c_int, C.c_uint32, C.c_uint32]),
     "sla_generate_host": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
                                     _vp, _vp, _vp]),
     "sla_khosla_solve": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp, _vp, C.POINTER(SlaStats)]),
@@ -111,7 +113,9 @@ SIGNATURES = {
                                             C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]),
     "sla_batch_solve": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_uint32, _vp, _vp, _vp,
                                   C.POINTER(SlaStats), C.POINTER(SlaStats)]),
-    "sla_part_begin": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double]),
+    "sla_part_begin": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double,
+                                 C.c_double]),
+    "sla_part_claim": (C.c_int, [_vp]),
     "sla_part_local_value_range": (C.c_int, [_vp, _f64p, _f64p, _f64p]),
     "sla_part_bid": (C.c_int, [_vp]),
     "sla_part_buffers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_uint64)]),

@@ -726,6 +726,23 @@ int sla_generate_device(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint
     return finish_csr(ctx, num_rows, num_cols, nnz);
 }
 
+int sla_generate_device_shard(sla_ctx* ctx, uint32_t global_rows, uint32_t num_cols, uint32_t k, uint64_t seed,
+                              uint32_t value_lo, uint32_t value_hi, int planted, uint32_t row_begin, uint32_t row_count) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (!row_count || (uint64_t)row_begin + row_count > global_rows) return fail(ctx, SLA_ERR_INVALID, "bad shard range");
+    const uint64_t nnz = (uint64_t)row_count * k;
+    int rc = check_shape(ctx, row_count, num_cols, nnz);
+    if (rc) return rc;
+    if (global_rows > num_cols) return fail(ctx, SLA_ERR_INVALID, "num_rows must be <= num_cols");
+    sla_synth::Spec s;
+    if ((rc = make_spec(ctx, &s, global_rows, num_cols, k, seed, value_lo, value_hi, planted))) return rc;
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = ensure_capacity(ctx, row_count, num_cols, nnz))) return rc;
+    generate_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(s, row_begin, row_count, ctx->d_row_ptr, ctx->d_cols,
+                                                                     ctx->d_vals);
+    return finish_csr(ctx, row_count, num_cols, nnz);
+}
+
 int sla_generate_host(uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed, uint32_t value_lo,
                       uint32_t value_hi, int planted, uint32_t* row_ptr, uint32_t* column_indices, double* values) {
     if (!row_ptr || !column_indices || !values) return SLA_ERR_INVALID;

@@ -21,8 +21,8 @@ enum : uint32_t { ALGO_KHOSLA = 0, ALGO_FORWARD = 1 };
 enum : uint32_t { ACTION_NONE = 0, ACTION_RESET = 1 };
 
 // Device-resident control block of one solve.  Only single threads write it (see the kernels).
-// The first 96 bytes are the fields every kernel needs at start-up; HotState mirrors them so that a kernel can
-// fetch them with six independent 128-bit loads (one L2 round trip instead of a chain of dependent ones).
+// The first 112 bytes are the fields every kernel needs at start-up; HotState mirrors them so that a kernel can
+// fetch them with seven independent 128-bit loads (one L2 round trip instead of a chain of dependent ones).
 struct DevState {
     // ---- hot (mirrored by HotState) ----
     uint32_t qlen[2];        // lengths of the two queue buffers
@@ -43,6 +43,8 @@ struct DevState {
     double threshold;        // Khosla price threshold (ksparse.rs:181)
     double target_eps;
     double tol;
+    uint32_t person_base;    // global id of local row 0 (row-partitioned instance; 0 otherwise)
+    uint32_t hot_pad[3];
     // ---- cold ----
     uint32_t nits;           // Forward: rounds (symmetric.rs:277); Khosla: filled from `bids` at the end
     uint32_t nreductions;
@@ -64,8 +66,9 @@ struct alignas(16) HotState {
     uint32_t n_rows, n_cols, start_opt, action;
     double eps, threshold;
     double target_eps, tol;
+    uint32_t person_base, hot_pad[3];
 };
-static_assert(sizeof(HotState) == 96, "HotState must mirror the first 96 bytes of DevState");
+static_assert(sizeof(HotState) == 112, "HotState must mirror the first 112 bytes of DevState");
 static_assert(sizeof(DevState) % 16 == 0, "DevState is copied as 128-bit words");
 
 __device__ __forceinline__ HotState load_hot(const DevState* st) {
@@ -73,7 +76,7 @@ __device__ __forceinline__ HotState load_hot(const DevState* st) {
     const uint4* src = reinterpret_cast<const uint4*>(st);
     uint4* dst = reinterpret_cast<uint4*>(&h);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) dst[i] = src[i];   // L1-cached: thousands of warps read the same 96 bytes (the L1 is
+    for (int i = 0; i < 7; ++i) dst[i] = src[i];   // L1-cached: thousands of warps read the same 96 bytes (the L1 is
                                                    // invalidated at every launch boundary, so the data is current)
     return h;
 }

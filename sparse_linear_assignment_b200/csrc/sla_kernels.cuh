@@ -19,7 +19,8 @@ namespace sla {
 template <int LPR, int MODE>
 __device__ __forceinline__ void bid_wide_body(const Params& p, const uint32_t qlen, const bool identity,
                                               const uint32_t* __restrict__ queue, const uint32_t algo, const double eps,
-                                              const double threshold, const uint32_t pbits, const uint32_t sign_flip) {
+                                              const double threshold, const uint32_t pbits, const uint32_t sign_flip,
+                                              const uint32_t person_base) {
     constexpr int GROUPS_PER_BLOCK = kWideThreads / LPR;
     const int lane = threadIdx.x % LPR;
     const uint32_t group = blockIdx.x * GROUPS_PER_BLOCK + threadIdx.x / LPR;
@@ -51,7 +52,7 @@ __device__ __forceinline__ void bid_wide_body(const Params& p, const uint32_t ql
             } else {
                 p.slot_obj[q] = r.obj;
                 p.slot_bid[q] = r.bid;
-                if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));   // NaN never bids
+                if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i + person_base, pbits));   // NaN never bids
             }
         }
     }
@@ -81,8 +82,8 @@ __global__ void __launch_bounds__(kWideThreads) bid_wide_kernel(const Params p) 
     const uint32_t algo = h.algo, pbits = h.pbits;
     const double eps = h.eps, thr = h.threshold;
     const uint32_t sf = h.sign_flip;
-    if (zero) bid_wide_body<LPR, PRICE_ZERO>(p, qlen, identity, cur ? p.queue[1] : p.queue[0], algo, eps, thr, pbits, sf);
-    else      bid_wide_body<LPR, PRICE_LDG>(p, qlen, identity, cur ? p.queue[1] : p.queue[0], algo, eps, thr, pbits, sf);
+    if (zero) bid_wide_body<LPR, PRICE_ZERO>(p, qlen, identity, cur ? p.queue[1] : p.queue[0], algo, eps, thr, pbits, sf, h.person_base);
+    else      bid_wide_body<LPR, PRICE_LDG>(p, qlen, identity, cur ? p.queue[1] : p.queue[0], algo, eps, thr, pbits, sf, h.person_base);
 }
 
 // Regular-CSR variant (every row has exactly K arcs, K % 8 == 0: all of BASELINE.json's configs): no row-extent
@@ -91,7 +92,7 @@ template <int LPR8, int MODE>
 __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t qlen, const bool identity,
                                                  const uint32_t* __restrict__ queue, const uint32_t algo, const double eps,
                                                  const double threshold, const uint32_t pbits, const uint32_t sign_flip,
-                                                 const uint32_t K) {
+                                                 const uint32_t K, const uint32_t person_base) {
     constexpr int GROUPS_PER_BLOCK = kWideThreads / LPR8;
     const int lane = threadIdx.x % LPR8;
     const uint32_t group = blockIdx.x * GROUPS_PER_BLOCK + threadIdx.x / LPR8;
@@ -121,7 +122,7 @@ __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t
             } else {
                 p.slot_obj[q] = r.obj;
                 p.slot_bid[q] = r.bid;
-                if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));
+                if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i + person_base, pbits));
             }
         }
     }
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kWideThreads, (MODE == PRICE_ZERO) ? 6 : 4) bi
     const uint32_t algo = h.algo, pbits = h.pbits, sf = h.sign_flip, K = h.regular_k;
     const double eps = h.eps, thr = h.threshold;
     const uint32_t* queue = cur ? p.queue[1] : p.queue[0];
-    bid_regular_body<LPR8, MODE>(p, qlen, identity, queue, algo, eps, thr, pbits, sf, K);
+    bid_regular_body<LPR8, MODE>(p, qlen, identity, queue, algo, eps, thr, pbits, sf, K, h.person_base);
 }
 
 // =============================================================================================================
