@@ -156,8 +156,9 @@ class PartitionedKhoslaSolver:
             p2o, o2p, prices, st = eng.finish()
             tot = torch.tensor([st["num_unassigned"], st["bids"], st["bid_arcs"]], dtype=torch.int64, device=dev)
             self._all_reduce(tot, dist.ReduceOp.SUM)
+            totals = [int(x) for x in tot.tolist()]      # read back on the engine's stream, behind the all-reduce
         st = dict(st)
-        st["global_num_unassigned"], st["global_bids"], st["global_bid_arcs"] = (int(x) for x in tot.tolist())
+        st["global_num_unassigned"], st["global_bids"], st["global_bid_arcs"] = totals
         st["row_begin"], st["global_rows"], st["rounds"] = row_begin, global_rows, self.rounds
         return dict(p2o=p2o, o2p=o2p, prices=prices, stats=st)
 
