@@ -132,6 +132,31 @@ __global__ void __launch_bounds__(kBatchThreads) batch_kernel(const BatchParams 
         while (true) {
             const bool small = qlen <= 32u;
             // ---- bidding phase ----
+            if (small) {
+                // one warp per bidder, several passes when there are more bidders than warps (<= 32 bidders)
+                for (uint32_t q = (uint32_t)warp; q < qlen; q += kBatchThreads / 32) {
+                    const uint32_t i = sq[q];
+                    const uint32_t a = __ldg(row_ptr + i), b = __ldg(row_ptr + i + 1);
+                    WarpChoice c;
+                    if (zero) c = warp_bid_scan<PRICE_ZERO, OWN_NONE>(p.cols, p.vals, s_prices, s_o2p, a, b, sign_flip, lane32);
+                    else      c = warp_bid_scan<PRICE_SMEM, OWN_SMEM>(p.cols, p.vals, s_prices, s_o2p, a, b, sign_flip, lane32);
+                    if (lane32 == 0) {
+                        uint32_t owner;
+                        const Bid r = zero ? make_bid_warp<PRICE_ZERO, OWN_NONE>(c, algo, eps, threshold, s_prices, s_o2p, &owner)
+                                           : make_bid_warp<PRICE_SMEM, OWN_SMEM>(c, algo, eps, threshold, s_prices, s_o2p, &owner);
+                        my_arcs += (unsigned long long)(b - a);
+                        if (r.dropped) {
+                            s_obj[q] = SLA_DEV_NONE;
+                            my_dropped += 1;
+                        } else {
+                            s_obj[q] = r.obj;
+                            s_bid[q] = r.bid;
+                            s_prev[q] = owner;
+                            s_word[q] = (r.bid == r.bid) ? pack_bid(r.bid, i, pbits) : 0ull;
+                        }
+                    }
+                }
+            } else {
             for (uint32_t base = 0; base < qlen; base += NGROUPS) {
                 if (base + (uint32_t)(warp * 32) / LPR >= qlen) break;   // warp-uniform: idle warps leave
                 const uint32_t q = base + group;
@@ -154,11 +179,10 @@ __global__ void __launch_bounds__(kBatchThreads) batch_kernel(const BatchParams 
                         s_obj[q] = r.obj;
                         s_bid[q] = r.bid;
                         s_prev[q] = s_o2p[r.obj];
-                        const bool is_bid = (r.bid == r.bid);
-                        if (small) s_word[q] = is_bid ? pack_bid(r.bid, i, pbits) : 0ull;
-                        else if (is_bid) atomicMax(s_best + r.obj, pack_bid(r.bid, i, pbits));
+                        if (r.bid == r.bid) atomicMax(s_best + r.obj, pack_bid(r.bid, i, pbits));
                     }
                 }
+            }
             }
             __syncthreads();
 

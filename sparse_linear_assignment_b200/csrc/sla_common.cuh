@@ -312,6 +312,79 @@ __device__ __forceinline__ void scan8(Choice& c, const uint32_t* __restrict__ co
     }
 }
 
+// ---- warp-per-bidder scan for the small rounds of the single-CTA engines ---------------------------------------
+// A whole warp scans one row (lane l takes arcs l, l+32, ...) and agrees on the choice with REDUX reductions on
+// order-preserving integer keys of the profits instead of a shuffle tree of f64 compares: the dependent chain is
+// five REDUX instructions whatever the row length.  Equivalent to the sequential choice rule: keys compare like the
+// f64 profits (-0.0 canonicalised to +0.0); NaN and -inf profits never pass the reference's strict '>' against the
+// initial -inf, so they get key 0 = "no arc"; ties go to the lowest arc position.
+struct WarpChoice {
+    double best, second, value, price;   // price = frozen price of the best column
+    uint32_t col, pos, owner;            // pos == SLA_DEV_NONE: no usable arc; owner = current owner of `col`
+};
+
+enum OwnerMode : int { OWN_NONE = 0, OWN_GLOBAL = 1, OWN_SMEM = 2 };
+
+__device__ __forceinline__ unsigned long long profit_key(double profit) {
+    profit += 0.0;
+    return (profit > neg_inf()) ? f64_order_key(profit) : 0ull;
+}
+__device__ __forceinline__ double key_profit(unsigned long long key) {
+    return key ? order_key_to_f64_host(key) : neg_inf();
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+    const uint32_t hi = __reduce_max_sync(0xffffffffu, (uint32_t)(k >> 32));
+    const uint32_t lo = __reduce_max_sync(0xffffffffu, ((uint32_t)(k >> 32) == hi) ? (uint32_t)k : 0u);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+template <int MODE, int OWN>
+__device__ __forceinline__ WarpChoice warp_bid_scan(const uint32_t* __restrict__ cols, const double* __restrict__ vals,
+                                                    const double* prices, const uint32_t* owners, uint32_t a, uint32_t b,
+                                                    uint32_t flip, int lane32) {
+    unsigned long long k1 = 0ull, k2 = 0ull;
+    uint32_t pos1 = SLA_DEV_NONE, col1 = 0u;
+    double val1 = neg_inf(), pr1 = 0.0;
+    for (uint32_t g = a + (uint32_t)lane32; g < b; g += 32u) {
+        const uint32_t col = __ldg(cols + g);
+        const double raw = __ldg(vals + g);
+        const double v = __hiloint2double(__double2hiint(raw) ^ (int)flip, __double2loint(raw));
+        const double pr = ld_price<MODE>(prices, col);
+        const unsigned long long key = profit_key((MODE == PRICE_ZERO) ? v : (v - pr));
+        const bool gt = key > k1, gs = key > k2;
+        k2 = gt ? k1 : (gs ? key : k2);
+        k1 = gt ? key : k1;
+        pos1 = gt ? g : pos1;
+        col1 = gt ? col : col1;
+        val1 = gt ? v : val1;
+        pr1 = gt ? pr : pr1;
+    }
+    // speculative: the current owner of this lane's best column, issued before the reductions so that its latency
+    // hides behind them (only the owning lane's value is used)
+    uint32_t own1 = SLA_DEV_NONE;
+    if (OWN == OWN_GLOBAL) { if (pos1 != SLA_DEV_NONE) own1 = ld_ca_u32(owners + col1); }
+    else if (OWN == OWN_SMEM) { if (pos1 != SLA_DEV_NONE) own1 = owners[col1]; }
+
+    const unsigned long long kmax = warp_max_u64(k1);
+    const bool is_max = (kmax != 0ull) && (k1 == kmax);
+    const uint32_t posmin = __reduce_min_sync(0xffffffffu, is_max ? pos1 : SLA_DEV_NONE);
+    const bool is_owner = is_max && (pos1 == posmin);
+    const uint32_t owner_ballot = __ballot_sync(0xffffffffu, is_owner);
+    const unsigned long long ksecond = warp_max_u64(is_owner ? k2 : k1);
+
+    WarpChoice r;
+    r.best = key_profit(kmax);
+    r.second = key_profit(ksecond);
+    r.pos = posmin;
+    const int src = owner_ballot ? (__ffs((int)owner_ballot) - 1) : 0;
+    r.value = __shfl_sync(0xffffffffu, val1, src);
+    r.price = __shfl_sync(0xffffffffu, pr1, src);
+    r.col = __shfl_sync(0xffffffffu, col1, src);
+    r.owner = __shfl_sync(0xffffffffu, own1, src);
+    if (!owner_ballot) { r.value = neg_inf(); r.price = 0.0; r.col = 0u; r.owner = SLA_DEV_NONE; r.pos = SLA_DEV_NONE; }
+    return r;
+}
+
 // Outcome of one person's bid: object (SLA_DEV_NONE = dropped by the Khosla threshold) and exact bid.
 struct Bid {
     uint32_t obj;
@@ -329,6 +402,32 @@ __device__ __forceinline__ Bid make_bid(const Choice& c, uint32_t algo, double e
     r.dropped = false;
     if (algo == ALGO_KHOSLA) {
         const double pj = ld_price<MODE>(prices, r.obj);
+        if (pj > threshold) { r.dropped = true; r.bid = 0.0; return r; }
+        r.bid = is_finite_f64(c.second) ? (c.value - c.second + eps) : (pj + eps);
+    } else {
+        r.bid = c.value - c.second + eps;
+    }
+    return r;
+}
+
+
+// Bid from a WarpChoice (same expressions as make_bid): Khosla ksparse.rs:218-227, Forward symmetric.rs:378.
+template <int MODE, int OWN>
+__device__ __forceinline__ Bid make_bid_warp(const WarpChoice& c, uint32_t algo, double eps, double threshold,
+                                             const double* prices, const uint32_t* owners, uint32_t* owner_out) {
+    Bid r;
+    r.dropped = false;
+    double pj = c.price;
+    uint32_t own = c.owner;
+    if (c.pos == SLA_DEV_NONE) {   // row without a usable arc: the reference stays on object 0 (ksparse.rs:196, symmetric.rs:355)
+        r.obj = 0u;
+        pj = ld_price<MODE>(prices, 0u);
+        own = (OWN == OWN_GLOBAL) ? ld_ca_u32(owners) : ((OWN == OWN_SMEM) ? owners[0] : SLA_DEV_NONE);
+    } else {
+        r.obj = c.col;
+    }
+    *owner_out = own;
+    if (algo == ALGO_KHOSLA) {
         if (pj > threshold) { r.dropped = true; r.bid = 0.0; return r; }
         r.bid = is_finite_f64(c.second) ? (c.value - c.second + eps) : (pj + eps);
     } else {

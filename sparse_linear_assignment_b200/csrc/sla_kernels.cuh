@@ -368,6 +368,35 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
 #endif
         // ---- bidding phase ----
         const uint32_t* sq = s_queue[buf];
+        if (small) {
+            // one warp per bidder: REDUX reductions on integer profit keys (sla_common.cuh: warp_bid_scan)
+            if ((uint32_t)warp < qlen) {
+                const uint32_t q = (uint32_t)warp;
+                const uint32_t i = sq[q];
+                uint32_t a, b;
+                if (regK) { a = i * regK; b = a + regK; }
+                else { a = __ldg(p.row_ptr + i); b = __ldg(p.row_ptr + i + 1); }
+                WarpChoice c;
+                if (zero) c = warp_bid_scan<PRICE_ZERO, OWN_NONE>(p.cols, p.vals, price_src, p.o2p, a, b, sign_flip, lane32);
+                else      c = warp_bid_scan<kPriceMode, OWN_GLOBAL>(p.cols, p.vals, price_src, p.o2p, a, b, sign_flip, lane32);
+                TK(tk_scan);
+                if (lane32 == 0) {
+                    uint32_t owner;
+                    const Bid r = zero ? make_bid_warp<PRICE_ZERO, OWN_NONE>(c, algo, eps, thr, price_src, p.o2p, &owner)
+                                       : make_bid_warp<kPriceMode, OWN_GLOBAL>(c, algo, eps, thr, price_src, p.o2p, &owner);
+                    my_arcs += (unsigned long long)(b - a);
+                    if (r.dropped) {
+                        s_obj[q] = SLA_DEV_NONE;
+                        my_dropped += 1;
+                    } else {
+                        s_obj[q] = r.obj;
+                        s_bid[q] = r.bid;
+                        s_prev[q] = owner;
+                        s_word[q] = (r.bid == r.bid) ? pack_bid(r.bid, i, pbits) : 0ull;   // NaN never bids
+                    }
+                }
+            }
+        } else {
         for (uint32_t base = 0; base < qlen; base += NGROUPS) {
             // warps none of whose groups has a bidder leave (warp-uniform, so the full-mask shuffles stay legal):
             // idle warps must not burn issue slots on the reduction while one or two warps do the real work
@@ -384,11 +413,9 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
             choice_init(c);
             if (zero) scan_row<LPR, PRICE_ZERO, false>(c, p.cols, p.vals, price_src, a, b, sign_flip, lane);
             else      scan_row<LPR, kPriceMode, false>(c, p.cols, p.vals, price_src, a, b, sign_flip, lane);
-            TK(tk_scan);
             choice_group_reduce<LPR>(c);
             // current owner of the chosen object (nobody owns anything while all prices are still zero)
             if (valid && lane == 0 && !zero) c.aux = ld_ca_u32(p.o2p + ((c.pos == SLA_DEV_NONE) ? 0u : c.col));
-            TK(tk_red);
             if (valid && lane == 0) {
                 const Bid r = zero ? make_bid<PRICE_ZERO>(c, algo, eps, thr, price_src)
                                    : make_bid<kPriceMode>(c, algo, eps, thr, price_src);
@@ -399,15 +426,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                 } else {
                     s_obj[q] = r.obj;
                     s_bid[q] = r.bid;
-                    const bool is_bid = (r.bid == r.bid);   // NaN never bids
                     s_prev[q] = c.aux;                      // owner of r.obj (only the winner uses it)
-                    if (small) {
-                        s_word[q] = is_bid ? pack_bid(r.bid, i, pbits) : 0ull;
-                    } else if (is_bid) {
-                        atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));
-                    }
+                    if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));   // NaN never bids
                 }
             }
+        }
         }
         TK(tk_bid);
         __syncthreads();

@@ -339,3 +339,48 @@ def test_cfg3_khosla_1Mx4M_k16(sla, oracle):
     st = dev.solve_resident(False, None)
     assert st["bid_arcs"] == solver.last_stats["bid_arcs"] and st["num_unassigned"] == 0
     assert dev.device_objective() == o.get_objective()
+
+
+# ---- edge cases of the reference's input space ------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_edge_cases_match_model_and_oracle(sla, oracle, kind, cls_name):
+    rng = np.random.default_rng(77)
+    cases = {}
+    # one person, one object
+    cases["1x1"] = (1, 1, np.array([0, 1], dtype=np.uint32), np.array([0], dtype=np.uint32), np.array([5.0]))
+    # all weights equal: every comparison is a tie (lowest row position / lowest person id must win)
+    n = 40
+    cases["all_ties"] = (n, n, np.arange(0, n * n + 1, n, dtype=np.uint32), np.tile(np.arange(n, dtype=np.uint32), n),
+                         np.full(n * n, 7.0))
+    # duplicate column indices inside a row (the builder does not forbid them, solver.rs:41-101)
+    rp = np.arange(0, 30 * 6 + 1, 6, dtype=np.uint32)
+    c = rng.integers(0, 45, size=30 * 6).astype(np.uint32)
+    c[::6] = np.arange(30, dtype=np.uint32)                     # keep a perfect matching available
+    cases["duplicate_columns"] = (30, 45, rp, c, rng.integers(1, 50, size=30 * 6).astype(np.float64))
+    # negative weights, maximise
+    r2, c2, v2 = random_sparse_instance(rng, 64, 80, 9, integer=True, lo=-500, hi=-1)
+    cases["negative_maximize"] = (64, 80, r2, c2, v2)
+    # long rows: 200 arcs per person (several 128-bit chunks per lane, 32 lanes per row)
+    r3, c3, v3 = random_sparse_instance(rng, 50, 400, 200, integer=True, lo=0, hi=10_000)
+    cases["long_rows"] = (50, 400, r3, c3, v3)
+    # dense 64 x 64
+    cases["dense64"] = (64, 64, np.arange(0, 64 * 64 + 1, 64, dtype=np.uint32), np.tile(np.arange(64, dtype=np.uint32), 64),
+                        rng.integers(0, 1000, size=64 * 64).astype(np.float64))
+    # huge magnitudes next to tiny ones (f64 bids far from the 32-bit range)
+    r4, c4, v4 = random_sparse_instance(rng, 33, 50, 5, integer=True, lo=1, hi=9)
+    cases["wide_dynamic_range"] = (33, 50, r4, c4, v4 * np.where(rng.random(v4.size) < 0.5, 1e9, 1.0))
+    for name, (n, m, rp, c, v) in cases.items():
+        maximize = name == "negative_maximize"
+        eps = 1.0 / (m + 1)
+        solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v, maximize=maximize, eps=eps)
+        assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v, maximize=maximize, eps=eps)
+        o = oracle.OracleSolver(kind, n, m, len(c))
+        o.load_csr(n, m, rp, c, v)
+        o.solve(maximize=maximize, eps=eps)
+        assert z.num_unassigned == o.num_unassigned, name
+        if z.num_unassigned == 0 and name != "wide_dynamic_range":
+            assert solver.get_objective(z) == o.get_objective(), name
+        if z.num_unassigned == 0 and name == "wide_dynamic_range":
+            assert abs(solver.get_objective(z) - o.get_objective()) <= n * eps + 1e-6, name
+        if name != "duplicate_columns":
+            check_matching(n, m, rp, c, z.person_to_object, z.object_to_person, z.num_unassigned)
