@@ -109,6 +109,13 @@ int sla_set_option(sla_ctx *ctx, const char *key, int64_t value);
 int sla_upload_csr(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *row_ptr,
                    const uint32_t *column_indices, const double *values, uint64_t nnz);
 
+/* sla_upload_csr preceded by the in-place negation of the HOST `values` that AuctionSolver::init_solve performs
+ * (solver.rs:214-216) when `maximize ^ (values[0] >= 0)`; the negation runs on `threads` host threads chunk by chunk and
+ * is pipelined with the upload of the finished chunks (the O(nnz) host pass hides behind the PCIe copy).  The device
+ * then holds the normalised values, so the following solve reports values_negated == 0. */
+int sla_upload_csr_negating(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *row_ptr,
+                            const uint32_t *column_indices, double *values, uint64_t nnz, int threads);
+
 /* Same, source arrays already in device memory (device-side generators, multi-GPU shards). */
 int sla_upload_csr_device(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *d_row_ptr,
                           const uint32_t *d_column_indices, const double *d_values, uint64_t nnz);

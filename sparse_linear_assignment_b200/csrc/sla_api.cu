@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -683,6 +684,49 @@ int sla_upload_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uin
     CU(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_cols, column_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_vals, values, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return finish_csr(ctx, num_rows, num_cols, nnz);
+}
+
+// Same as sla_upload_csr, but first applies the in-place sign normalisation of AuctionSolver::init_solve
+// (reference src/solver.rs:214-216) to the HOST values, pipelined with their upload: worker threads negate the
+// array chunk by chunk while the copy engine uploads the chunks that are already done, so the O(nnz) host pass the
+// reference performs inside solve() hides behind the PCIe transfer.  The device then holds the normalised values.
+int sla_upload_csr_negating(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* row_ptr,
+                            const uint32_t* column_indices, double* values, uint64_t nnz, int threads) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (!row_ptr || !column_indices || !values) return fail(ctx, SLA_ERR_INVALID, "null input array");
+    int rc = check_shape(ctx, num_rows, num_cols, nnz);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_cols, column_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t chunk = (size_t)1 << 20;   // 8 MB of f64 per pipeline stage
+    const size_t n_chunks = ((size_t)nnz + chunk - 1) / chunk;
+    if (threads < 1) threads = 1;
+    if (threads > 32) threads = 32;
+    if ((size_t)threads > n_chunks) threads = (int)n_chunks;
+    std::vector<std::atomic<int>> ready(n_chunks);
+    for (auto& r : ready) r.store(0, std::memory_order_relaxed);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([&, t]() {
+            for (size_t c = (size_t)t; c < n_chunks; c += (size_t)threads) {
+                const size_t lo = c * chunk, hi = (lo + chunk < (size_t)nnz) ? lo + chunk : (size_t)nnz;
+                for (size_t i = lo; i < hi; ++i) values[i] = -values[i];
+                ready[c].store(1, std::memory_order_release);
+            }
+        });
+    }
+    cudaError_t copy_err = cudaSuccess;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        while (!ready[c].load(std::memory_order_acquire)) std::this_thread::yield();
+        const size_t lo = c * chunk, hi = (lo + chunk < (size_t)nnz) ? lo + chunk : (size_t)nnz;
+        if (copy_err == cudaSuccess)
+            copy_err = cudaMemcpyAsync(ctx->d_vals + lo, values + lo, (hi - lo) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    for (auto& th : pool) th.join();
+    if (copy_err != cudaSuccess) return fail(ctx, SLA_ERR_CUDA, std::string("cudaMemcpyAsync(values): ") + cudaGetErrorString(copy_err));
     return finish_csr(ctx, num_rows, num_cols, nnz);
 }
 

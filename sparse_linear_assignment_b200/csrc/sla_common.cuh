@@ -186,7 +186,15 @@ enum PriceMode : int {
 template <int MODE>
 __device__ __forceinline__ double ld_price(const double* prices, uint32_t j) {
     if (MODE == PRICE_ZERO) return 0.0;
-    if (MODE == PRICE_LDG) return __ldg(prices + j);
+    if (MODE == PRICE_LDG) {
+#ifdef SLA_PRICE_NA
+        double r;
+        asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(prices + j));
+        return r;
+#else
+        return __ldg(prices + j);
+#endif
+    }
     if (MODE == PRICE_CA) return ld_ca_f64(prices + j);
     if (MODE == PRICE_SMEM) return prices[j];
     return __ldcg(prices + j);

@@ -151,7 +151,10 @@ __global__ void __launch_bounds__(kWideThreads, (MODE == PRICE_ZERO) ? 6 : 4) bi
 // winner that evicts -> the evicted owner, winner of a free object or dropped person -> nothing).
 // =============================================================================================================
 constexpr int kAssignChunk = 2048;   // queue slots one block stages before it reserves output space
-constexpr int kAssignUnroll = 4;     // slots per thread whose dependent loads are issued together
+#ifndef SLA_ASSIGN_UNROLL
+#define SLA_ASSIGN_UNROLL 4
+#endif
+constexpr int kAssignUnroll = SLA_ASSIGN_UNROLL;   // slots per thread whose dependent loads are issued together
 
 __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params p) {
     DevState* st = p.st;

@@ -395,16 +395,25 @@ class AuctionSolver:
         ctx = self._context()
         _lib.check(ctx, _lib.load().sla_set_option(ctx, key.encode(), int(value)))
 
-    def _sync_device(self):
+    def _sync_device(self, maximize=None):
+        """Mirrors the host CSR into HBM when it changed.  With `maximize` given (the solve paths), a pending in-place
+        sign normalisation of `values` (solver.rs:209-216) is applied to the host copy while it is being uploaded
+        (sla_upload_csr_negating), so the reference's O(nnz) host pass overlaps the PCIe transfer."""
         ctx = self._context()
         if self._dirty:
             n, nnz = self._num_rows, self.num_of_arcs()
             row_ptr = np.ascontiguousarray(self._i_starts_stops.view[: n + 1], dtype=np.uint32)
             cols = np.ascontiguousarray(self._column_indices.view, dtype=np.uint32)
-            vals = np.ascontiguousarray(self._values.view, dtype=np.float64)
+            vals = self._values.view
             _ensure(row_ptr.size == n + 1, "fewer rows populated than num_rows")
-            _lib.check(ctx, _lib.load().sla_upload_csr(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
-                                                       vals.ctypes.data, nnz))
+            flip = maximize is not None and (bool(maximize) ^ bool((vals[0] if vals.size else 0.0) >= 0.0))
+            if flip and vals.size >= (1 << 16):
+                rc = _lib.load().sla_upload_csr_negating(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
+                                                         vals.ctypes.data, nnz, min(8, os.cpu_count() or 1))
+            else:
+                rc = _lib.load().sla_upload_csr(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
+                                                vals.ctypes.data, nnz)
+            _lib.check(ctx, rc)
             self._dirty = False
         return ctx
 
@@ -523,7 +532,7 @@ class KhoslaSolver(AuctionSolver):
         """ksparse.rs:153-251"""
         if not self._device_only:
             self.validate_input()
-        ctx = self._sync_device()
+        ctx = self._sync_device(maximize)
         p2o, o2p = self._outputs(solution)
         st = SlaStats()
         neg = self._begin_negation(maximize)
@@ -557,7 +566,7 @@ class ForwardAuctionSolver(AuctionSolver):
         """symmetric.rs:217-332"""
         if not self._device_only:
             self.validate_input()
-        ctx = self._sync_device()
+        ctx = self._sync_device(maximize)
         p2o, o2p = self._outputs(solution)
         # Some(0) behaves like Some(1) in the reference (the check runs after the first round, symmetric.rs:326)
         self.max_iterations = max(int(max_iterations), 1) if max_iterations is not None else self.MAX_ITERATIONS
