@@ -407,7 +407,8 @@ class AuctionSolver:
             vals = self._values.view
             _ensure(row_ptr.size == n + 1, "fewer rows populated than num_rows")
             flip = maximize is not None and (bool(maximize) ^ bool((vals[0] if vals.size else 0.0) >= 0.0))
-            if flip and vals.size >= (1 << 16):
+            self._pre_negated = bool(flip and vals.size >= (1 << 16))
+            if self._pre_negated:
                 rc = _lib.load().sla_upload_csr_negating(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
                                                          vals.ctypes.data, nnz, min(8, os.cpu_count() or 1))
             else:
@@ -447,6 +448,9 @@ class AuctionSolver:
         solution.eps = float(stats.eps)
         self.nits = int(stats.nits)
         self.last_stats = stats.as_dict()
+        if getattr(self, "_pre_negated", False):     # the normalisation already happened during the upload of this solve
+            self.last_stats["values_negated"] = 1
+            self._pre_negated = False
 
     def _outputs(self, solution: AuctionSolution):
         """Output buffers: the caller's solution vectors are reused when they already have the right shape (the
