@@ -109,10 +109,11 @@ int sla_set_option(sla_ctx *ctx, const char *key, int64_t value);
 int sla_upload_csr(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *row_ptr,
                    const uint32_t *column_indices, const double *values, uint64_t nnz);
 
-/* sla_upload_csr preceded by the in-place negation of the HOST `values` that AuctionSolver::init_solve performs
- * (solver.rs:214-216) when `maximize ^ (values[0] >= 0)`; the negation runs on `threads` host threads chunk by chunk and
- * is pipelined with the upload of the finished chunks (the O(nnz) host pass hides behind the PCIe copy).  The device
- * then holds the normalised values, so the following solve reports values_negated == 0. */
+/* sla_upload_csr plus the in-place negation of the HOST `values` that AuctionSolver::init_solve performs
+ * (solver.rs:214-216) when `maximize ^ (values[0] >= 0)`: `values` crosses PCIe first; once that copy has completed,
+ * `threads` host threads negate the array while the column indices are still being uploaded and the solve runs.
+ * They are joined before the next sla_*_solve / upload / destroy on this context returns.  The device keeps the
+ * original values: the following solve still reports values_negated == 1, and the host must not negate again. */
 int sla_upload_csr_negating(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *row_ptr,
                             const uint32_t *column_indices, double *values, uint64_t nnz, int threads);
 

@@ -86,12 +86,25 @@ struct sla_ctx {
     int grid_wide = 0;
 
     std::vector<sla_round_profile> profile;
+    std::vector<std::thread> workers;      // host threads still negating the caller's `values` (sla_upload_csr_negating)
+    cudaEvent_t ev_vals_copied = nullptr;
 
     sla_batch_state* batch = nullptr;
     sla_part_state* part = nullptr;
 };
 
 namespace {
+
+void join_workers(sla_ctx* c) {
+    for (auto& th : c->workers)
+        if (th.joinable()) th.join();
+    c->workers.clear();
+}
+
+struct WorkerJoinGuard {   // whatever path leaves a solve, the caller's host arrays are quiescent afterwards
+    sla_ctx* c;
+    ~WorkerJoinGuard() { if (c) join_workers(c); }
+};
 
 int fail(sla_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
@@ -302,6 +315,7 @@ int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz)
 int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double start_eps_in, uint32_t max_iterations,
                  uint32_t* h_p2o, uint32_t* h_o2p, double* h_prices, sla_stats* stats) {
     if (!ctx) return SLA_ERR_INVALID;
+    WorkerJoinGuard join_guard{ctx};
     if (!ctx->has_csr) return fail(ctx, SLA_ERR_STATE, "solve called before a CSR was uploaded");
     CU(cudaSetDevice(ctx->device));
     const bool forward = (algo == SLA_ALGO_FORWARD);
@@ -584,6 +598,7 @@ int sla_ctx_create(int device, size_t row_capacity, size_t col_capacity, size_t 
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_vals_copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMallocHost((void**)&ctx->h_state, sizeof(DevState))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_csr_stats, sizeof(DevCsrStats))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_scratch, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -623,8 +638,10 @@ void sla_part_free(sla_ctx* ctx);
 
 void sla_ctx_destroy(sla_ctx* ctx) {
     if (!ctx) return;
+    join_workers(ctx);
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_vals_copied) cudaEventDestroy(ctx->ev_vals_copied);
     sla_batch_free(ctx);
     sla_part_free(ctx);
     drop_graphs(ctx);
@@ -677,6 +694,7 @@ int sla_upload_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uin
                    const uint32_t* column_indices, const double* values, uint64_t nnz) {
     if (!ctx) return SLA_ERR_INVALID;
     if (!row_ptr || !column_indices || !values) return fail(ctx, SLA_ERR_INVALID, "null input array");
+    join_workers(ctx);
     int rc = check_shape(ctx, num_rows, num_cols, nnz);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
@@ -687,47 +705,42 @@ int sla_upload_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uin
     return finish_csr(ctx, num_rows, num_cols, nnz);
 }
 
-// Same as sla_upload_csr, but first applies the in-place sign normalisation of AuctionSolver::init_solve
-// (reference src/solver.rs:214-216) to the HOST values, pipelined with their upload: worker threads negate the
-// array chunk by chunk while the copy engine uploads the chunks that are already done, so the O(nnz) host pass the
-// reference performs inside solve() hides behind the PCIe transfer.  The device then holds the normalised values.
+// Same as sla_upload_csr, plus the in-place sign normalisation of AuctionSolver::init_solve (reference
+// src/solver.rs:214-216) on the HOST values: `values` is uploaded first; as soon as that copy has completed, worker
+// threads negate the host array while the column indices are still crossing PCIe and the solve runs.  The workers
+// are joined before the next solve / upload / destroy call on this context returns, so the caller observes the
+// negated values when solve() returns -- exactly the reference's post-condition.  The device holds the ORIGINAL values
+// (the following solve reports values_negated == 1 as usual; the host must then not negate again).
 int sla_upload_csr_negating(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* row_ptr,
                             const uint32_t* column_indices, double* values, uint64_t nnz, int threads) {
     if (!ctx) return SLA_ERR_INVALID;
     if (!row_ptr || !column_indices || !values) return fail(ctx, SLA_ERR_INVALID, "null input array");
+    join_workers(ctx);
     int rc = check_shape(ctx, num_rows, num_cols, nnz);
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_vals, values, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_vals_copied, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_cols, column_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-    const size_t chunk = (size_t)1 << 20;   // 8 MB of f64 per pipeline stage
-    const size_t n_chunks = ((size_t)nnz + chunk - 1) / chunk;
     if (threads < 1) threads = 1;
     if (threads > 32) threads = 32;
-    if ((size_t)threads > n_chunks) threads = (int)n_chunks;
-    std::vector<std::atomic<int>> ready(n_chunks);
-    for (auto& r : ready) r.store(0, std::memory_order_relaxed);
-    std::vector<std::thread> pool;
+    const size_t total = (size_t)nnz, per = (total + (size_t)threads - 1) / (size_t)threads;
+    cudaEvent_t ev = ctx->ev_vals_copied;
+    const int device = ctx->device;
     for (int t = 0; t < threads; ++t) {
-        pool.emplace_back([&, t]() {
-            for (size_t c = (size_t)t; c < n_chunks; c += (size_t)threads) {
-                const size_t lo = c * chunk, hi = (lo + chunk < (size_t)nnz) ? lo + chunk : (size_t)nnz;
-                for (size_t i = lo; i < hi; ++i) values[i] = -values[i];
-                ready[c].store(1, std::memory_order_release);
-            }
+        const size_t lo = (size_t)t * per, hi = lo + per < total ? lo + per : total;
+        if (lo >= hi) break;
+        ctx->workers.emplace_back([values, lo, hi, ev, device]() {
+            cudaSetDevice(device);
+            cudaEventSynchronize(ev);          // the DMA engine has finished reading `values`
+            for (size_t i = lo; i < hi; ++i) values[i] = -values[i];
         });
     }
-    cudaError_t copy_err = cudaSuccess;
-    for (size_t c = 0; c < n_chunks; ++c) {
-        while (!ready[c].load(std::memory_order_acquire)) std::this_thread::yield();
-        const size_t lo = c * chunk, hi = (lo + chunk < (size_t)nnz) ? lo + chunk : (size_t)nnz;
-        if (copy_err == cudaSuccess)
-            copy_err = cudaMemcpyAsync(ctx->d_vals + lo, values + lo, (hi - lo) * 8, cudaMemcpyHostToDevice, ctx->stream);
-    }
-    for (auto& th : pool) th.join();
-    if (copy_err != cudaSuccess) return fail(ctx, SLA_ERR_CUDA, std::string("cudaMemcpyAsync(values): ") + cudaGetErrorString(copy_err));
-    return finish_csr(ctx, num_rows, num_cols, nnz);
+    rc = finish_csr(ctx, num_rows, num_cols, nnz);
+    if (rc) join_workers(ctx);
+    return rc;
 }
 
 int sla_upload_csr_device(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* d_row_ptr,

@@ -397,8 +397,8 @@ class AuctionSolver:
 
     def _sync_device(self, maximize=None):
         """Mirrors the host CSR into HBM when it changed.  With `maximize` given (the solve paths), a pending in-place
-        sign normalisation of `values` (solver.rs:209-216) is applied to the host copy while it is being uploaded
-        (sla_upload_csr_negating), so the reference's O(nnz) host pass overlaps the PCIe transfer."""
+        sign normalisation of `values` (solver.rs:209-216) is started on the library's worker threads as soon as the
+        values have crossed PCIe (sla_upload_csr_negating), overlapping the rest of the upload and the solve."""
         ctx = self._context()
         if self._dirty:
             n, nnz = self._num_rows, self.num_of_arcs()
@@ -410,7 +410,7 @@ class AuctionSolver:
             self._pre_negated = bool(flip and vals.size >= (1 << 16))
             if self._pre_negated:
                 rc = _lib.load().sla_upload_csr_negating(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
-                                                         vals.ctypes.data, nnz, min(8, os.cpu_count() or 1))
+                                                         vals.ctypes.data, nnz, min(16, os.cpu_count() or 1))
             else:
                 rc = _lib.load().sla_upload_csr(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
                                                 vals.ctypes.data, nnz)
@@ -423,13 +423,17 @@ class AuctionSolver:
         the GPU solves (the device applies the same sign on the fly).  Returns (thread or None, flip)."""
         if self._device_only:
             return None, None
+        if getattr(self, "_pre_negated", False):
+            # the upload of this very solve already started the negation on the library's worker threads
+            # (sla_upload_csr_negating); they are joined inside the solve call
+            return None, True
         vals = self._values.view
         flip = bool(maximize) ^ bool((vals[0] if vals.size else 0.0) >= 0.0)
         if not flip:
             return None, False
         lib = _lib.load()
         th = threading.Thread(target=lib.sla_host_negate_f64,
-                              args=(vals.ctypes.data, vals.size, min(8, os.cpu_count() or 1)))
+                              args=(vals.ctypes.data, vals.size, min(16, os.cpu_count() or 1)))
         th.start()
         return th, True
 
@@ -439,6 +443,7 @@ class AuctionSolver:
             th.join()
         if flip is not None and bool(stats.values_negated) != flip:
             raise SlaError(_lib.SLA_ERR_STATE, "host / device disagree on the sign normalisation of values")
+        self._pre_negated = False
         if self.index_dtype == np.dtype(np.uint32):
             solution.person_to_object, solution.object_to_person = p2o, o2p
         else:   # SLA_NONE truncates to u16::MAX
@@ -448,9 +453,6 @@ class AuctionSolver:
         solution.eps = float(stats.eps)
         self.nits = int(stats.nits)
         self.last_stats = stats.as_dict()
-        if getattr(self, "_pre_negated", False):     # the normalisation already happened during the upload of this solve
-            self.last_stats["values_negated"] = 1
-            self._pre_negated = False
 
     def _outputs(self, solution: AuctionSolution):
         """Output buffers: the caller's solution vectors are reused when they already have the right shape (the
