@@ -10,7 +10,15 @@
 
 namespace sla {
 
-constexpr int kBatchThreads = 256;
+// 128 threads and >= 8 CTAs per SM measured best on cfg4 (profiles/README.md): every CTA is a latency-bound chain of
+// rounds, so the SM needs many co-resident instances to keep its issue slots busy.
+#ifndef SLA_BATCH_THREADS
+#define SLA_BATCH_THREADS 128
+#endif
+#ifndef SLA_BATCH_MINBLOCKS
+#define SLA_BATCH_MINBLOCKS 8
+#endif
+constexpr int kBatchThreads = SLA_BATCH_THREADS;
 
 struct DevInstStats {   // per-instance result scalars (expanded into sla_stats on the host)
     uint32_t num_unassigned, nits, nreductions, optimal;
@@ -44,7 +52,7 @@ __device__ __forceinline__ double batch_toleration(double c) {
 }
 
 template <int LPR>
-__global__ void __launch_bounds__(kBatchThreads) batch_kernel(const BatchParams p) {
+__global__ void __launch_bounds__(kBatchThreads, SLA_BATCH_MINBLOCKS) batch_kernel(const BatchParams p) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     // ---- shared-memory carve-up (sizes from the largest instance of the batch) ----
     double* s_prices = reinterpret_cast<double*>(s_dyn);                                   // max_cols
