@@ -29,6 +29,6 @@ for (cls, name), sp in itertools.product(((S.ForwardAuctionSolver, "forward"), (
     lib.sla_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     out = (C.c_uint64 * 8)()
     lib.sla_debug_counters(solver._context(), out)
-    tot, scan, red, bar1, asg, bar2, rounds, bid = [out[i] for i in range(8)]
+    tot, scan, _, bar1, asg, bar2, rounds, bid = [out[i] for i in range(8)]
     print(name, "ms", st["ms_solve"], "tail rounds", rounds, "cycles/round", tot / max(rounds, 1),
-          {k: round(v / max(rounds, 1), 1) for k, v in dict(scan=scan, reduce=red, bid=bid, bar1=bar1, assign=asg, bar2=bar2).items()})
+          {k: round(v / max(rounds, 1), 1) for k, v in dict(scan_and_reduce=scan, bid=bid, bar1=bar1, assign=asg, bar2=bar2).items()})

@@ -186,15 +186,7 @@ enum PriceMode : int {
 template <int MODE>
 __device__ __forceinline__ double ld_price(const double* prices, uint32_t j) {
     if (MODE == PRICE_ZERO) return 0.0;
-    if (MODE == PRICE_LDG) {
-#ifdef SLA_PRICE_NA
-        double r;
-        asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(prices + j));
-        return r;
-#else
-        return __ldg(prices + j);
-#endif
-    }
+    if (MODE == PRICE_LDG) return __ldg(prices + j);   // L1-allocating on purpose: no_allocate gathers measured 1.6x slower
     if (MODE == PRICE_CA) return ld_ca_f64(prices + j);
     if (MODE == PRICE_SMEM) return prices[j];
     return __ldcg(prices + j);
@@ -207,7 +199,7 @@ struct Choice {
     double value;    // edge value of the best arc
     uint32_t pos;    // global arc index of the best arc (lowest index wins ties) or SLA_DEV_NONE
     uint32_t col;    // its column
-    uint32_t aux;    // single-CTA engines: current owner of that column, gathered together with its price
+    uint32_t aux;    // single-CTA engines: current owner of the chosen column, filled in after the reduction
 };
 
 __device__ __forceinline__ void choice_init(Choice& c) {
@@ -263,12 +255,9 @@ __device__ __forceinline__ void choice_group_reduce(Choice& c) {
 // in bounds.  `flip` is 0 or 0x80000000 (sign normalisation of solver.rs:209-216 applied on the fly).
 // STREAM: the CSR is read once per kernel (wide rounds) -> do not allocate in L1; otherwise (persistent single-CTA
 // engines, where the same persons bid again and again) let the rows live in L1.
-// OWNER: also gather the current owner of every scanned column (o2p, coherent L1 loads) so that the eviction
-// victim of the best column is known without a further dependent memory round trip.
-template <int LPR, int MODE, bool STREAM = true, bool OWNER = false>
+template <int LPR, int MODE, bool STREAM = true>
 __device__ __forceinline__ void scan_row(Choice& c, const uint32_t* __restrict__ cols, const double* __restrict__ vals,
-                                         const double* prices, uint32_t a, uint32_t b, uint32_t flip, int lane,
-                                         const uint32_t* o2p = nullptr) {
+                                         const double* prices, uint32_t a, uint32_t b, uint32_t flip, int lane) {
     for (uint32_t base = (a & ~3u) + 4u * (uint32_t)lane; base < b; base += 4u * LPR) {
         uint4 cj;
         double2 v01, v23;
@@ -284,20 +273,18 @@ __device__ __forceinline__ void scan_row(Choice& c, const uint32_t* __restrict__
         const uint32_t jj[4] = {cj.x, cj.y, cj.z, cj.w};
         double vv[4] = {v01.x, v01.y, v23.x, v23.y};
         double pr[4];
-        uint32_t ow[4];
         bool ok[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const uint32_t g = base + t;
             ok[t] = (g >= a) && (g < b);
             pr[t] = ok[t] ? ld_price<MODE>(prices, jj[t]) : 0.0;
-            ow[t] = (OWNER && MODE != PRICE_ZERO && ok[t]) ? ld_ca_u32(o2p + jj[t]) : SLA_DEV_NONE;
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const double v = __hiloint2double(__double2hiint(vv[t]) ^ (int)flip, __double2loint(vv[t]));
             // arcs outside [a, b) get profit -inf, which never passes the strict '>' tests
-            choice_update(c, ok[t] ? (v - pr[t]) : neg_inf(), v, base + t, jj[t], ow[t]);
+            choice_update(c, ok[t] ? (v - pr[t]) : neg_inf(), v, base + t, jj[t]);
         }
     }
 }

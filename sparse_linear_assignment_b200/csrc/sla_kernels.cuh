@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     bool hit_limit = false;
 
 #ifdef SLA_TAIL_TIMING
-    long long tk0 = clock64(), tk_scan = 0, tk_red = 0, tk_bid = 0, tk_bar1 = 0, tk_asg = 0, tk_bar2 = 0, tk1, tk2;
+    long long tk0 = clock64(), tk_scan = 0, tk_bid = 0, tk_bar1 = 0, tk_asg = 0, tk_bar2 = 0, tk1, tk2;
 #define TK(acc) do { tk2 = clock64(); acc += tk2 - tk1; tk1 = tk2; } while (0)
 #else
 #define TK(acc) do { } while (0)
@@ -555,7 +555,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
 #ifdef SLA_TAIL_TIMING
         st->dbg[0] += (unsigned long long)(clock64() - tk0);
         st->dbg[1] += (unsigned long long)tk_scan;
-        st->dbg[2] += (unsigned long long)tk_red;
         st->dbg[3] += (unsigned long long)tk_bar1;
         st->dbg[4] += (unsigned long long)tk_asg;
         st->dbg[5] += (unsigned long long)tk_bar2;
