@@ -65,9 +65,9 @@ public:
     virtual ~AuctionSolver() { if (ctx_) sla_ctx_destroy(ctx_); }
     // #[derive(Clone)]: deep copy of the host state; the device context is re-created lazily
     AuctionSolver(const AuctionSolver& o)
-        : num_rows_(o.num_rows_), num_cols_(o.num_cols_), prices_(o.prices_), i_starts_stops_(o.i_starts_stops_),
-          j_counts_(o.j_counts_), column_indices_(o.column_indices_), values_(o.values_), nits(o.nits),
-          device_(o.device_), caps_(o.caps_) {}
+        : nits(o.nits), num_rows_(o.num_rows_), num_cols_(o.num_cols_), prices_(o.prices_),
+          i_starts_stops_(o.i_starts_stops_), j_counts_(o.j_counts_), column_indices_(o.column_indices_),
+          values_(o.values_), device_(o.device_), caps_(o.caps_) {}
     AuctionSolver& operator=(const AuctionSolver&) = delete;
 
     // accessors (solver.rs:22-38); the *_mut twins mark the device mirror stale
