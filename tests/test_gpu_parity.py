@@ -384,3 +384,22 @@ def test_edge_cases_match_model_and_oracle(sla, oracle, kind, cls_name):
             assert abs(solver.get_objective(z) - o.get_objective()) <= n * eps + 1e-6, name
         if name != "duplicate_columns":
             check_matching(n, m, rp, c, z.person_to_object, z.object_to_person, z.num_unassigned)
+
+
+# ---- randomized sweep: shapes, degrees, float / integer weights, maximise / minimise, explicit / default eps -----------
+def test_randomized_sweep_matches_model(sla, oracle):
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        kind, cls_name = SOLVERS[trial % 2]
+        n = int(rng.integers(1, 700))
+        m = n if (kind == "forward" and trial % 3) else n + int(rng.integers(0, 500))
+        kmax = int(min(m, rng.integers(1, 70)))
+        rp, c, v = ragged_instance(rng, n, m, 1 if trial % 7 == 0 and kind == "khosla" else min(2, kmax), max(kmax, min(2, m)),
+                                   integer=bool(trial % 4))
+        if trial % 5 == 0:
+            v = -v - 1.0                                         # all-negative weights
+        maximize = bool(trial % 3 == 0)
+        eps = None if trial % 2 else float(rng.uniform(1e-4, 0.5))
+        solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v, maximize=maximize, eps=eps)
+        assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v, maximize=maximize, eps=eps)
+        check_matching(n, m, rp, c, z.person_to_object, z.object_to_person, z.num_unassigned)
