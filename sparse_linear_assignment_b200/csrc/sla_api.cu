@@ -27,6 +27,7 @@ struct GraphSlot {
     int super_rounds = 0;
     uint32_t regular_k = 0;
     bool smem_prices = false;
+    bool tail_only = false;
 };
 
 }  // namespace
@@ -245,9 +246,13 @@ void launch_one(sla_ctx* c, const Params& p, int which, bool zero_first = false)
     }
 }
 
-void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_first) {
-    launch_one(c, p, 0, zero_first);
-    launch_one(c, p, 1);
+// tail_only: the instance has at most tail_max persons, so the queue can never be long enough for the wide pair --
+// leave those two (no-op) launches out of the super-round.
+void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_first, bool tail_only) {
+    if (!tail_only) {
+        launch_one(c, p, 0, zero_first);
+        launch_one(c, p, 1);
+    }
     launch_one(c, p, 2);
     if (forward) {
         launch_one(c, p, 3);
@@ -255,13 +260,22 @@ void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_fir
     }
 }
 
-int kernels_per_super_round(bool forward) { return forward ? 5 : 3; }
+int kernels_per_super_round(bool forward, bool tail_only) { return (forward ? 5 : 3) - (tail_only ? 2 : 0); }
+
+bool is_tail_only(const sla_ctx* c) { return c->n_rows <= (uint32_t)c->opt_tail_max; }
+
+// Khosla on a tail-only instance finishes inside the first tail launch: further super-rounds would be pure no-ops.
+int super_rounds_for(const sla_ctx* c, bool forward) {
+    return (!forward && is_tail_only(c)) ? 1 : c->opt_super_rounds;
+}
 
 int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out) {
     GraphSlot& g = ctx->graphs[(forward ? 2 : 0) + (zero_first ? 1 : 0)];
     const uint32_t reg_key = use_regular(ctx) ? ctx->regular_k : 0u;
-    if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == ctx->opt_super_rounds &&
-        g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices) {
+    const bool tail_only = is_tail_only(ctx);
+    const int n_super = super_rounds_for(ctx, forward);
+    if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == n_super &&
+        g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices && g.tail_only == tail_only) {
         *out = g.exec;
         return SLA_OK;
     }
@@ -269,7 +283,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     const Params p = make_params(ctx);
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    for (int r = 0; r < ctx->opt_super_rounds; ++r) launch_super_round(ctx, p, forward, zero_first && r == 0);
+    for (int r = 0; r < n_super; ++r) launch_super_round(ctx, p, forward, zero_first && r == 0, tail_only);
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (e != cudaSuccess) return fail(ctx, SLA_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
     e = cudaGraphInstantiate(&g.exec, graph, 0);
@@ -280,7 +294,8 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     }
     g.generation = ctx->generation;
     g.lpr = ctx->lpr;
-    g.super_rounds = ctx->opt_super_rounds;
+    g.super_rounds = n_super;
+    g.tail_only = tail_only;
     g.regular_k = reg_key;
     g.smem_prices = ctx->tail_smem_prices;
     *out = g.exec;
@@ -400,7 +415,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
             first = false;
             CU(cudaGraphLaunch(exec, ctx->stream));
             graph_launches += 1;
-            launches += (uint32_t)(ctx->opt_super_rounds * kernels_per_super_round(forward));
+            launches += (uint32_t)(super_rounds_for(ctx, forward) * kernels_per_super_round(forward, is_tail_only(ctx)));
             if ((rc = poll_state(ctx))) return rc;
             done = ctx->h_state->done != 0;
             if (!done && timed_out()) return fail(ctx, SLA_ERR_STATE, "solve exceeded the wall-clock guard (timeout_s)");

@@ -432,6 +432,9 @@ class AuctionSolver:
         if not flip:
             return None, False
         lib = _lib.load()
+        if vals.size < (1 << 16):      # too small to be worth a helper thread: negate right here
+            lib.sla_host_negate_f64(vals.ctypes.data, vals.size, 1)
+            return None, True
         th = threading.Thread(target=lib.sla_host_negate_f64,
                               args=(vals.ctypes.data, vals.size, min(16, os.cpu_count() or 1)))
         th.start()
