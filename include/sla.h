@@ -187,6 +187,14 @@ int sla_part_claim(sla_ctx *ctx);
 int sla_part_assign(sla_ctx *ctx, uint32_t *local_queue_len, uint32_t *local_dropped);
 int sla_part_finish(sla_ctx *ctx, uint32_t *person_to_object /* local rows */, uint32_t *object_to_person,
                     double *prices, sla_stats *stats);
+/* Sparse exchange (same rounds, same results): instead of all-reducing one word per OBJECT, the ranks all-gather the
+ * lists of their local winners (3 x int64 per entry: object, packed word, bits of the exact f64 bid):
+ *     sla_part_bid -> sla_part_collect (local winners -> send list, local losers re-queue; returns the count)
+ *     all_gather(counts) ; all_gather(send[: 3 * max_count]) into recv        [caller]
+ *     sla_part_apply_sparse (global maximum per object over all lists, winners applied to the replica). */
+int sla_part_sparse_buffers(sla_ctx *ctx, int world, void **d_send, void **d_recv, void **d_counts, uint64_t *send_capacity);
+int sla_part_collect(sla_ctx *ctx, uint32_t *local_winners);
+int sla_part_apply_sparse(sla_ctx *ctx, int world, uint32_t max_count, uint32_t *local_queue_len, uint32_t *local_dropped);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,5 @@
 """torchrun target: one KhoslaSolver instance row-partitioned over the ranks (NCCL), generated shard by shard in HBM.
-    torchrun --nproc-per-node N scripts/run_partitioned.py ROWS COLS K [check]
+    torchrun --nproc-per-node N scripts/run_partitioned.py ROWS COLS K [dense|sparse] [check]
 Rank 0 prints one JSON line; with `check` the same instance is also solved on rank 0 alone and compared."""
 import json
 import os
@@ -16,7 +16,8 @@ from sparse_linear_assignment_b200 import _lib
 from sparse_linear_assignment_b200.distributed import CudaShardEngine, PartitionedKhoslaSolver, shard_rows
 
 rows, cols, k = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-check = len(sys.argv) > 4
+exchange = sys.argv[4] if len(sys.argv) > 4 else "dense"
+check = len(sys.argv) > 5
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
@@ -27,7 +28,7 @@ ctx = solver._context()
 _lib.check(ctx, _lib.load().sla_generate_device_shard(ctx, rows, cols, k, 1, 300, 1000, 0, begin, count))
 solver._num_rows, solver._num_cols, solver._dirty, solver._device_only = count, cols, False, True
 eng = CudaShardEngine(solver)
-drv = PartitionedKhoslaSolver(eng)
+drv = PartitionedKhoslaSolver(eng, exchange=exchange)
 times = []
 for rep in range(3):
     if world > 1:
@@ -38,7 +39,7 @@ for rep in range(3):
     torch.cuda.synchronize()
     times.append(time.perf_counter() - t)
 st = res["stats"]
-out = {"world": world, "rows": rows, "cols": cols, "k": k, "rounds": st["rounds"], "bid_arcs": st["global_bid_arcs"],
+out = {"exchange": exchange, "world": world, "rows": rows, "cols": cols, "k": k, "rounds": st["rounds"], "bid_arcs": st["global_bid_arcs"],
        "unassigned": st["global_num_unassigned"], "solve_ms": [round(x * 1e3, 3) for x in times],
        "bid_arcs_per_s": st["global_bid_arcs"] / min(times)}
 if check and rank == 0:

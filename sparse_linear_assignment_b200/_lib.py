@@ -122,6 +122,9 @@ SIGNATURES = {
     "sla_part_buffers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_uint64)]),
     "sla_part_assign": (C.c_int, [_vp, _u32p, _u32p]),
     "sla_part_finish": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(SlaStats)]),
+    "sla_part_sparse_buffers": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_uint64)]),
+    "sla_part_collect": (C.c_int, [_vp, _u32p]),
+    "sla_part_apply_sparse": (C.c_int, [_vp, C.c_int, C.c_uint32, _u32p, _u32p]),
 }
 
 _lib = None

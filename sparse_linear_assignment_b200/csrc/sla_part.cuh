@@ -93,6 +93,127 @@ __global__ void __launch_bounds__(kWideThreads) part_apply_kernel(const Params p
     }
 }
 
+// ---- sparse exchange: ranks trade the lists of their local winners instead of all-reducing M words -------------------
+// Entry layout (3 x int64, all-gathered as one tensor): { object, packed word, bits of the exact f64 bid }.
+
+// Local winners (their word is the local maximum of their object) are appended to the send list and their word is
+// cleared again; local losers can never win globally and go straight back to the local queue.
+__global__ void __launch_bounds__(kWideThreads) part_collect_kernel(const Params p, long long* __restrict__ send,
+                                                                    uint32_t* __restrict__ send_count) {
+    DevState* st = p.st;
+    const HotState h = load_hot(st);
+    const uint32_t cur = h.cur;
+    const uint32_t qlen = h.qlen[cur & 1u];
+    if (qlen == 0) return;
+    const bool identity = h.identity != 0;
+    const uint32_t* __restrict__ queue = cur ? p.queue[1] : p.queue[0];
+    uint32_t* __restrict__ next_queue = cur ? p.queue[0] : p.queue[1];
+    uint32_t* next_len = &st->qlen[(cur ^ 1u) & 1u];
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (qlen + stride - 1) / stride;
+    for (uint32_t it = 0; it < rounds; ++it) {
+        const uint32_t q = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t emit = SLA_DEV_NONE, obj = SLA_DEV_NONE;
+        unsigned long long word = 0ull;
+        double bid = 0.0;
+        bool win = false;
+        if (q < qlen) {
+            const uint32_t j = p.slot_obj[q];
+            if (j != SLA_DEV_NONE) {
+                const uint32_t i = identity ? q : __ldg(queue + q);
+                bid = p.slot_bid[q];
+                word = pack_bid(bid, i + h.person_base, h.pbits);
+                win = (bid == bid) && (__ldcg(p.best + j) == word);
+                if (win) { obj = j; p.best[j] = 0ull; }
+                else emit = i;
+            }
+        }
+        const uint32_t wb = __ballot_sync(0xffffffffu, win);
+        if (wb) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(send_count, (uint32_t)__popc(wb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (win) {
+                long long* e = send + 3ull * (base + __popc(wb & ((1u << lane) - 1u)));
+                e[0] = (long long)obj;
+                e[1] = (long long)word;
+                e[2] = __double_as_longlong(bid);
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
+        if (ballot) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(next_len, (uint32_t)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (emit != SLA_DEV_NONE) next_queue[base + __popc(ballot & ((1u << lane) - 1u))] = emit;
+        }
+    }
+}
+
+// Pass 1 over every rank's winners: global maximum word per object.
+__global__ void __launch_bounds__(kWideThreads) part_sparse_max_kernel(const Params p, const long long* __restrict__ recv,
+                                                                       const long long* __restrict__ counts, const uint32_t world,
+                                                                       const uint32_t max_count) {
+    const unsigned long long total = (unsigned long long)world * max_count;
+    for (unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; f < total;
+         f += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(f / max_count), e = (uint32_t)(f % max_count);
+        if ((long long)e >= counts[r]) continue;
+        const long long* ent = recv + 3ull * f;
+        atomicMax(p.best + (uint32_t)ent[0], (unsigned long long)ent[1]);
+    }
+}
+
+// Pass 2: the global winner of each object is applied to this rank's replica; local persons that lost re-queue.
+__global__ void __launch_bounds__(kWideThreads) part_sparse_apply_kernel(const Params p, const long long* __restrict__ recv,
+                                                                         const long long* __restrict__ counts, const uint32_t world,
+                                                                         const uint32_t max_count, const uint32_t row_begin,
+                                                                         const uint32_t n_local) {
+    DevState* st = p.st;
+    const HotState h = load_hot(st);
+    uint32_t* __restrict__ next_queue = h.cur ? p.queue[0] : p.queue[1];
+    uint32_t* next_len = &st->qlen[(h.cur ^ 1u) & 1u];
+    const unsigned long long pmask = (1ull << h.pbits) - 1ull;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long total = (unsigned long long)world * max_count;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long rounds = (total + stride - 1) / stride;
+    for (unsigned long long it = 0; it < rounds; ++it) {
+        const unsigned long long f = it * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t emit = SLA_DEV_NONE;
+        if (f < total) {
+            const uint32_t r = (uint32_t)(f / max_count), e = (uint32_t)(f % max_count);
+            if ((long long)e < counts[r]) {
+                const long long* ent = recv + 3ull * f;
+                const uint32_t j = (uint32_t)ent[0];
+                const unsigned long long w = (unsigned long long)ent[1];
+                const uint32_t person = (uint32_t)(pmask - (w & pmask));
+                if (__ldcg(p.best + j) == w) {
+                    const uint32_t prev = p.o2p[j];
+                    p.prices[j] = __longlong_as_double(ent[2]);
+                    p.o2p[j] = person;
+                    p.best[j] = 0ull;   // losers comparing later see 0 or this word: neither equals theirs
+                    if (person - row_begin < n_local) p.p2o[person - row_begin] = j;
+                    if (prev != SLA_DEV_NONE && prev - row_begin < n_local) {
+                        p.p2o[prev - row_begin] = SLA_DEV_NONE;
+                        emit = prev - row_begin;
+                    }
+                } else if (person - row_begin < n_local) {
+                    emit = person - row_begin;
+                }
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
+        if (ballot) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(next_len, (uint32_t)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (emit != SLA_DEV_NONE) next_queue[base + __popc(ballot & ((1u << lane) - 1u))] = emit;
+        }
+    }
+}
+
 // Round bookkeeping after the apply sweep (one thread).
 __global__ void part_control_kernel(const Params p) {
     DevState* st = p.st;
@@ -117,6 +238,12 @@ __global__ void __launch_bounds__(kWideThreads) part_clear_kernel(double* cand, 
 struct sla_part_state {
     double* d_cand = nullptr;   // exact f64 bid of the winner per object, -inf = no bid (all-reduced with MAX)
     size_t cap_cols = 0;
+    // sparse exchange
+    long long* d_send = nullptr;      // 3 x int64 per local winner
+    long long* d_recv = nullptr;      // world x max_count entries
+    long long* d_counts = nullptr;    // winners per rank (all-gathered by the caller), world entries
+    uint32_t* d_send_count = nullptr;
+    size_t cap_send = 0, cap_recv = 0, cap_world = 0;
     uint32_t row_begin = 0, global_rows = 0;
     bool active = false, first_round = true;
     double eps = 0.0;
@@ -129,6 +256,7 @@ extern "C" {
 void sla_part_free(sla_ctx* ctx) {
     if (!ctx || !ctx->part) return;
     cudaFree(ctx->part->d_cand);
+    cudaFree(ctx->part->d_send); cudaFree(ctx->part->d_recv); cudaFree(ctx->part->d_counts); cudaFree(ctx->part->d_send_count);
     delete ctx->part;
     ctx->part = nullptr;
 }
@@ -278,6 +406,76 @@ int sla_part_finish(sla_ctx* ctx, uint32_t* person_to_object, uint32_t* object_t
     ctx->part->active = false;
     ctx->has_solution = true;
     ctx->best_dirty = false;
+    return SLA_OK;
+}
+
+// ---- sparse exchange entry points ----
+int sla_part_sparse_buffers(sla_ctx* ctx, int world, void** d_send, void** d_recv, void** d_counts, uint64_t* send_capacity) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (!ctx->part || !ctx->part->active) return fail(ctx, SLA_ERR_STATE, "sla_part_begin has not been called");
+    if (world < 1) return fail(ctx, SLA_ERR_INVALID, "world must be >= 1");
+    CU(cudaSetDevice(ctx->device));
+    sla_part_state* ps = ctx->part;
+    int rc;
+    // every rank may send up to the largest shard (shards differ by at most one row): size by that bound
+    const size_t cap = (size_t)(ps->global_rows + (uint32_t)world - 1) / (size_t)world + 1;
+    if (cap > ps->cap_send) {
+        if ((rc = dev_alloc(ctx, &ps->d_send, 3 * cap))) return rc;
+        ps->cap_send = cap;
+    }
+    if ((size_t)world * cap > ps->cap_recv) {
+        if ((rc = dev_alloc(ctx, &ps->d_recv, 3 * (size_t)world * cap))) return rc;
+        ps->cap_recv = (size_t)world * cap;
+    }
+    if ((size_t)world > ps->cap_world) {
+        if ((rc = dev_alloc(ctx, &ps->d_counts, (size_t)world))) return rc;
+        ps->cap_world = (size_t)world;
+    }
+    if (!ps->d_send_count && (rc = dev_alloc(ctx, &ps->d_send_count, 4))) return rc;
+    if (d_send) *d_send = ps->d_send;
+    if (d_recv) *d_recv = ps->d_recv;
+    if (d_counts) *d_counts = ps->d_counts;
+    if (send_capacity) *send_capacity = ps->cap_send;
+    return SLA_OK;
+}
+
+int sla_part_collect(sla_ctx* ctx, uint32_t* local_winners) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (!ctx->part || !ctx->part->active || !ctx->part->d_send) return fail(ctx, SLA_ERR_STATE, "sla_part_sparse_buffers has not been called");
+    CU(cudaSetDevice(ctx->device));
+    const Params p = make_params(ctx);
+    sla_part_state* ps = ctx->part;
+    CU(cudaMemsetAsync(ps->d_send_count, 0, sizeof(uint32_t), ctx->stream));
+    part_collect_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, ps->d_send, ps->d_send_count);
+    CU(cudaMemcpyAsync(ctx->h_scratch, ps->d_send_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    ps->launches += 1;
+    if (local_winners) *local_winners = ctx->h_scratch[0];
+    return SLA_OK;
+}
+
+int sla_part_apply_sparse(sla_ctx* ctx, int world, uint32_t max_count, uint32_t* local_queue_len, uint32_t* local_dropped) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (!ctx->part || !ctx->part->active || !ctx->part->d_recv) return fail(ctx, SLA_ERR_STATE, "sla_part_sparse_buffers has not been called");
+    if ((size_t)world * max_count > ctx->part->cap_recv) return fail(ctx, SLA_ERR_INVALID, "gathered list exceeds the receive buffer");
+    CU(cudaSetDevice(ctx->device));
+    const Params p = make_params(ctx);
+    sla_part_state* ps = ctx->part;
+    if (max_count) {
+        part_sparse_max_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, ps->d_recv, ps->d_counts, (uint32_t)world, max_count);
+        part_sparse_apply_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, ps->d_recv, ps->d_counts, (uint32_t)world, max_count,
+                                                                                  ps->row_begin, ctx->n_rows);
+        ps->launches += 2;
+    }
+    part_control_kernel<<<1, 1, 0, ctx->stream>>>(p);
+    ps->launches += 1;
+    int rc = poll_state(ctx);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    const DevState& f = *ctx->h_state;
+    if (local_queue_len) *local_queue_len = f.qlen[f.cur & 1u];
+    if (local_dropped) *local_dropped = f.dropped;
     return SLA_OK;
 }
 

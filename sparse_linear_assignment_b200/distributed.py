@@ -92,6 +92,34 @@ class CudaShardEngine:
     def candidates(self) -> torch.Tensor:
         return self._cand
 
+    # ---- sparse exchange ----
+    def sparse_setup(self, world: int):
+        send, recv, counts, cap = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+        _lib.check(self.ctx, self.lib.sla_part_sparse_buffers(self.ctx, world, C.byref(send), C.byref(recv), C.byref(counts),
+                                                              C.byref(cap)))
+        self._send = torch.as_tensor(_DevBuf(send.value, 3 * cap.value, "<i8"), device=self.device)
+        self._recv = torch.as_tensor(_DevBuf(recv.value, 3 * cap.value * world, "<i8"), device=self.device)
+        self._counts = torch.as_tensor(_DevBuf(counts.value, world, "<i8"), device=self.device)
+
+    def collect(self) -> int:
+        n = C.c_uint32()
+        _lib.check(self.ctx, self.lib.sla_part_collect(self.ctx, C.byref(n)))
+        return n.value
+
+    def send_list(self) -> torch.Tensor:
+        return self._send
+
+    def recv_lists(self) -> torch.Tensor:
+        return self._recv
+
+    def counts(self) -> torch.Tensor:
+        return self._counts
+
+    def apply_sparse(self, world: int, max_count: int):
+        q, d = C.c_uint32(), C.c_uint32()
+        _lib.check(self.ctx, self.lib.sla_part_apply_sparse(self.ctx, world, max_count, C.byref(q), C.byref(d)))
+        return q.value, d.value
+
     def finish(self):
         n, m = self.num_local_rows, self.num_cols
         p2o = np.empty(n, dtype=np.uint32)
@@ -109,9 +137,11 @@ class CudaShardEngine:
 class PartitionedKhoslaSolver:
     """Drives one row-partitioned solve; `engine` is this rank's shard (CudaShardEngine or a test model)."""
 
-    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None, exchange: str = "dense"):
+        assert exchange in ("dense", "sparse")
         self.engine = engine
         self.group = group
+        self.exchange = exchange
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.rounds = 0
@@ -142,12 +172,17 @@ class PartitionedKhoslaSolver:
 
             self.rounds = 0
             qlen = torch.zeros(1, dtype=torch.int64, device=dev)
+            if self.exchange == "sparse":
+                eng.sparse_setup(self.world)
             while self.rounds < max_rounds:
                 eng.bid()
-                self._all_reduce(eng.words(), dist.ReduceOp.MAX)
-                eng.claim()
-                self._all_reduce(eng.candidates(), dist.ReduceOp.MAX)
-                local_q, _ = eng.assign()
+                if self.exchange == "dense":
+                    self._all_reduce(eng.words(), dist.ReduceOp.MAX)
+                    eng.claim()
+                    self._all_reduce(eng.candidates(), dist.ReduceOp.MAX)
+                    local_q, _ = eng.assign()
+                else:
+                    local_q = self._sparse_round(eng, dev)
                 self.rounds += 1
                 qlen[0] = local_q
                 self._all_reduce(qlen, dist.ReduceOp.SUM)
@@ -161,6 +196,32 @@ class PartitionedKhoslaSolver:
         st["global_num_unassigned"], st["global_bids"], st["global_bid_arcs"] = totals
         st["row_begin"], st["global_rows"], st["rounds"] = row_begin, global_rows, self.rounds
         return dict(p2o=p2o, o2p=o2p, prices=prices, stats=st)
+
+
+def _sparse_round(self, eng, dev):
+    """One round of the sparse exchange: all-gather the per-rank winner counts, then the padded winner lists."""
+    cnt = eng.collect()
+    counts = eng.counts()
+    mine = torch.tensor([cnt], dtype=torch.int64, device=dev)
+    if self.world > 1:
+        dist.all_gather(list(counts.view(self.world, 1).unbind(0)), mine, group=self.group)
+    else:
+        counts.copy_(mine)
+    maxc = int(counts.max().item())
+    if maxc > 0:
+        send, recv = eng.send_list()[: 3 * maxc], eng.recv_lists()[: 3 * maxc * self.world]
+        if self.world > 1:
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_gather_into_tensor(recv, send, group=self.group)
+            else:
+                dist.all_gather(list(recv.view(self.world, 3 * maxc).unbind(0)), send, group=self.group)
+        else:
+            recv.copy_(send)
+    local_q, _ = eng.apply_sparse(self.world, maxc)
+    return local_q
+
+
+PartitionedKhoslaSolver._sparse_round = _sparse_round
 
 
 class _NullCtx:

@@ -109,6 +109,69 @@ class ModelShardEngine:
         self.rounds += 1
         return len(self.queue), self.dropped
 
+    # ---- sparse exchange (same interface as CudaShardEngine) ----
+    def sparse_setup(self, world):
+        cap = (self.global_rows + world - 1) // world + 1
+        self._send = torch.zeros(3 * cap, dtype=torch.int64)
+        self._recv = torch.zeros(3 * cap * world, dtype=torch.int64)
+        self._counts_t = torch.zeros(world, dtype=torch.int64)
+
+    def send_list(self):
+        return self._send
+
+    def recv_lists(self):
+        return self._recv
+
+    def counts(self):
+        return self._counts_t
+
+    def collect(self):
+        w = self._words.numpy()
+        send = self._send.numpy()
+        self.next_queue = []
+        n = 0
+        for i, j, bid in self.slots:
+            if j == NONE:
+                continue
+            word = self.O.pack_bid(bid, i + self.row_begin, self.pbits) if bid == bid else 0
+            if bid == bid and int(w[j]) == word:
+                send[3 * n:3 * n + 3] = (j, word, np.float64(bid).view(np.int64))
+                n += 1
+            else:
+                self.next_queue.append(i)
+        for i, j, bid in self.slots:
+            if j != NONE:
+                w[j] = 0
+        return n
+
+    def apply_sparse(self, world, maxc):
+        w = self._words.numpy()
+        recv = self._recv.numpy()
+        cnt = self._counts_t.numpy()
+        pmask = (1 << self.pbits) - 1
+        entries = [tuple(int(x) for x in recv[3 * (r * maxc + e):3 * (r * maxc + e) + 3]) for r in range(world) for e in range(int(cnt[r]))]
+        for j, word, _ in entries:
+            if word > w[j]:
+                w[j] = word
+        for j, word, bits in entries:
+            person = pmask - (word & pmask)
+            if int(w[j]) == word:
+                prev = int(self.o2p[j])
+                self.prices[j] = np.int64(bits).view(np.float64)
+                self.o2p[j] = person
+                if 0 <= person - self.row_begin < self.n:
+                    self.p2o[person - self.row_begin] = j
+                if prev != NONE and 0 <= prev - self.row_begin < self.n:
+                    self.p2o[prev - self.row_begin] = NONE
+                    self.next_queue.append(prev - self.row_begin)
+            elif 0 <= person - self.row_begin < self.n:
+                self.next_queue.append(person - self.row_begin)
+        for j, _, _ in entries:
+            w[j] = 0
+        self.queue = self.next_queue
+        self.rounds += 1
+        return len(self.queue), self.dropped
+
     def finish(self):
         st = dict(num_unassigned=self.dropped, nits=self.bids, bids=self.bids, bid_arcs=self.arcs, rounds=self.rounds,
                   dropped=self.dropped, eps=self.eps, values_negated=int(self.flip))

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _worker(rank, world, port, seed, n, m, k, maximize, out_dir):
+def _worker(rank, world, port, seed, n, m, k, maximize, out_dir, exchange):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -29,19 +29,20 @@ def _worker(rank, world, port, seed, n, m, k, maximize, out_dir):
     begin, count = shard_rows(n, world, rank)
     a, b = int(rp[begin]), int(rp[begin + count])
     eng = ModelShardEngine(O, m, rp[begin:begin + count + 1].astype(np.int64) - a, c[a:b], v[a:b])
-    res = PartitionedKhoslaSolver(eng).solve(maximize=maximize, eps=1.0 / (m + 1))
+    res = PartitionedKhoslaSolver(eng, exchange=exchange).solve(maximize=maximize, eps=1.0 / (m + 1))
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), p2o=res["p2o"], o2p=res["o2p"], prices=res["prices"],
              row_begin=res["stats"]["row_begin"], rounds=res["stats"]["rounds"], bids=res["stats"]["global_bids"],
              arcs=res["stats"]["global_bid_arcs"], unassigned=res["stats"]["global_num_unassigned"])
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,seed,maximize", [(2, 0, False), (2, 1, True), (3, 2, False)])
-def test_partitioned_driver_equals_single_instance_model(oracle, tmp_path, world, seed, maximize):
+@pytest.mark.parametrize("world,seed,maximize,exchange", [(2, 0, False, "dense"), (2, 1, True, "dense"), (3, 2, False, "dense"),
+                                                          (2, 3, False, "sparse"), (3, 4, True, "sparse")])
+def test_partitioned_driver_equals_single_instance_model(oracle, tmp_path, world, seed, maximize, exchange):
     from helpers import random_sparse_instance
     n, m, k = 61, 90, 5
     port = 29600 + seed
-    mp.spawn(_worker, args=(world, port, seed, n, m, k, maximize, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, seed, n, m, k, maximize, str(tmp_path), exchange), nprocs=world, join=True)
     rng = np.random.default_rng(seed)
     rp, c, v = random_sparse_instance(rng, n, m, k, integer=True, lo=1, hi=200)
     ref = oracle.jacobi_model("khosla", n, m, rp, c, v, maximize=maximize, eps=1.0 / (m + 1))
