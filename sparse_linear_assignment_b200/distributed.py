@@ -120,14 +120,18 @@ class CudaShardEngine:
         _lib.check(self.ctx, self.lib.sla_part_apply_sparse(self.ctx, world, max_count, C.byref(q), C.byref(d)))
         return q.value, d.value
 
-    def finish(self):
+    def finish(self, download: bool = True):
+        """Ends the solve; with download=False the local person_to_object slice and the replicated object_to_person /
+        prices stay resident in HBM (fetch them later with solver.download_solution)."""
         n, m = self.num_local_rows, self.num_cols
-        p2o = np.empty(n, dtype=np.uint32)
-        o2p = np.empty(m, dtype=np.uint32)
-        prices = np.empty(m, dtype=np.float64)
+        p2o = o2p = prices = None
+        if download:
+            from .solver import host_array
+            p2o, o2p, prices = host_array(n, np.uint32), host_array(m, np.uint32), host_array(m, np.float64)
         st = SlaStats()
-        _lib.check(self.ctx, self.lib.sla_part_finish(self.ctx, p2o.ctypes.data, o2p.ctypes.data, prices.ctypes.data,
-                                                      C.byref(st)))
+        _lib.check(self.ctx, self.lib.sla_part_finish(self.ctx, p2o.ctypes.data if download else None,
+                                                      o2p.ctypes.data if download else None,
+                                                      prices.ctypes.data if download else None, C.byref(st)))
         return p2o, o2p, prices, st.as_dict()
 
     def scalar_device(self):
@@ -151,7 +155,8 @@ class PartitionedKhoslaSolver:
             dist.all_reduce(t, op=op, group=self.group)
         return t
 
-    def solve(self, maximize: bool = False, eps: Optional[float] = None, max_rounds: int = 1 << 30) -> dict:
+    def solve(self, maximize: bool = False, eps: Optional[float] = None, max_rounds: int = 1 << 30,
+              download: bool = True) -> dict:
         eng = self.engine
         dev = eng.scalar_device()
         stream_ctx = torch.cuda.stream(eng.stream) if getattr(eng, "stream", None) is not None else _NullCtx()
@@ -188,7 +193,7 @@ class PartitionedKhoslaSolver:
                 self._all_reduce(qlen, dist.ReduceOp.SUM)
                 if int(qlen.item()) == 0:
                     break
-            p2o, o2p, prices, st = eng.finish()
+            p2o, o2p, prices, st = eng.finish(download) if download is False else eng.finish()
             tot = torch.tensor([st["num_unassigned"], st["bids"], st["bid_arcs"]], dtype=torch.int64, device=dev)
             self._all_reduce(tot, dist.ReduceOp.SUM)
             totals = [int(x) for x in tot.tolist()]      # read back on the engine's stream, behind the all-reduce

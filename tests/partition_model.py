@@ -172,7 +172,7 @@ class ModelShardEngine:
         self.rounds += 1
         return len(self.queue), self.dropped
 
-    def finish(self):
+    def finish(self, download=True):
         st = dict(num_unassigned=self.dropped, nits=self.bids, bids=self.bids, bid_arcs=self.arcs, rounds=self.rounds,
                   dropped=self.dropped, eps=self.eps, values_negated=int(self.flip))
         return self.p2o, self.o2p, self.prices, st
