@@ -68,25 +68,53 @@ def describe(workload):
 
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    """Samples SM clocks / throttle reasons every 200 ms while the timed region runs: NVML (what nvidia-smi reads;
+    no process spawn, so the sampler does not disturb microsecond-scale steps), nvidia-smi as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, device_index):
         super().__init__(daemon=True)
         self.device_index = device_index
-        self.samples = []
+        self.samples = []          # (sm_mhz, sm_max_mhz, set(reasons))
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() else device_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def sample_once(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            smax = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append((sm, smax, {k for k, bit in self.REASONS.items() if mask & bit}))
+            return
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                              str(self.device_index)], capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            s = [x.strip() for x in out.split(",")]
+            reasons = {name for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9])
+                       if val.lower().startswith("active")}
+            self.samples.append((float(s[1]), float(s[2]), reasons))
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.device_index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.sample_once()
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
@@ -94,19 +122,14 @@ class ClockSampler(threading.Thread):
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=3)
-        sm, smax, reasons = [], 0.0, set()
-        for s in self.samples:
-            try:
-                sm.append(float(s[1]))
-                smax = max(smax, float(s[2]))
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        try:
+            self.sample_once()      # at least one sample right at the end of the timed region
+        except Exception:
+            pass
+        sm = sorted(s[0] for s in self.samples)
+        reasons = set().union(*[s[2] for s in self.samples]) if self.samples else set()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((s[1] for s in self.samples), default=None),
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peak_gbs():
