@@ -32,6 +32,14 @@ def _imax(dtype) -> int:
     return int(np.iinfo(dtype).max)
 
 
+def host_threads() -> int:
+    """Host threads one solver may use for the in-place negation: the cores of the box divided by the number of
+    co-located ranks (torchrun exports LOCAL_WORLD_SIZE), at most 16."""
+    cores = os.cpu_count() or 1
+    local_world = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1), 1)
+    return max(1, min(16, cores // local_world))
+
+
 _PIN_MIN_BYTES = 1 << 16
 _pin_state = {"ok": None}
 
@@ -410,7 +418,7 @@ class AuctionSolver:
             self._pre_negated = bool(flip and vals.size >= (1 << 16))
             if self._pre_negated:
                 rc = _lib.load().sla_upload_csr_negating(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
-                                                         vals.ctypes.data, nnz, min(16, os.cpu_count() or 1))
+                                                         vals.ctypes.data, nnz, host_threads())
             else:
                 rc = _lib.load().sla_upload_csr(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
                                                 vals.ctypes.data, nnz)
@@ -436,7 +444,7 @@ class AuctionSolver:
             lib.sla_host_negate_f64(vals.ctypes.data, vals.size, 1)
             return None, True
         th = threading.Thread(target=lib.sla_host_negate_f64,
-                              args=(vals.ctypes.data, vals.size, min(16, os.cpu_count() or 1)))
+                              args=(vals.ctypes.data, vals.size, host_threads()))
         th.start()
         return th, True
 
