@@ -39,7 +39,7 @@ struct sla_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
 
     // capacities (elements)
@@ -251,6 +251,8 @@ void launch_one(sla_ctx* c, const Params& p, int which, bool zero_first = false)
 void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_first, bool tail_only) {
     if (!tail_only) {
         launch_one(c, p, 0, zero_first);
+        // first round with all prices zero: prices / owners / assignment are initialised behind the scan
+        if (zero_first) init_solve_late_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
         launch_one(c, p, 1);
     }
     launch_one(c, p, 2);
@@ -389,10 +391,17 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
     ctx->profile.clear();
     ctx->has_solution = false;
 
+    // The initialisation of prices / owners / assignment (solver.rs:218-229) runs BEHIND the first bid scan when that
+    // scan does not read them (all prices zero, wide first round); otherwise up front.
+    const bool late_init = ctx->opt_skip_zero != 0 && !is_tail_only(ctx);
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_state, ctx->h_state, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
-    init_solve_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, N, M, ctx->best_dirty ? 1 : 0);
-    launches += 1;
+    if (late_init) {
+        if (ctx->best_dirty) CU(cudaMemsetAsync(ctx->d_best, 0, (size_t)M * sizeof(unsigned long long), ctx->stream));
+    } else {
+        init_solve_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, N, M, ctx->best_dirty ? 1 : 0);
+        launches += 1;
+    }
     ctx->best_dirty = true;   // until the solve ends at a round boundary
 
     const bool use_graph = ctx->opt_graph && !ctx->opt_profile;
@@ -416,6 +425,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
             CU(cudaGraphLaunch(exec, ctx->stream));
             graph_launches += 1;
             launches += (uint32_t)(super_rounds_for(ctx, forward) * kernels_per_super_round(forward, is_tail_only(ctx)));
+            if (late_init && graph_launches == 1) launches += 1;   // init_solve_late_kernel sits in the first graph
             if ((rc = poll_state(ctx))) return rc;
             done = ctx->h_state->done != 0;
             if (!done && timed_out()) return fail(ctx, SLA_ERR_STATE, "solve exceeded the wall-clock guard (timeout_s)");
@@ -429,8 +439,14 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
             const bool wide = !prev.done && prev.qlen[prev.cur] > prev.tail_max;
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
             launch_one(ctx, p, 0, first && ctx->opt_skip_zero != 0);
-            first = false;
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+            const bool late_now = first && late_init;
+            if (late_now) {
+                init_solve_late_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p);
+                launches += 1;
+                if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[4], ctx->stream));   // assign time excludes the init
+            }
+            first = false;
             launch_one(ctx, p, 1);
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
             launches += 2;
@@ -446,7 +462,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
                     r.rounds_covered = 1;
                     r.arcs = prev.regular_k ? (uint64_t)r.bidders * prev.regular_k : ctx->h_state->bid_arcs - prev.bid_arcs;
                     cudaEventElapsedTime(&r.bid_ms, ctx->ev[1], ctx->ev[2]);
-                    cudaEventElapsedTime(&r.assign_ms, ctx->ev[2], ctx->ev[3]);
+                    cudaEventElapsedTime(&r.assign_ms, late_now ? ctx->ev[4] : ctx->ev[2], ctx->ev[3]);
                     ctx->profile.push_back(r);
                 }
                 CU(cudaEventRecord(ctx->ev[1], ctx->stream));
