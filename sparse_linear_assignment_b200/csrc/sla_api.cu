@@ -228,8 +228,8 @@ void launch_one_t(sla_ctx* c, const Params& p, int which, bool zero_first) {
             break;
         case 1: assign_wide_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
         case 2:
-            if (c->tail_smem_prices) tail_kernel<LPR, true><<<1, kTailThreads, kTailSmemPriceCols * sizeof(double), c->stream>>>(p);
-            else tail_kernel<LPR, false><<<1, kTailThreads, 0, c->stream>>>(p);
+            if (c->tail_smem_prices) tail_kernel<LPR, true><<<1, kTailThreads, kTailSmemPriceCols * sizeof(double) + kTailHashBytes, c->stream>>>(p);
+            else tail_kernel<LPR, false><<<1, kTailThreads, kTailHashBytes, c->stream>>>(p);
             break;
         case 3: ecs_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
         default: phase_apply_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
@@ -634,13 +634,21 @@ int sla_ctx_create(int device, size_t row_capacity, size_t col_capacity, size_t 
     if ((e = cudaMallocHost((void**)&ctx->h_csr_stats, sizeof(DevCsrStats))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_scratch, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMallocHost", e);
     {
-        const int dyn = kTailSmemPriceCols * (int)sizeof(double);
+        const int dyn = kTailSmemPriceCols * (int)sizeof(double) + kTailHashBytes;
         cudaFuncSetAttribute(tail_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         cudaFuncSetAttribute(tail_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         cudaFuncSetAttribute(tail_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         cudaFuncSetAttribute(tail_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         cudaFuncSetAttribute(tail_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         if ((e = cudaFuncSetAttribute(tail_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess)
+            return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
+        // static (29 KB) + the hash table (24 KB) already exceeds the 48 KB default of the variants without the price mirror
+        cudaFuncSetAttribute(tail_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes);
+        cudaFuncSetAttribute(tail_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes);
+        cudaFuncSetAttribute(tail_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes);
+        cudaFuncSetAttribute(tail_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes);
+        cudaFuncSetAttribute(tail_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes);
+        if ((e = cudaFuncSetAttribute(tail_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes)) != cudaSuccess)
             return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
     }
     // blocks per SM of the widest kernel decide the persistent grid

@@ -15,6 +15,9 @@ namespace sla {
 constexpr int kTailCap = 1024;       // max bidders the single-CTA tail engine accepts (smem-resident queue)
 constexpr int kWideThreads = 256;    // block size of the grid-wide kernels
 constexpr int kTailThreads = 1024;   // block size of the tail engine
+constexpr int kTailHashBits = 11;
+constexpr int kTailHashSlots = 1 << kTailHashBits;   // shared-memory hash table of the tail engine (<= 1024 bidders per round)
+constexpr int kTailHashBytes = kTailHashSlots * 12;    // u64 word + u32 key per slot
 constexpr int kTailSmemPriceCols = 20480;   // objects whose prices the tail engine can mirror in shared memory (160 KB)
 
 enum : uint32_t { ALGO_KHOSLA = 0, ALGO_FORWARD = 1 };

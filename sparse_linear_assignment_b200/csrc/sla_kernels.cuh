@@ -283,7 +283,8 @@ __device__ __forceinline__ uint32_t control_after_wide(DevState* st) {
 // the queue is short.  Queue and per-slot bids live in shared memory; prices / owners are read through the L1
 // (coherent for this CTA's own stores), CSR rows of repeat bidders stay L1-resident.  Conflict resolution:
 //   * <= 32 bidders: entirely in shared memory by one warp (no global atomics, no L2 round trips);
-//   * more bidders : the same packed-word atomicMax on best[] as the wide kernels.
+//   * more bidders : an open-addressing hash table in shared memory keyed by the object (atomicCAS on the key,
+//                    atomicMax on the packed word) -- still no global atomics and no L2 round trips.
 // Also hosts control step A (it is the first single-CTA kernel after the wide pair).
 // =============================================================================================================
 // SPRICES: the object prices are mirrored in dynamic shared memory for the lifetime of the launch (write-through to
@@ -293,6 +294,9 @@ template <int LPR, bool SPRICES>
 __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     double* s_prices = reinterpret_cast<double*>(s_dyn);
+    unsigned long long* h_word = reinterpret_cast<unsigned long long*>(s_dyn + (SPRICES ? kTailSmemPriceCols * sizeof(double) : 0));
+    uint32_t* h_key = reinterpret_cast<uint32_t*>(h_word + kTailHashSlots);
+    __shared__ uint32_t s_hslot[kTailCap];
     __shared__ uint32_t s_queue[2][kTailCap];
     __shared__ uint32_t s_obj[kTailCap];
     __shared__ double s_bid[kTailCap];
@@ -346,6 +350,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
         const uint32_t n_cols = st->n_cols;
         for (uint32_t j = tid; j < n_cols; j += kTailThreads) s_prices[j] = zero ? 0.0 : p.prices[j];
     }
+    for (uint32_t h = tid; h < (uint32_t)kTailHashSlots; h += kTailThreads) { h_key[h] = SLA_DEV_NONE; h_word[h] = 0ull; }
     __syncthreads();
     constexpr int kPriceMode = SPRICES ? PRICE_SMEM : PRICE_CA;
     const double* price_src = SPRICES ? s_prices : p.prices;
@@ -416,9 +421,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
             choice_init(c);
             if (zero) scan_row<LPR, PRICE_ZERO, false>(c, p.cols, p.vals, price_src, a, b, sign_flip, lane);
             else      scan_row<LPR, kPriceMode, false>(c, p.cols, p.vals, price_src, a, b, sign_flip, lane);
+            // speculative: the owner of each lane's local best column, issued before the reduction so that its latency
+            // hides behind the shuffles (nobody owns anything while all prices are still zero)
+            if (!zero && c.pos != SLA_DEV_NONE) c.aux = ld_ca_u32(p.o2p + c.col);
             choice_group_reduce<LPR>(c);
-            // current owner of the chosen object (nobody owns anything while all prices are still zero)
-            if (valid && lane == 0 && !zero) c.aux = ld_ca_u32(p.o2p + ((c.pos == SLA_DEV_NONE) ? 0u : c.col));
+            if (valid && lane == 0 && !zero && c.pos == SLA_DEV_NONE) c.aux = ld_ca_u32(p.o2p);   // row without usable arc -> object 0
             if (valid && lane == 0) {
                 const Bid r = zero ? make_bid<PRICE_ZERO>(c, algo, eps, thr, price_src)
                                    : make_bid<kPriceMode>(c, algo, eps, thr, price_src);
@@ -430,7 +437,16 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                     s_obj[q] = r.obj;
                     s_bid[q] = r.bid;
                     s_prev[q] = c.aux;                      // owner of r.obj (only the winner uses it)
-                    if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));   // NaN never bids
+                    if (r.bid == r.bid) {                   // NaN never bids
+                        uint32_t h = (r.obj * 2654435761u) >> (32 - kTailHashBits);
+                        while (true) {
+                            const uint32_t old = atomicCAS(h_key + h, SLA_DEV_NONE, r.obj);
+                            if (old == SLA_DEV_NONE || old == r.obj) break;
+                            h = (h + 1u) & (uint32_t)(kTailHashSlots - 1);
+                        }
+                        atomicMax(h_word + h, pack_bid(r.bid, i, pbits));
+                        s_hslot[q] = h;
+                    }
                 }
             }
         }
@@ -492,13 +508,12 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                         const uint32_t i = sq[q];
                         const double bid = s_bid[q];
                         const uint32_t prev = s_prev[q];
-                        const bool won = (bid == bid) && (__ldcg(p.best + j) == pack_bid(bid, i, pbits));
+                        const bool won = (bid == bid) && (h_word[s_hslot[q]] == pack_bid(bid, i, pbits));
                         if (won) {
                             p.prices[j] = bid;
                             if (SPRICES) s_prices[j] = bid;
                             p.o2p[j] = i;
                             p.p2o[i] = j;
-                            atomicExch(p.best + j, 0ull);
                             if (prev != SLA_DEV_NONE) { p.p2o[prev] = SLA_DEV_NONE; emit = prev; }
                         } else {
                             emit = i;
@@ -519,6 +534,15 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                 out += total;
                 __syncthreads();
             }
+            // every word has been compared: empty the table entries this round used
+            for (uint32_t q = tid; q < qlen; q += kTailThreads) {
+                if (s_obj[q] != SLA_DEV_NONE && s_bid[q] == s_bid[q]) {
+                    const uint32_t h = s_hslot[q];
+                    h_key[h] = SLA_DEV_NONE;
+                    h_word[h] = 0ull;
+                }
+            }
+            __syncthreads();
         }
 
         bids_done += qlen;
