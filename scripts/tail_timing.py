@@ -1,34 +1,66 @@
-"""Development probe: builds the library with -DSLA_TAIL_TIMING into a scratch .so and prints where the tail
-engine's cycles go on cfg2 (thread 0's view)."""
+"""Development probe: builds the library with -DSLA_TAIL_TIMING into a scratch .so and prints where the cycles of the
+tail engine's small rounds go (stamps of the busiest warp; see TK() in csrc/sla_kernels.cuh)."""
 import ctypes as C
 import subprocess
 import sys
+
+import numpy as np
 
 sys.path.insert(0, ".")
 from sparse_linear_assignment_b200 import _lib
 
 so = "/tmp/libsla_timing.so"
-extra = sys.argv[1:]
+extra = [a for a in sys.argv[1:] if a.startswith("-") and a != "--notiming"]
+TIMING = "--notiming" not in sys.argv
+which = [a for a in sys.argv[1:] if not a.startswith("-")] or ["chain", "cfg2f", "cfg2k"]
 print("flags", extra)
-subprocess.run(["nvcc"] + _lib.NVCC_FLAGS + ["-DSLA_TAIL_TIMING"] + extra + ["-o", so, _lib.CSRC + "/sla_api.cu"], check=True)
+subprocess.run(["nvcc"] + _lib.NVCC_FLAGS + (["-DSLA_TAIL_TIMING"] if TIMING else []) + extra + ["-o", so, _lib.CSRC + "/sla_api.cu"], check=True)
 _lib.LIB_PATH = so
 import sparse_linear_assignment_b200 as S
 from sparse_linear_assignment_b200 import generators as G
 
-import itertools
-for (cls, name), sp in itertools.product(((S.ForwardAuctionSolver, "forward"), (S.KhoslaSolver, "khosla")), (1, 0, 2)):
-    n = 20000
-    solver, z = cls.new(n, n, n * 64)
-    G.kregular_device(solver, n, n, 64, seed=1, planted=True)
-    solver.set_option("smem_prices", 1 if sp else 0)
-    if sp == 2:
-        solver.set_option("regular", 0)
-    name += f" smem_prices={sp}" + (" regular=0 (no evict_first stream)" if sp == 2 else "")
-    st = solver.solve_resident(False, None)
+SEG = ["lane scan (price + keys)", "REDUX agreement", "owner", "prefetch issue + bid", "STS", "barrier 1", "resolve (LDS + any)",
+       "stores + row move", "atomicOr", "barrier 2", "mask read + loop"]
+
+
+def report(name, solver, st):
     lib = _lib.load()
     lib.sla_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-    out = (C.c_uint64 * 8)()
+    out = (C.c_uint64 * 24)()
     lib.sla_debug_counters(solver._context(), out)
-    tot, scan, _, bar1, asg, bar2, rounds, bid = [out[i] for i in range(8)]
-    print(name, "ms", st["ms_solve"], "tail rounds", rounds, "cycles/round", tot / max(rounds, 1),
-          {k: round(v / max(rounds, 1), 1) for k, v in dict(scan_and_reduce=scan, bid=bid, bar1=bar1, assign=asg, bar2=bar2).items()})
+    if not TIMING:
+        print(name, "ms", round(st["ms_solve"], 3), "tail rounds", st["tail_rounds"], "cycles/round (1.965 GHz)",
+              round(st["ms_solve"] * 1.965e6 / max(st["tail_rounds"], 1), 1))
+        return
+    tot, rounds, act = out[0], max(out[6], 1), max(out[7], 1)
+    seg = {SEG[i]: round(out[8 + i] / act, 1) for i in range(11)}
+    print(name, "ms", round(st["ms_solve"], 3), "tail rounds", out[6], "cycles/round", round(tot / rounds, 1),
+          "busiest warp active rounds", out[7], "its cycles/active round", round(sum(out[8:19]) / act, 1))
+    for k, v in seg.items():
+        print(f"      {k:28s} {v}")
+
+
+if "chain" in which:
+    # one long eviction chain: 3 persons fight over 2 good objects in steps of eps -> ~2e5 rounds with one bidder
+    for cls, name in ((S.KhoslaSolver, "chain khosla 3x3"),):
+        solver, z = cls.new(3, 3, 9)
+        solver.init(3, 3)
+        for i in range(3):
+            solver.extend_from_values(i, np.array([0, 1, 2], dtype=np.uint32), np.array([1000.0, 1000.0, 0.0]))
+        for own in (1, 0):
+            solver.set_option("smem_owners", own)
+            solver._dirty = True
+            solver.solve(z, True, 0.01)
+            report(f"{name} smem_owners={own}", solver, solver.last_stats)
+
+for tag, cls in (("cfg2f", S.ForwardAuctionSolver), ("cfg2k", S.KhoslaSolver)):
+    if tag not in which:
+        continue
+    for sp in (3, 1, 0):
+        n = 20000
+        solver, z = cls.new(n, n, n * 64)
+        G.kregular_device(solver, n, n, 64, seed=1, planted=True)
+        solver.set_option("smem_prices", 1 if sp else 0)
+        solver.set_option("smem_owners", 1 if sp == 3 else 0)
+        st = solver.solve_resident(False, None)
+        report(f"{tag} smem_prices={1 if sp else 0} smem_owners={1 if sp == 3 else 0}", solver, st)

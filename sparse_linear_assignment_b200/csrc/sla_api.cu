@@ -28,6 +28,8 @@ struct GraphSlot {
     uint32_t regular_k = 0;
     bool smem_prices = false;
     bool tail_only = false;
+    uint32_t tail_smem_bytes = 0;
+    uint32_t tail_max = 0;
 };
 
 }  // namespace
@@ -76,8 +78,13 @@ struct sla_ctx {
     uint32_t regular_k = 0;   // all rows have this many arcs (multiple of 8): the regular bid kernel is used
     int lpr8 = 1;
     int opt_regular = 1;
-    int opt_smem_prices = 1;
-    bool tail_smem_prices = false;   // n_cols small enough for the tail engine's shared-memory price mirror
+    int opt_smem_prices = 1, opt_smem_owners = 1;
+    // tail-engine plan of the current instance (plan_tail): what is mirrored in shared memory and how many bidders fit
+    bool tail_smem_prices = false;   // object prices mirrored
+    uint32_t tail_own_mode = 0;      // owners mirrored: 0 no, 1 u32, 2 u16
+    uint32_t tail_cap = 1024;        // capacity of the queue arrays (power of two)
+    uint32_t tail_max_eff = 1024;    // bidders at or below which the tail engine runs (min(option tail_max, tail_cap))
+    uint32_t tail_smem_bytes = 0;    // dynamic shared memory of a tail launch
 
     // options
     int opt_graph = 1, opt_tail_max = 1024, opt_skip_zero = 1, opt_profile = 0, opt_super_rounds = 6;
@@ -228,8 +235,8 @@ void launch_one_t(sla_ctx* c, const Params& p, int which, bool zero_first) {
             break;
         case 1: assign_wide_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
         case 2:
-            if (c->tail_smem_prices) tail_kernel<LPR, true><<<1, kTailThreads, kTailSmemPriceCols * sizeof(double) + kTailHashBytes, c->stream>>>(p);
-            else tail_kernel<LPR, false><<<1, kTailThreads, kTailHashBytes, c->stream>>>(p);
+            if (c->tail_smem_prices) tail_kernel<LPR, true><<<1, kTailThreads, c->tail_smem_bytes, c->stream>>>(p);
+            else tail_kernel<LPR, false><<<1, kTailThreads, c->tail_smem_bytes, c->stream>>>(p);
             break;
         case 3: ecs_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
         default: phase_apply_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
@@ -264,7 +271,7 @@ void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_fir
 
 int kernels_per_super_round(bool forward, bool tail_only) { return (forward ? 5 : 3) - (tail_only ? 2 : 0); }
 
-bool is_tail_only(const sla_ctx* c) { return c->n_rows <= (uint32_t)c->opt_tail_max; }
+bool is_tail_only(const sla_ctx* c) { return c->n_rows <= c->tail_max_eff; }
 
 // Khosla on a tail-only instance finishes inside the first tail launch: further super-rounds would be pure no-ops.
 int super_rounds_for(const sla_ctx* c, bool forward) {
@@ -277,7 +284,8 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     const bool tail_only = is_tail_only(ctx);
     const int n_super = super_rounds_for(ctx, forward);
     if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == n_super &&
-        g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices && g.tail_only == tail_only) {
+        g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices && g.tail_only == tail_only &&
+        g.tail_smem_bytes == ctx->tail_smem_bytes && g.tail_max == ctx->tail_max_eff) {
         *out = g.exec;
         return SLA_OK;
     }
@@ -300,8 +308,52 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     g.tail_only = tail_only;
     g.regular_k = reg_key;
     g.smem_prices = ctx->tail_smem_prices;
+    g.tail_smem_bytes = ctx->tail_smem_bytes;
+    g.tail_max = ctx->tail_max_eff;
     *out = g.exec;
     return SLA_OK;
+}
+
+// Dynamic shared memory a tail launch may use: the 227 KB of an sm_100 CTA minus the kernel's static arrays.
+constexpr uint32_t kTailDynSmemMax = 232448u - 2048u;
+
+// Decide what the tail engine mirrors in shared memory for the current instance and how many bidders it accepts.
+// Preference: prices + owners (u32, else u16 when person ids fit) > prices only > nothing, as long as at least
+// min(256, requested) bidders still fit beside the mirrors.
+void plan_tail(sla_ctx* c) {
+    const uint32_t want = (uint32_t)c->opt_tail_max;
+    uint32_t cap = 32;
+    while (cap < want) cap <<= 1;
+    bool sp = false;
+    uint32_t om = 0;
+    if (c->has_csr && want > 0) {
+        const uint32_t M = c->n_cols, N = c->n_rows;
+        const uint32_t min_cap = cap < 256u ? cap : 256u;
+        struct Cand { bool sp; uint32_t om; bool ok; };
+        const Cand cands[4] = {
+            {true, 1u, c->opt_smem_prices && c->opt_smem_owners},
+            {true, 2u, c->opt_smem_prices && c->opt_smem_owners && N <= 65535u},
+            {true, 0u, c->opt_smem_prices != 0},
+            {false, 0u, true},
+        };
+        bool chosen = false;
+        for (const Cand& k : cands) {
+            if (!k.ok) continue;
+            const uint64_t mirror = (uint64_t)M * ((k.sp ? 8u : 0u) + (k.om == 1u ? 4u : (k.om == 2u ? 2u : 0u)));
+            if (mirror > kTailDynSmemMax) continue;
+            for (uint32_t cc = cap; cc >= min_cap && !chosen; cc >>= 1) {
+                if (tail_smem_layout(k.sp, k.om, M, cc).total <= kTailDynSmemMax) {
+                    sp = k.sp; om = k.om; cap = cc; chosen = true;
+                }
+            }
+            if (chosen) break;
+        }
+    }
+    c->tail_smem_prices = sp;
+    c->tail_own_mode = om;
+    c->tail_cap = cap;
+    c->tail_max_eff = want < cap ? want : cap;
+    c->tail_smem_bytes = tail_smem_layout(sp, om, c->has_csr ? c->n_cols : 0u, cap).total;
 }
 
 double get_toleration_host(double c) {
@@ -354,7 +406,9 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
     s.zero_prices = 1;
     s.algo = forward ? ALGO_FORWARD : ALGO_KHOSLA;
     s.pbits = person_bits(N);
-    s.tail_max = (uint32_t)ctx->opt_tail_max;
+    s.tail_max = ctx->tail_max_eff;
+    s.own_mode = ctx->tail_own_mode;
+    s.tail_cap = ctx->tail_cap;
     s.skip_zero = (uint32_t)ctx->opt_skip_zero;
     s.sign_flip = ctx->dev_sign < 0 ? 0x80000000u : 0u;
     s.n_rows = N;
@@ -572,9 +626,9 @@ int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz)
         while (l < 32 && (uint32_t)(l * 8) < ctx->regular_k) l *= 2;
         ctx->lpr8 = l;
     }
-    ctx->tail_smem_prices = ctx->opt_smem_prices && num_cols <= (uint32_t)kTailSmemPriceCols;
     ctx->has_csr = true;
     ctx->has_solution = false;
+    plan_tail(ctx);
     return SLA_OK;
 }
 
@@ -634,22 +688,23 @@ int sla_ctx_create(int device, size_t row_capacity, size_t col_capacity, size_t 
     if ((e = cudaMallocHost((void**)&ctx->h_csr_stats, sizeof(DevCsrStats))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_scratch, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMallocHost", e);
     {
-        const int dyn = kTailSmemPriceCols * (int)sizeof(double) + kTailHashBytes;
-        cudaFuncSetAttribute(tail_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        cudaFuncSetAttribute(tail_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        cudaFuncSetAttribute(tail_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        cudaFuncSetAttribute(tail_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        cudaFuncSetAttribute(tail_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        if ((e = cudaFuncSetAttribute(tail_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess)
-            return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
-        // static (29 KB) + the hash table (24 KB) already exceeds the 48 KB default of the variants without the price mirror
-        cudaFuncSetAttribute(tail_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes);
-        cudaFuncSetAttribute(tail_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes);
-        cudaFuncSetAttribute(tail_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes);
-        cudaFuncSetAttribute(tail_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes);
-        cudaFuncSetAttribute(tail_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes);
-        if ((e = cudaFuncSetAttribute(tail_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHashBytes)) != cudaSuccess)
-            return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
+        const int dyn = (int)kTailDynSmemMax;
+        cudaError_t ea[12] = {
+            cudaFuncSetAttribute(tail_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+            cudaFuncSetAttribute(tail_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn),
+        };
+        for (cudaError_t x : ea)
+            if (x != cudaSuccess) return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", x);
     }
     // blocks per SM of the widest kernel decide the persistent grid
     int occ = 0;
@@ -707,6 +762,7 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
     if (k == "tail_max") {
         if (value < 0 || value > kTailCap) return fail(ctx, SLA_ERR_INVALID, "tail_max must be in [0, 1024]");
         ctx->opt_tail_max = (int)value;
+        plan_tail(ctx);
     } else if (k == "graph") {
         ctx->opt_graph = value ? 1 : 0;
     } else if (k == "zero_price_skip") {
@@ -715,7 +771,10 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
         ctx->opt_profile = value ? 1 : 0;
     } else if (k == "smem_prices") {
         ctx->opt_smem_prices = value ? 1 : 0;
-        ctx->tail_smem_prices = ctx->opt_smem_prices && ctx->has_csr && ctx->n_cols <= (uint32_t)kTailSmemPriceCols;
+        plan_tail(ctx);
+    } else if (k == "smem_owners") {
+        ctx->opt_smem_owners = value ? 1 : 0;
+        plan_tail(ctx);
     } else if (k == "regular") {
         ctx->opt_regular = value ? 1 : 0;
     } else if (k == "timeout_s") {
@@ -966,9 +1025,9 @@ void sla_host_negate_f64(double* values, size_t n, int threads) {
 }
 
 // Development aid (not part of include/sla.h): raw tail-engine cycle counters of the last solve.
-int sla_debug_counters(sla_ctx* ctx, uint64_t* out8) {
-    if (!ctx || !out8) return SLA_ERR_INVALID;
-    for (int i = 0; i < 8; ++i) out8[i] = ctx->h_state->dbg[i];
+int sla_debug_counters(sla_ctx* ctx, uint64_t* out24) {
+    if (!ctx || !out24) return SLA_ERR_INVALID;
+    for (int i = 0; i < 24; ++i) out24[i] = ctx->h_state->dbg[i];
     return SLA_OK;
 }
 

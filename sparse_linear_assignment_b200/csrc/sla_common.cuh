@@ -14,11 +14,11 @@ namespace sla {
 
 constexpr int kTailCap = 1024;       // max bidders the single-CTA tail engine accepts (smem-resident queue)
 constexpr int kWideThreads = 256;    // block size of the grid-wide kernels
-constexpr int kTailThreads = 1024;   // block size of the tail engine
-constexpr int kTailHashBits = 11;
-constexpr int kTailHashSlots = 1 << kTailHashBits;   // shared-memory hash table of the tail engine (<= 1024 bidders per round)
-constexpr int kTailHashBytes = kTailHashSlots * 12;    // u64 word + u32 key per slot
-constexpr int kTailSmemPriceCols = 20480;   // objects whose prices the tail engine can mirror in shared memory (160 KB)
+#ifndef SLA_TAIL_THREADS
+#define SLA_TAIL_THREADS 1024
+#endif
+constexpr int kTailThreads = SLA_TAIL_THREADS;   // block size of the tail engine
+constexpr uint32_t kTailSlots = kTailThreads / 32;   // bidders of a "small" round: one warp per slot
 
 enum : uint32_t { ALGO_KHOSLA = 0, ALGO_FORWARD = 1 };
 enum : uint32_t { ACTION_NONE = 0, ACTION_RESET = 1 };
@@ -47,7 +47,9 @@ struct DevState {
     double target_eps;
     double tol;
     uint32_t person_base;    // global id of local row 0 (row-partitioned instance; 0 otherwise)
-    uint32_t hot_pad[3];
+    uint32_t own_mode;       // tail engine: owners mirrored in shared memory (0 no, 1 as u32, 2 as u16)
+    uint32_t tail_cap;       // tail engine: capacity of its shared-memory queue arrays (power of two, >= tail_max)
+    uint32_t hot_pad[1];
     // ---- cold ----
     uint32_t nits;           // Forward: rounds (symmetric.rs:277); Khosla: filled from `bids` at the end
     uint32_t nreductions;
@@ -59,7 +61,7 @@ struct DevState {
     uint32_t tail_round_cap; // rounds one tail launch may run before handing control back to the host
     unsigned long long rounds, bids, bid_arcs, wide_rounds, tail_rounds;
     unsigned long long safety_rounds_left;
-    unsigned long long dbg[8];   // cycle counters of the tail engine when built with -DSLA_TAIL_TIMING
+    unsigned long long dbg[24];  // cycle counters of the tail engine when built with -DSLA_TAIL_TIMING
 };
 
 struct alignas(16) HotState {
@@ -69,7 +71,7 @@ struct alignas(16) HotState {
     uint32_t n_rows, n_cols, start_opt, action;
     double eps, threshold;
     double target_eps, tol;
-    uint32_t person_base, hot_pad[3];
+    uint32_t person_base, own_mode, tail_cap, hot_pad[1];
 };
 static_assert(sizeof(HotState) == 112, "HotState must mirror the first 112 bytes of DevState");
 static_assert(sizeof(DevState) % 16 == 0, "DevState is copied as 128-bit words");
@@ -108,6 +110,28 @@ struct Params {
     double* slot_bid;           // per queue slot: exact f64 bid
     DevState* st;
 };
+
+// Dynamic shared memory of the tail engine: [price mirror][owner mirror][hash words][hash keys][per-slot arrays].
+// Shared by the kernel (carving) and the host (launch size, choice of what to mirror).
+struct TailSmemLayout {
+    uint32_t owners, hash_words, hash_keys, bid, queue0, total;
+};
+__host__ __device__ __forceinline__ TailSmemLayout tail_smem_layout(bool sprices, uint32_t own_mode, uint32_t n_cols, uint32_t cap) {
+    TailSmemLayout l;
+    uint32_t off = sprices ? ((n_cols * 8u + 15u) & ~15u) : 0u;
+    l.owners = off;
+    off += (own_mode == 1u) ? ((n_cols * 4u + 15u) & ~15u) : ((own_mode == 2u) ? ((n_cols * 2u + 15u) & ~15u) : 0u);
+    l.hash_words = off;
+    off += 2u * cap * 8u;
+    l.hash_keys = off;
+    off += 2u * cap * 4u;
+    l.bid = off;
+    off += cap * 8u;
+    l.queue0 = off;
+    off += 5u * cap * 4u;          // two queue buffers, object, previous owner, hash slot
+    l.total = off;
+    return l;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long f64_order_key(double x) {
@@ -165,6 +189,64 @@ __device__ __forceinline__ uint32_t ld_ca_u32(const uint32_t* p) {
     asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
     return r;
 }
+
+// Explicit shared-space accesses through 32-bit addresses.  On sm_100 the address of a shared variable embeds the
+// CTA's rank in its cluster, which the compiler re-derives (S2UR SR_CgaCtaId + uniform arithmetic, tens of cycles on
+// the critical path) wherever register pressure makes it drop the base; the latency-bound engines therefore compute
+// their bases once (volatile, so they cannot be rematerialised) and address relative to them.
+__device__ __forceinline__ uint32_t smem_base_u32(const void* p) {
+    unsigned long long a;
+    asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(a) : "l"(p));
+    return (uint32_t)a;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double r;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
+    unsigned long long r;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(r) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t r;
+    asm volatile("{\n .reg .u16 t;\n ld.shared.u16 t, [%1];\n cvt.u32.u16 %0, t;\n}" : "=r"(r) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_u64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("{\n .reg .u16 t;\n cvt.u16.u32 t, %1;\n st.shared.u16 [%0], t;\n}" :: "r"(a), "r"(v) : "memory");
+}
+// Barrier among the first-class participants of a small round only (warps whose slot is empty sleep at barrier 0).
+__device__ __forceinline__ void named_bar_sync(uint32_t nthreads) {
+    asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory");
+}
+
+// Where the tail engine reads the current owner of an object from: the global o2p array (coherent L1 loads) or a
+// shared-memory mirror kept for the lifetime of the launch (u32, or u16 with 0xFFFF = none when N <= 65535).
+struct OwnerView {
+    const uint32_t* g;
+    uint32_t* s32;
+    uint16_t* s16;
+    __device__ __forceinline__ bool mirrored() const { return s32 != nullptr || s16 != nullptr; }
+    __device__ __forceinline__ uint32_t load(uint32_t j) const {
+        if (s32) return s32[j];
+        if (s16) { const uint32_t v = s16[j]; return v == 0xFFFFu ? SLA_DEV_NONE : v; }
+        return ld_ca_u32(g + j);
+    }
+    __device__ __forceinline__ void store_mirror(uint32_t j, uint32_t person) const {
+        if (s32) s32[j] = person;
+        else if (s16) s16[j] = (uint16_t)person;
+    }
+};
 
 // 256-bit streaming loads (sm_100): one LDG.256 per 8 column indices / 4 values, evict-first in L2 so that the
 // once-per-round CSR stream does not push the object state (prices, owners, bid words) out of the L2.
@@ -323,9 +405,15 @@ struct WarpChoice {
 
 enum OwnerMode : int { OWN_NONE = 0, OWN_GLOBAL = 1, OWN_SMEM = 2 };
 
+// Order-preserving key of a profit; 0 = "no arc" for NaN and -inf (they never pass the reference's strict '>' against
+// the initial -inf).  All-integer on purpose: the FP64 pipe costs ~35 cycles per dependent op on the latency-bound
+// single-CTA engines.  -0.0 is canonicalised to +0.0 so that keys compare exactly like the f64 values.
 __device__ __forceinline__ unsigned long long profit_key(double profit) {
-    profit += 0.0;
-    return (profit > neg_inf()) ? f64_order_key(profit) : 0ull;
+    unsigned long long u = (unsigned long long)__double_as_longlong(profit);
+    u = (u == 0x8000000000000000ull) ? 0ull : u;
+    const unsigned long long k = u ^ ((u >> 63) ? ~0ull : (1ull << 63));
+    // valid keys: key(-inf) < k <= key(+inf); negative NaNs fall below, positive NaNs above
+    return (k > 0x000FFFFFFFFFFFFFull && k <= 0xFFF0000000000000ull) ? k : 0ull;
 }
 __device__ __forceinline__ double key_profit(unsigned long long key) {
     return key ? order_key_to_f64_host(key) : neg_inf();
@@ -336,51 +424,135 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k)
     return ((unsigned long long)hi << 32) | lo;
 }
 
-template <int MODE, int OWN>
-__device__ __forceinline__ WarpChoice warp_bid_scan(const uint32_t* __restrict__ cols, const double* __restrict__ vals,
-                                                    const double* prices, const uint32_t* owners, uint32_t a, uint32_t b,
-                                                    uint32_t flip, int lane32) {
-    unsigned long long k1 = 0ull, k2 = 0ull;
-    uint32_t pos1 = SLA_DEV_NONE, col1 = 0u;
-    double val1 = neg_inf(), pr1 = 0.0;
-    for (uint32_t g = a + (uint32_t)lane32; g < b; g += 32u) {
-        const uint32_t col = __ldg(cols + g);
-        const double raw = __ldg(vals + g);
-        const double v = __hiloint2double(__double2hiint(raw) ^ (int)flip, __double2loint(raw));
-        const double pr = ld_price<MODE>(prices, col);
-        const unsigned long long key = profit_key((MODE == PRICE_ZERO) ? v : (v - pr));
-        const bool gt = key > k1, gs = key > k2;
-        k2 = gt ? k1 : (gs ? key : k2);
-        k1 = gt ? key : k1;
-        pos1 = gt ? g : pos1;
-        col1 = gt ? col : col1;
-        val1 = gt ? v : val1;
-        pr1 = gt ? pr : pr1;
-    }
+// Per-lane running top-2 of the profit keys seen so far (lane-local part of the warp-per-bidder scan).
+struct LaneTop2 {
+    unsigned long long k1, k2;
+    uint32_t pos1, col1;
+    double val1, pr1;
+};
+__device__ __forceinline__ void lane_top2_init(LaneTop2& t) {
+    t.k1 = 0ull; t.k2 = 0ull; t.pos1 = SLA_DEV_NONE; t.col1 = 0u; t.val1 = neg_inf(); t.pr1 = 0.0;
+}
+__device__ __forceinline__ void lane_top2_update(LaneTop2& t, unsigned long long key, uint32_t g, uint32_t col, double v,
+                                                 double pr) {
+    const bool gt = key > t.k1, gs = key > t.k2;
+    t.k2 = gt ? t.k1 : (gs ? key : t.k2);
+    t.k1 = gt ? key : t.k1;
+    t.pos1 = gt ? g : t.pos1;
+    t.col1 = gt ? col : t.col1;
+    t.val1 = gt ? v : t.val1;
+    t.pr1 = gt ? pr : t.pr1;
+}
+
+// Warp-wide agreement on the choice from the 32 lane-local top-2 records.
+template <int OWN>
+__device__ __forceinline__ WarpChoice warp_choice_finish(const LaneTop2& t, const uint32_t* owners) {
     // speculative: the current owner of this lane's best column, issued before the reductions so that its latency
     // hides behind them (only the owning lane's value is used)
     uint32_t own1 = SLA_DEV_NONE;
-    if (OWN == OWN_GLOBAL) { if (pos1 != SLA_DEV_NONE) own1 = ld_ca_u32(owners + col1); }
-    else if (OWN == OWN_SMEM) { if (pos1 != SLA_DEV_NONE) own1 = owners[col1]; }
+    if (OWN == OWN_GLOBAL) { if (t.pos1 != SLA_DEV_NONE) own1 = ld_ca_u32(owners + t.col1); }
+    else if (OWN == OWN_SMEM) { if (t.pos1 != SLA_DEV_NONE) own1 = owners[t.col1]; }
 
-    const unsigned long long kmax = warp_max_u64(k1);
-    const bool is_max = (kmax != 0ull) && (k1 == kmax);
-    const uint32_t posmin = __reduce_min_sync(0xffffffffu, is_max ? pos1 : SLA_DEV_NONE);
-    const bool is_owner = is_max && (pos1 == posmin);
+    const unsigned long long kmax = warp_max_u64(t.k1);
+    const bool is_max = (kmax != 0ull) && (t.k1 == kmax);
+    const uint32_t posmin = __reduce_min_sync(0xffffffffu, is_max ? t.pos1 : SLA_DEV_NONE);
+    const bool is_owner = is_max && (t.pos1 == posmin);
     const uint32_t owner_ballot = __ballot_sync(0xffffffffu, is_owner);
-    const unsigned long long ksecond = warp_max_u64(is_owner ? k2 : k1);
+    const unsigned long long ksecond = warp_max_u64(is_owner ? t.k2 : t.k1);
 
     WarpChoice r;
     r.best = key_profit(kmax);
     r.second = key_profit(ksecond);
     r.pos = posmin;
     const int src = owner_ballot ? (__ffs((int)owner_ballot) - 1) : 0;
-    r.value = __shfl_sync(0xffffffffu, val1, src);
-    r.price = __shfl_sync(0xffffffffu, pr1, src);
-    r.col = __shfl_sync(0xffffffffu, col1, src);
+    r.value = __shfl_sync(0xffffffffu, t.val1, src);
+    r.price = __shfl_sync(0xffffffffu, t.pr1, src);
+    r.col = __shfl_sync(0xffffffffu, t.col1, src);
     r.owner = __shfl_sync(0xffffffffu, own1, src);
     if (!owner_ballot) { r.value = neg_inf(); r.price = 0.0; r.col = 0u; r.owner = SLA_DEV_NONE; r.pos = SLA_DEV_NONE; }
     return r;
+}
+
+template <int MODE, int OWN>
+__device__ __forceinline__ WarpChoice warp_bid_scan(const uint32_t* __restrict__ cols, const double* __restrict__ vals,
+                                                    const double* prices, const uint32_t* owners, uint32_t a, uint32_t b,
+                                                    uint32_t flip, int lane32) {
+    LaneTop2 t;
+    lane_top2_init(t);
+    for (uint32_t g = a + (uint32_t)lane32; g < b; g += 32u) {
+        const uint32_t col = __ldg(cols + g);
+        const double raw = __ldg(vals + g);
+        const double v = __hiloint2double(__double2hiint(raw) ^ (int)flip, __double2loint(raw));
+        const double pr = ld_price<MODE>(prices, col);
+        lane_top2_update(t, profit_key((MODE == PRICE_ZERO) ? v : (v - pr)), g, col, v, pr);
+    }
+    return warp_choice_finish<OWN>(t, owners);
+}
+
+// ---- register-resident rows (slot-stable small rounds of the tail engine) --------------------------------------------
+// A row of at most 32 * RPL arcs held by one warp: lane l keeps arcs a + l + 32 t (t < RPL) with the RAW uploaded
+// values (the sign is applied where a value is used: a fetched row must not be touched before it is needed, or the
+// fetch stops being asynchronous); slots past the end of the row are flagged in `len` terms by the user.
+template <int RPL>
+struct RowRegs {
+    uint32_t c[RPL];
+    double v[RPL];
+    uint32_t a, len;
+};
+
+template <int RPL>
+__device__ __forceinline__ void row_extents(RowRegs<RPL>& r, const uint32_t* __restrict__ row_ptr, uint32_t regK, uint32_t person) {
+    if (regK) { r.a = person * regK; r.len = regK; }
+    else { r.a = __ldg(row_ptr + person); r.len = __ldg(row_ptr + person + 1) - r.a; }
+}
+
+template <int RPL>
+__device__ __forceinline__ void row_load(RowRegs<RPL>& r, const uint32_t* __restrict__ cols, const double* __restrict__ vals,
+                                         int lane32) {
+#pragma unroll
+    for (int t = 0; t < RPL; ++t) {
+        const uint32_t off = (uint32_t)lane32 + 32u * (uint32_t)t;
+        r.c[t] = 0u;
+        r.v[t] = 0.0;
+        if (off < r.len && r.len <= 32u * RPL) {
+            r.c[t] = __ldg(cols + r.a + off);
+            r.v[t] = __ldg(vals + r.a + off);
+        }
+    }
+}
+
+template <int RPL, int MODE>
+__device__ __forceinline__ LaneTop2 lane_scan_regs(const RowRegs<RPL>& r, const double* prices, uint32_t flip, int lane32) {
+    LaneTop2 t;
+    lane_top2_init(t);
+    double pr[RPL];
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) pr[u] = ld_price<MODE>(prices, r.c[u]);
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) {
+        const uint32_t off = (uint32_t)lane32 + 32u * (uint32_t)u;
+        const double v = __hiloint2double(__double2hiint(r.v[u]) ^ (int)flip, __double2loint(r.v[u]));
+        // arcs past the end of the row get key 0 = "no arc"
+        lane_top2_update(t, (off < r.len) ? profit_key(v - pr[u]) : 0ull, r.a + off, r.c[u], v, pr[u]);
+    }
+    return t;
+}
+
+// Same scan with the price mirror addressed explicitly in shared space (`price_saddr` = shared address of price 0).
+template <int RPL>
+__device__ __forceinline__ LaneTop2 lane_scan_regs_smem(const RowRegs<RPL>& r, uint32_t price_saddr, uint32_t flip, int lane32) {
+    LaneTop2 t;
+    lane_top2_init(t);
+    double pr[RPL];
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) pr[u] = lds_f64(price_saddr + 8u * r.c[u]);
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) {
+        const uint32_t off = (uint32_t)lane32 + 32u * (uint32_t)u;
+        const double v = __hiloint2double(__double2hiint(r.v[u]) ^ (int)flip, __double2loint(r.v[u]));
+        lane_top2_update(t, (off < r.len) ? profit_key(v - pr[u]) : 0ull, r.a + off, r.c[u], v, pr[u]);
+    }
+    return t;
 }
 
 // Outcome of one person's bid: object (SLA_DEV_NONE = dropped by the Khosla threshold) and exact bid.
@@ -425,6 +597,30 @@ __device__ __forceinline__ Bid make_bid_warp(const WarpChoice& c, uint32_t algo,
         r.obj = c.col;
     }
     *owner_out = own;
+    if (algo == ALGO_KHOSLA) {
+        if (pj > threshold) { r.dropped = true; r.bid = 0.0; return r; }
+        r.bid = is_finite_f64(c.second) ? (c.value - c.second + eps) : (pj + eps);
+    } else {
+        r.bid = c.value - c.second + eps;
+    }
+    return r;
+}
+
+// Bid from a WarpChoice whose owner has been settled by the caller (same expressions as make_bid): Khosla
+// ksparse.rs:218-227, Forward symmetric.rs:378.  A row without a usable arc stays on object 0 (ksparse.rs:196,
+// symmetric.rs:355).
+template <int MODE>
+__device__ __forceinline__ Bid make_bid_choice(const WarpChoice& c, uint32_t algo, double eps, double threshold,
+                                               const double* prices) {
+    Bid r;
+    r.dropped = false;
+    double pj = c.price;
+    if (c.pos == SLA_DEV_NONE) {
+        r.obj = 0u;
+        pj = ld_price<MODE>(prices, 0u);
+    } else {
+        r.obj = c.col;
+    }
     if (algo == ALGO_KHOSLA) {
         if (pj > threshold) { r.dropped = true; r.bid = 0.0; return r; }
         r.bid = is_finite_f64(c.second) ? (c.value - c.second + eps) : (pj + eps);

@@ -289,22 +289,19 @@ __device__ __forceinline__ uint32_t control_after_wide(DevState* st) {
 // =============================================================================================================
 // SPRICES: the object prices are mirrored in dynamic shared memory for the lifetime of the launch (write-through to
 // global), which removes k scattered L1 misses per bidder -- the single SM's miss throughput, not latency, is
-// what bounds a tail round otherwise (profiles/README.md).
+// what bounds a tail round otherwise (profiles/README.md).  DevState::own_mode says whether the owners (o2p) are
+// mirrored as well (1: u32, 2: u16); DevState::tail_cap is the capacity of the queue arrays.  The host sizes the
+// dynamic shared memory with tail_smem_bytes() from the same three facts.
 template <int LPR, bool SPRICES>
 __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    double* s_prices = reinterpret_cast<double*>(s_dyn);
-    unsigned long long* h_word = reinterpret_cast<unsigned long long*>(s_dyn + (SPRICES ? kTailSmemPriceCols * sizeof(double) : 0));
-    uint32_t* h_key = reinterpret_cast<uint32_t*>(h_word + kTailHashSlots);
-    __shared__ uint32_t s_hslot[kTailCap];
-    __shared__ uint32_t s_queue[2][kTailCap];
-    __shared__ uint32_t s_obj[kTailCap];
-    __shared__ double s_bid[kTailCap];
     __shared__ unsigned long long s_word[32];
-    __shared__ uint32_t s_prev[kTailCap];
+    __shared__ uint32_t s_sobj[32];
     __shared__ uint32_t s_warp_cnt[kTailThreads / 32];
     __shared__ uint32_t s_ctl[2];
-    __shared__ uint32_t s_next_len;
+    __shared__ uint32_t s_next[32];
+    struct SmallFin { uint32_t qlen, nits, hit_limit, pad; unsigned long long safety, rounds_done, bids_done; };
+    __shared__ SmallFin s_fin;
     __shared__ unsigned long long s_arcs;
     __shared__ uint32_t s_dropped;
 
@@ -343,14 +340,34 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     uint32_t nits = st->nits;
     unsigned long long safety = st->safety_rounds_left;
     const uint32_t round_cap = st->tail_round_cap;
+    const uint32_t n_cols = st->n_cols, own_mode = st->own_mode, cap = st->tail_cap;
+
+    // ---- carve the dynamic shared memory (same arithmetic as tail_smem_bytes) ----
+    const TailSmemLayout lay = tail_smem_layout(SPRICES, own_mode, n_cols, cap);
+    double* const s_prices = reinterpret_cast<double*>(s_dyn);
+    OwnerView own;
+    own.g = p.o2p;
+    own.s32 = (own_mode == 1u) ? reinterpret_cast<uint32_t*>(s_dyn + lay.owners) : nullptr;
+    own.s16 = (own_mode == 2u) ? reinterpret_cast<uint16_t*>(s_dyn + lay.owners) : nullptr;
+    unsigned long long* const h_word = reinterpret_cast<unsigned long long*>(s_dyn + lay.hash_words);
+    uint32_t* const h_key = reinterpret_cast<uint32_t*>(s_dyn + lay.hash_keys);
+    double* const s_bid = reinterpret_cast<double*>(s_dyn + lay.bid);
+    uint32_t* const s_queue0 = reinterpret_cast<uint32_t*>(s_dyn + lay.queue0);
+    uint32_t* const s_queue1 = s_queue0 + cap;
+    uint32_t* const s_obj = s_queue1 + cap;
+    uint32_t* const s_prev = s_obj + cap;
+    uint32_t* const s_hslot = s_prev + cap;
+    const uint32_t hslots = 2u * cap, hshift = 32u - (uint32_t)__ffs((int)hslots) + 1u;   // hslots is a power of two
 
     uint32_t* gqueue = cur ? p.queue[1] : p.queue[0];
-    for (uint32_t q = tid; q < qlen; q += kTailThreads) s_queue[0][q] = identity ? q : gqueue[q];
-    if (SPRICES) {
-        const uint32_t n_cols = st->n_cols;
+    for (uint32_t q = tid; q < qlen; q += kTailThreads) s_queue0[q] = identity ? q : gqueue[q];
+    if (SPRICES)
         for (uint32_t j = tid; j < n_cols; j += kTailThreads) s_prices[j] = zero ? 0.0 : p.prices[j];
-    }
-    for (uint32_t h = tid; h < (uint32_t)kTailHashSlots; h += kTailThreads) { h_key[h] = SLA_DEV_NONE; h_word[h] = 0ull; }
+    if (own.s32)
+        for (uint32_t j = tid; j < n_cols; j += kTailThreads) own.s32[j] = p.o2p[j];
+    if (own.s16)
+        for (uint32_t j = tid; j < n_cols; j += kTailThreads) own.s16[j] = (uint16_t)p.o2p[j];
+    for (uint32_t h = tid; h < hslots; h += kTailThreads) { h_key[h] = SLA_DEV_NONE; h_word[h] = 0ull; }
     __syncthreads();
     constexpr int kPriceMode = SPRICES ? PRICE_SMEM : PRICE_CA;
     const double* price_src = SPRICES ? s_prices : p.prices;
@@ -364,47 +381,157 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     bool hit_limit = false;
 
 #ifdef SLA_TAIL_TIMING
-    long long tk0 = clock64(), tk_scan = 0, tk_bid = 0, tk_bar1 = 0, tk_asg = 0, tk_bar2 = 0, tk1, tk2;
-#define TK(acc) do { tk2 = clock64(); acc += tk2 - tk1; tk1 = tk2; } while (0)
+    // Development instrumentation: cycle stamps of the busiest warp of the small rounds.  Each stamp is taken behind an
+    // instruction that consumes `dep`, so that it is not issued before that value has arrived.
+    long long tk0 = clock64(), tk1 = 0, tkv[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long act_rounds = 0;
+    __shared__ unsigned long long s_busiest;
+    if (tid == 0) s_busiest = 0ull;
+#define TK(i, dep) do { unsigned long long t_; asm volatile("{\n .reg .pred p;\n setp.eq.u32 p, %1, 0x7ffffff1;\n @p trap;\n mov.u64 %0, %%clock64;\n}" \
+        : "=l"(t_) : "r"((uint32_t)(dep)) : "memory"); tkv[i] += (long long)t_ - tk1; tk1 = (long long)t_; } while (0)
 #else
-#define TK(acc) do { } while (0)
+#define TK(i, dep) do { } while (0)
 #endif
     while (true) {
-        const bool small = qlen <= 32u;
+        if (qlen <= kTailSlots) {
+            // =================================================================================================
+            // Small rounds (<= one bidder per warp): slot-stable, one warp per slot.  Warp q keeps serving "slot q":
+            // after a round the slot holds the loser itself, the owner it evicted, or nothing -- no queue compaction,
+            // no single-warp assignment phase.  Warps whose slot is empty SLEEP at barrier 0 until the engine is done;
+            // the bidders of a round synchronise among themselves on barrier 1 (bar.sync 1, 32 * #bidders), so an
+            // empty slot costs neither issue slots nor barrier latency.  The row of the slot's person lives in
+            // registers (rows of <= 32 RPL arcs); the row of the owner that would be evicted is fetched as soon as the
+            // choice is known, so that its L2 latency hides behind the bid arithmetic, both barriers and the conflict
+            // resolution.  Conflicts: every bidder compares its own packed word with the words of all slots (one
+            // vote).  A Jacobi round is independent of the order of its bidders, so the results equal the compacting
+            // formulation bit for bit.
+            // =================================================================================================
+            constexpr int RPL = (LPR <= 8) ? 1 : 2;
+            const uint32_t* sq0 = buf ? s_queue1 : s_queue0;
+            uint32_t mask = (qlen == 32u) ? 0xffffffffu : ((1u << qlen) - 1u);   // qlen <= kTailSlots <= 32
+            bool active = (uint32_t)warp < qlen;
+            uint32_t person = active ? sq0[warp] : 0u;
+            __syncthreads();                             // the queue buffer is rewritten at the end
+            if (active) {
+                // shared-space bases, computed once (sla_common.cuh: smem_base_u32)
+                const uint32_t a_sobj = smem_base_u32(s_sobj), a_word = smem_base_u32(s_word), a_next = smem_base_u32(s_next);
+                const uint32_t a_prices = smem_base_u32(s_prices);
+                const uint32_t a_own = smem_base_u32(s_dyn + lay.owners);
+                RowRegs<RPL> row;
+                row_extents<RPL>(row, p.row_ptr, regK, person);
+                row_load<RPL>(row, p.cols, p.vals, lane32);
+                while (true) {
+                    const uint32_t nthreads = 32u * (uint32_t)__popc(mask);
 #ifdef SLA_TAIL_TIMING
-        tk1 = clock64();
+                    if (tk1 == 0) tk1 = clock64();
+                    act_rounds += 1;
 #endif
-        // ---- bidding phase ----
-        const uint32_t* sq = s_queue[buf];
-        if (small) {
-            // one warp per bidder: REDUX reductions on integer profit keys (sla_common.cuh: warp_bid_scan)
-            if ((uint32_t)warp < qlen) {
-                const uint32_t q = (uint32_t)warp;
-                const uint32_t i = sq[q];
-                uint32_t a, b;
-                if (regK) { a = i * regK; b = a + regK; }
-                else { a = __ldg(p.row_ptr + i); b = __ldg(p.row_ptr + i + 1); }
-                WarpChoice c;
-                if (zero) c = warp_bid_scan<PRICE_ZERO, OWN_NONE>(p.cols, p.vals, price_src, p.o2p, a, b, sign_flip, lane32);
-                else      c = warp_bid_scan<kPriceMode, OWN_GLOBAL>(p.cols, p.vals, price_src, p.o2p, a, b, sign_flip, lane32);
-                TK(tk_scan);
-                if (lane32 == 0) {
-                    uint32_t owner;
-                    const Bid r = zero ? make_bid_warp<PRICE_ZERO, OWN_NONE>(c, algo, eps, thr, price_src, p.o2p, &owner)
-                                       : make_bid_warp<kPriceMode, OWN_GLOBAL>(c, algo, eps, thr, price_src, p.o2p, &owner);
-                    my_arcs += (unsigned long long)(b - a);
-                    if (r.dropped) {
-                        s_obj[q] = SLA_DEV_NONE;
-                        my_dropped += 1;
+                    // ---- bid ----
+                    uint32_t obj = SLA_DEV_NONE, prev = SLA_DEV_NONE;
+                    unsigned long long word = 0ull;
+                    double bid = 0.0;
+                    RowRegs<RPL> nrow;
+                    nrow.a = 0u; nrow.len = 0u;
+                    WarpChoice c;
+                    if (row.len <= 32u * RPL) {
+                        const LaneTop2 t = SPRICES ? lane_scan_regs_smem<RPL>(row, a_prices, sign_flip, lane32)
+                                                   : lane_scan_regs<RPL, PRICE_CA>(row, p.prices, sign_flip, lane32);
+                        TK(0, t.k1);
+                        if (own_mode) c = warp_choice_finish<OWN_NONE>(t, nullptr);
+                        else c = warp_choice_finish<OWN_GLOBAL>(t, p.o2p);
                     } else {
-                        s_obj[q] = r.obj;
-                        s_bid[q] = r.bid;
-                        s_prev[q] = owner;
-                        s_word[q] = (r.bid == r.bid) ? pack_bid(r.bid, i, pbits) : 0ull;   // NaN never bids
+                        if (own_mode) c = warp_bid_scan<kPriceMode, OWN_NONE>(p.cols, p.vals, price_src, nullptr, row.a, row.a + row.len, sign_flip, lane32);
+                        else c = warp_bid_scan<kPriceMode, OWN_GLOBAL>(p.cols, p.vals, price_src, p.o2p, row.a, row.a + row.len, sign_flip, lane32);
                     }
+                    TK(1, c.col);
+                    // owner of the chosen object (c.col is 0 for a row without usable arc, like the reference's start object)
+                    if (own_mode == 1u) c.owner = lds_u32(a_own + 4u * c.col);
+                    else if (own_mode == 2u) { const uint32_t o16 = lds_u16(a_own + 2u * c.col); c.owner = (o16 == 0xFFFFu) ? SLA_DEV_NONE : o16; }
+                    else if (c.pos == SLA_DEV_NONE) c.owner = ld_ca_u32(p.o2p);
+                    prev = c.owner;
+                    TK(2, prev);
+                    if (prev != SLA_DEV_NONE) {          // whoever wins this object evicts `prev`: fetch its row now
+                        row_extents<RPL>(nrow, p.row_ptr, regK, prev);
+                        row_load<RPL>(nrow, p.cols, p.vals, lane32);
+                    }
+                    const Bid r = make_bid_choice<kPriceMode>(c, algo, eps, thr, price_src);
+                    if (lane32 == 0) my_arcs += (unsigned long long)row.len;
+                    if (r.dropped) {
+                        if (lane32 == 0) my_dropped += 1;
+                    } else {
+                        obj = r.obj;
+                        bid = r.bid;
+                        word = (r.bid == r.bid) ? pack_bid(r.bid, person, pbits) : 0ull;   // NaN never bids
+                    }
+                    TK(3, (uint32_t)word);
+                    if (lane32 == 0) { sts_u32(a_sobj + 4u * (uint32_t)warp, obj); sts_u64(a_word + 8u * (uint32_t)warp, word); }
+                    TK(4, 0);
+                    named_bar_sync(nthreads);
+                    TK(5, 0);
+                    // ---- resolve + assign ----
+                    const bool lv = ((mask >> lane32) & 1u) != 0u;
+                    bool next_active = false;
+                    if (obj != SLA_DEV_NONE) {
+                        const uint32_t ro = lv ? lds_u32(a_sobj + 4u * (uint32_t)lane32) : SLA_DEV_NONE;
+                        const unsigned long long rw = lv ? lds_u64(a_word + 8u * (uint32_t)lane32) : 0ull;
+                        const bool lost = __any_sync(0xffffffffu, ro == obj && rw > word);
+                        TK(6, lost);
+                        if (word != 0ull && !lost) {     // word 0 == NaN bid: never wins
+                            if (lane32 == 0) {
+                                p.prices[obj] = bid;
+                                if (SPRICES) sts_f64(a_prices + 8u * obj, bid);
+                                p.o2p[obj] = person;
+                                if (own_mode == 1u) sts_u32(a_own + 4u * obj, person);
+                                else if (own_mode == 2u) sts_u16(a_own + 2u * obj, person);
+                                p.p2o[person] = obj;
+                                if (prev != SLA_DEV_NONE) p.p2o[prev] = SLA_DEV_NONE;
+                            }
+                            if (prev != SLA_DEV_NONE) { person = prev; row = nrow; next_active = true; }
+                        } else {
+                            next_active = true;          // lost: bids again
+                        }
+                        TK(7, row.c[0]);
+                    }
+                    if (lane32 == 0) sts_u32(a_next + 4u * (uint32_t)warp, next_active ? 1u : 0u);
+                    TK(8, 0);
+                    named_bar_sync(nthreads);
+                    TK(9, 0);
+                    const uint32_t nmask = __ballot_sync(0xffffffffu, lv && lds_u32(a_next + 4u * (uint32_t)lane32) != 0u);
+                    bids_done += (unsigned long long)__popc(mask);
+                    rounds_done += 1;
+                    const uint32_t pmask = mask;
+                    mask = nmask;
+                    qlen = (uint32_t)__popc(mask);
+                    if (algo == ALGO_FORWARD) nits += 1;
+                    TK(10, qlen);
+                    bool finish = false;
+                    if (qlen == 0) finish = true;
+                    else if (algo == ALGO_FORWARD && nits >= max_it) { hit_limit = true; finish = true; }   // symmetric.rs:326-328
+                    else if (safety <= 1) { hit_limit = true; finish = true; }
+                    else {
+                        safety -= 1;
+                        if (rounds_done >= round_cap) finish = true;
+                    }
+                    if (finish) {
+                        // every bidder of the last round holds the same complete counters: the lowest one publishes them
+                        if (lane32 == 0 && (uint32_t)warp == (uint32_t)__ffs((int)pmask) - 1u) {
+                            s_fin.qlen = qlen; s_fin.nits = nits; s_fin.hit_limit = hit_limit ? 1u : 0u;
+                            s_fin.safety = safety; s_fin.rounds_done = rounds_done; s_fin.bids_done = bids_done;
+                        }
+                        // compact the surviving slots into the queue buffer for the write-back below
+                        if (next_active && lane32 == 0) (buf ? s_queue1 : s_queue0)[__popc(mask & ((1u << warp) - 1u))] = person;
+                        break;
+                    }
+                    if (!next_active) break;             // this slot is empty from now on: sleep until the engine is done
                 }
             }
-        } else {
+            __syncthreads();
+            qlen = s_fin.qlen; nits = s_fin.nits; hit_limit = s_fin.hit_limit != 0u;
+            safety = s_fin.safety; rounds_done = s_fin.rounds_done; bids_done = s_fin.bids_done;
+            break;
+        }
+        // ---- bidding phase (33 .. cap bidders): one group of LPR lanes per bidder ----
+        const uint32_t* sq = buf ? s_queue1 : s_queue0;
         for (uint32_t base = 0; base < qlen; base += NGROUPS) {
             // warps none of whose groups has a bidder leave (warp-uniform, so the full-mask shuffles stay legal):
             // idle warps must not burn issue slots on the reduction while one or two warps do the real work
@@ -423,9 +550,9 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
             else      scan_row<LPR, kPriceMode, false>(c, p.cols, p.vals, price_src, a, b, sign_flip, lane);
             // speculative: the owner of each lane's local best column, issued before the reduction so that its latency
             // hides behind the shuffles (nobody owns anything while all prices are still zero)
-            if (!zero && c.pos != SLA_DEV_NONE) c.aux = ld_ca_u32(p.o2p + c.col);
+            if (!zero && c.pos != SLA_DEV_NONE) c.aux = own.load(c.col);
             choice_group_reduce<LPR>(c);
-            if (valid && lane == 0 && !zero && c.pos == SLA_DEV_NONE) c.aux = ld_ca_u32(p.o2p);   // row without usable arc -> object 0
+            if (valid && lane == 0 && !zero && c.pos == SLA_DEV_NONE) c.aux = own.load(0u);   // row without usable arc -> object 0
             if (valid && lane == 0) {
                 const Bid r = zero ? make_bid<PRICE_ZERO>(c, algo, eps, thr, price_src)
                                    : make_bid<kPriceMode>(c, algo, eps, thr, price_src);
@@ -438,11 +565,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                     s_bid[q] = r.bid;
                     s_prev[q] = c.aux;                      // owner of r.obj (only the winner uses it)
                     if (r.bid == r.bid) {                   // NaN never bids
-                        uint32_t h = (r.obj * 2654435761u) >> (32 - kTailHashBits);
+                        uint32_t h = (r.obj * 2654435761u) >> hshift;
                         while (true) {
                             const uint32_t old = atomicCAS(h_key + h, SLA_DEV_NONE, r.obj);
                             if (old == SLA_DEV_NONE || old == r.obj) break;
-                            h = (h + 1u) & (uint32_t)(kTailHashSlots - 1);
+                            h = (h + 1u) & (hslots - 1u);
                         }
                         atomicMax(h_word + h, pack_bid(r.bid, i, pbits));
                         s_hslot[q] = h;
@@ -450,100 +577,56 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                 }
             }
         }
-        }
-        TK(tk_bid);
         __syncthreads();
-        TK(tk_bar1);
 
         // ---- assignment phase + deterministic compaction into the other smem queue ----
-        uint32_t* nq = s_queue[buf ^ 1u];
+        uint32_t* nq = buf ? s_queue0 : s_queue1;
         uint32_t out = 0;
-        if (small) {
-            if (warp == 0) {
-                const uint32_t q = (uint32_t)lane32;
-                const bool live = q < qlen;
-                uint32_t j = live ? s_obj[q] : SLA_DEV_NONE;
-                const bool bidding = j != SLA_DEV_NONE;            // not dropped by the Khosla threshold
-                const uint32_t i = live ? sq[q] : 0u;
-                const unsigned long long w = bidding ? s_word[q] : 0ull;
-                const double bid = bidding ? s_bid[q] : 0.0;
-                const uint32_t prev = bidding ? s_prev[q] : SLA_DEV_NONE;
-                // lanes that bid on the same object; idle lanes get unique keys so that they match nobody
-                const uint32_t peers = __match_any_sync(0xffffffffu, bidding ? j : (0xFFFFFF00u + (uint32_t)lane32));
-                bool won = bidding && (w != 0ull);                  // word 0 == NaN bid: never wins
-                if (__any_sync(0xffffffffu, bidding && (peers & (peers - 1u)) != 0u)) {
-                    // rare: at least two bidders share an object -> compare words lane by lane (warp-uniform loop)
-                    for (uint32_t r = 0; r < qlen; ++r) {
-                        const unsigned long long ow = __shfl_sync(0xffffffffu, w, (int)r);
-                        won = won && !(((peers >> r) & 1u) && ow > w);
-                    }
-                }
-                uint32_t emit = SLA_DEV_NONE;
-                if (bidding) {
+        for (uint32_t base = 0; base < qlen; base += kTailThreads) {
+            const uint32_t q = base + tid;
+            uint32_t emit = SLA_DEV_NONE;
+            if (q < qlen) {
+                const uint32_t j = s_obj[q];
+                if (j != SLA_DEV_NONE) {
+                    const uint32_t i = sq[q];
+                    const double bid = s_bid[q];
+                    const uint32_t prev = s_prev[q];
+                    const bool won = (bid == bid) && (h_word[s_hslot[q]] == pack_bid(bid, i, pbits));
                     if (won) {
                         p.prices[j] = bid;
                         if (SPRICES) s_prices[j] = bid;
                         p.o2p[j] = i;
+                        own.store_mirror(j, i);
                         p.p2o[i] = j;
                         if (prev != SLA_DEV_NONE) { p.p2o[prev] = SLA_DEV_NONE; emit = prev; }
                     } else {
                         emit = i;
                     }
                 }
-                const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
-                if (emit != SLA_DEV_NONE) nq[__popc(ballot & ((1u << lane32) - 1u))] = emit;
-                if (lane32 == 0) s_next_len = __popc(ballot);
             }
-            TK(tk_asg);
+            const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
+            if (lane32 == 0) s_warp_cnt[warp] = __popc(ballot);
             __syncthreads();
-            TK(tk_bar2);
-            out = s_next_len;
-        } else {
-            for (uint32_t base = 0; base < qlen; base += kTailThreads) {
-                const uint32_t q = base + tid;
-                uint32_t emit = SLA_DEV_NONE;
-                if (q < qlen) {
-                    const uint32_t j = s_obj[q];
-                    if (j != SLA_DEV_NONE) {
-                        const uint32_t i = sq[q];
-                        const double bid = s_bid[q];
-                        const uint32_t prev = s_prev[q];
-                        const bool won = (bid == bid) && (h_word[s_hslot[q]] == pack_bid(bid, i, pbits));
-                        if (won) {
-                            p.prices[j] = bid;
-                            if (SPRICES) s_prices[j] = bid;
-                            p.o2p[j] = i;
-                            p.p2o[i] = j;
-                            if (prev != SLA_DEV_NONE) { p.p2o[prev] = SLA_DEV_NONE; emit = prev; }
-                        } else {
-                            emit = i;
-                        }
-                    }
-                }
-                const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
-                if (lane32 == 0) s_warp_cnt[warp] = __popc(ballot);
-                __syncthreads();
-                uint32_t off = 0, total = 0;
+            uint32_t off = 0, total = 0;
 #pragma unroll
-                for (int w = 0; w < kTailThreads / 32; ++w) {
-                    const uint32_t cnt = s_warp_cnt[w];
-                    off += (w < warp) ? cnt : 0u;
-                    total += cnt;
-                }
-                if (emit != SLA_DEV_NONE) nq[out + off + __popc(ballot & ((1u << lane32) - 1u))] = emit;
-                out += total;
-                __syncthreads();
+            for (int w = 0; w < kTailThreads / 32; ++w) {
+                const uint32_t cnt = s_warp_cnt[w];
+                off += (w < warp) ? cnt : 0u;
+                total += cnt;
             }
-            // every word has been compared: empty the table entries this round used
-            for (uint32_t q = tid; q < qlen; q += kTailThreads) {
-                if (s_obj[q] != SLA_DEV_NONE && s_bid[q] == s_bid[q]) {
-                    const uint32_t h = s_hslot[q];
-                    h_key[h] = SLA_DEV_NONE;
-                    h_word[h] = 0ull;
-                }
-            }
+            if (emit != SLA_DEV_NONE) nq[out + off + __popc(ballot & ((1u << lane32) - 1u))] = emit;
+            out += total;
             __syncthreads();
         }
+        // every word has been compared: empty the table entries this round used
+        for (uint32_t q = tid; q < qlen; q += kTailThreads) {
+            if (s_obj[q] != SLA_DEV_NONE && s_bid[q] == s_bid[q]) {
+                const uint32_t h = s_hslot[q];
+                h_key[h] = SLA_DEV_NONE;
+                h_word[h] = 0ull;
+            }
+        }
+        __syncthreads();
 
         bids_done += qlen;
         rounds_done += 1;
@@ -561,7 +644,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     // ---- write the state back ----
     if (my_arcs) atomicAdd(&s_arcs, my_arcs);
     if (my_dropped) atomicAdd(&s_dropped, my_dropped);
-    for (uint32_t q = tid; q < qlen; q += kTailThreads) gqueue[q] = s_queue[buf][q];
+    for (uint32_t q = tid; q < qlen; q += kTailThreads) gqueue[q] = (buf ? s_queue1 : s_queue0)[q];
     __syncthreads();
     if (tid == 0) {
         st->rounds += rounds_done;
@@ -578,14 +661,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
         else if (qlen == 0) finish_if_possible(st);
 #ifdef SLA_TAIL_TIMING
         st->dbg[0] += (unsigned long long)(clock64() - tk0);
-        st->dbg[1] += (unsigned long long)tk_scan;
-        st->dbg[3] += (unsigned long long)tk_bar1;
-        st->dbg[4] += (unsigned long long)tk_asg;
-        st->dbg[5] += (unsigned long long)tk_bar2;
         st->dbg[6] += rounds_done;
-        st->dbg[7] += (unsigned long long)tk_bid;
 #endif
     }
+#ifdef SLA_TAIL_TIMING
+    if (lane32 == 0) atomicMax(&s_busiest, (act_rounds << 5) | (unsigned long long)warp);
+    __syncthreads();
+    if (lane32 == 0 && (s_busiest & 31ull) == (unsigned long long)warp && act_rounds) {
+        st->dbg[7] += act_rounds;
+        for (int i = 0; i < 12; ++i) st->dbg[8 + i] += (unsigned long long)tkv[i];
+    }
+#endif
     __syncthreads();
     if (tid < kStateWords) reinterpret_cast<uint4*>(gst)[tid] = reinterpret_cast<const uint4*>(st)[tid];
 #undef TK
