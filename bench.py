@@ -416,6 +416,9 @@ def main_ours(args):
     for _ in range(args.steps):
         if small_inputs:
             flush_l2(torch, device)
+            torch.cuda.synchronize(device)         # the flush runs on torch's stream, the solve on the context's own:
+                                                   # without this they would overlap (no flush, and a solve timed under
+                                                   # 512 MB of foreign HBM traffic)
         st = resident.solve_resident(False, eps)
         arcs += st["bid_arcs"]
         launches += st["kernel_launches"]

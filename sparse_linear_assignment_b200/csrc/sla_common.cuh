@@ -15,9 +15,9 @@ namespace sla {
 constexpr int kTailCap = 1024;       // max bidders the single-CTA tail engine accepts (smem-resident queue)
 constexpr int kWideThreads = 256;    // block size of the grid-wide kernels
 #ifndef SLA_TAIL_THREADS
-#define SLA_TAIL_THREADS 1024
+#define SLA_TAIL_THREADS 768
 #endif
-constexpr int kTailThreads = SLA_TAIL_THREADS;   // block size of the tail engine
+constexpr int kTailThreads = SLA_TAIL_THREADS;   // block size of the tail engine (24 warps: 80 registers per thread)
 constexpr uint32_t kTailSlots = kTailThreads / 32;   // bidders of a "small" round: one warp per slot
 
 enum : uint32_t { ALGO_KHOSLA = 0, ALGO_FORWARD = 1 };
@@ -214,6 +214,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
     return r;
 }
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
+    return r;
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     uint32_t r;
     asm volatile("{\n .reg .u16 t;\n ld.shared.u16 t, [%1];\n cvt.u32.u16 %0, t;\n}" : "=r"(r) : "r"(a) : "memory");
@@ -225,6 +230,8 @@ __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
     asm volatile("{\n .reg .u16 t;\n cvt.u16.u32 t, %1;\n st.shared.u16 [%0], t;\n}" :: "r"(a), "r"(v) : "memory");
 }
+// First caller wins (small rounds: which of the equally informed last bidders publishes the totals).
+__device__ __forceinline__ bool s_fin_claim(uint32_t* flag) { return atomicExch(flag, 1u) == 0u; }
 // Barrier among the first-class participants of a small round only (warps whose slot is empty sleep at barrier 0).
 __device__ __forceinline__ void named_bar_sync(uint32_t nthreads) {
     asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory");
@@ -506,17 +513,20 @@ __device__ __forceinline__ void row_extents(RowRegs<RPL>& r, const uint32_t* __r
     else { r.a = __ldg(row_ptr + person); r.len = __ldg(row_ptr + person + 1) - r.a; }
 }
 
+// `cols_lane` / `vals_lane` are the array bases already advanced by the lane index.
 template <int RPL>
-__device__ __forceinline__ void row_load(RowRegs<RPL>& r, const uint32_t* __restrict__ cols, const double* __restrict__ vals,
+__device__ __forceinline__ void row_load(RowRegs<RPL>& r, const uint32_t* __restrict__ cols_lane, const double* __restrict__ vals_lane,
                                          int lane32) {
+    const uint32_t* pc = cols_lane + r.a;
+    const double* pv = vals_lane + r.a;
 #pragma unroll
     for (int t = 0; t < RPL; ++t) {
         const uint32_t off = (uint32_t)lane32 + 32u * (uint32_t)t;
         r.c[t] = 0u;
         r.v[t] = 0.0;
         if (off < r.len && r.len <= 32u * RPL) {
-            r.c[t] = __ldg(cols + r.a + off);
-            r.v[t] = __ldg(vals + r.a + off);
+            r.c[t] = __ldg(pc + 32 * t);
+            r.v[t] = __ldg(pv + 32 * t);
         }
     }
 }

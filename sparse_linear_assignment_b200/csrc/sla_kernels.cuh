@@ -295,12 +295,10 @@ __device__ __forceinline__ uint32_t control_after_wide(DevState* st) {
 template <int LPR, bool SPRICES>
 __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    __shared__ unsigned long long s_word[32];
-    __shared__ uint32_t s_sobj[32];
+    __shared__ __align__(16) uint4 s_xchg[32];   // small rounds: per slot {packed word (2 x u32), object, still-active flag}
     __shared__ uint32_t s_warp_cnt[kTailThreads / 32];
     __shared__ uint32_t s_ctl[2];
-    __shared__ uint32_t s_next[32];
-    struct SmallFin { uint32_t qlen, nits, hit_limit, pad; unsigned long long safety, rounds_done, bids_done; };
+    struct SmallFin { uint32_t qlen, nits, hit_limit, claimed; unsigned long long safety, rounds_done, bids_done; };
     __shared__ SmallFin s_fin;
     __shared__ unsigned long long s_arcs;
     __shared__ uint32_t s_dropped;
@@ -323,6 +321,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
         s_ctl[1] = qlen0;
         s_arcs = 0;
         s_dropped = 0;
+        s_fin.claimed = 0u;
     }
     __syncthreads();
     if (!s_ctl[0]) {
@@ -413,15 +412,31 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
             uint32_t person = active ? sq0[warp] : 0u;
             __syncthreads();                             // the queue buffer is rewritten at the end
             if (active) {
-                // shared-space bases, computed once (sla_common.cuh: smem_base_u32)
-                const uint32_t a_sobj = smem_base_u32(s_sobj), a_word = smem_base_u32(s_word), a_next = smem_base_u32(s_next);
-                const uint32_t a_prices = smem_base_u32(s_prices);
-                const uint32_t a_own = smem_base_u32(s_dyn + lay.owners);
+                // Shared-space addresses, computed once.  `opq` is a run-time zero the compiler cannot see through: without
+                // it ptxas rematerialises the bases inside the loop (S2UR SR_CgaCtaId / SR_SWINHI chains per access).
+                const uint32_t opq = st->hot_pad[0];
+                const uint32_t a_xchg = smem_base_u32(s_xchg) + opq;
+                const uint32_t a_mine = a_xchg + 16u * (uint32_t)warp, a_lane = a_xchg + 16u * (uint32_t)lane32;
+                const uint32_t a_prices = smem_base_u32(s_prices) + opq;
+                const uint32_t a_own = smem_base_u32(s_dyn + lay.owners) + opq;
+                const uint32_t* const cols_lane = p.cols + lane32;
+                const double* const vals_lane = p.vals + lane32;
+                // Rounds this engine may still run: the limit that ends the solve (max_iterations of the Forward solver,
+                // symmetric.rs:326-328, or the safety budget) and the hand-back cap of one launch, as one countdown.
+                const unsigned long long lim_iter = (algo == ALGO_FORWARD) ? (nits < max_it ? (unsigned long long)(max_it - nits) : 1ull) : ~0ull;
+                const unsigned long long lim_hit = lim_iter < safety ? lim_iter : (safety ? safety : 1ull);
+                const unsigned long long lim_cap = rounds_done < round_cap ? (unsigned long long)round_cap - rounds_done : 1ull;
+                unsigned long long lim = lim_hit < lim_cap ? lim_hit : lim_cap;
+                const bool budget_ends_solve = lim_hit <= lim_cap && lim <= 0x7fffffffull;   // running out of budget == hitting a limit
+                if (lim > 0x7fffffffull) lim = 0x7fffffffull;
+                const uint32_t budget = (uint32_t)lim;
+                uint32_t left = budget, bids_local = 0u, arcs_local = 0u;
                 RowRegs<RPL> row;
                 row_extents<RPL>(row, p.row_ptr, regK, person);
-                row_load<RPL>(row, p.cols, p.vals, lane32);
+                row_load<RPL>(row, cols_lane, vals_lane, lane32);
+                bool next_active = false;
                 while (true) {
-                    const uint32_t nthreads = 32u * (uint32_t)__popc(mask);
+                    const uint32_t nbid = (uint32_t)__popc(mask);
 #ifdef SLA_TAIL_TIMING
                     if (tk1 == 0) tk1 = clock64();
                     act_rounds += 1;
@@ -452,10 +467,10 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                     TK(2, prev);
                     if (prev != SLA_DEV_NONE) {          // whoever wins this object evicts `prev`: fetch its row now
                         row_extents<RPL>(nrow, p.row_ptr, regK, prev);
-                        row_load<RPL>(nrow, p.cols, p.vals, lane32);
+                        row_load<RPL>(nrow, cols_lane, vals_lane, lane32);
                     }
                     const Bid r = make_bid_choice<kPriceMode>(c, algo, eps, thr, price_src);
-                    if (lane32 == 0) my_arcs += (unsigned long long)row.len;
+                    arcs_local += row.len;
                     if (r.dropped) {
                         if (lane32 == 0) my_dropped += 1;
                     } else {
@@ -464,17 +479,18 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                         word = (r.bid == r.bid) ? pack_bid(r.bid, person, pbits) : 0ull;   // NaN never bids
                     }
                     TK(3, (uint32_t)word);
-                    if (lane32 == 0) { sts_u32(a_sobj + 4u * (uint32_t)warp, obj); sts_u64(a_word + 8u * (uint32_t)warp, word); }
+                    if (lane32 == 0) { sts_u64(a_mine, word); sts_u32(a_mine + 8u, obj); }
                     TK(4, 0);
-                    named_bar_sync(nthreads);
+                    named_bar_sync(32u * nbid);
                     TK(5, 0);
                     // ---- resolve + assign ----
                     const bool lv = ((mask >> lane32) & 1u) != 0u;
-                    bool next_active = false;
+                    next_active = false;
                     if (obj != SLA_DEV_NONE) {
-                        const uint32_t ro = lv ? lds_u32(a_sobj + 4u * (uint32_t)lane32) : SLA_DEV_NONE;
-                        const unsigned long long rw = lv ? lds_u64(a_word + 8u * (uint32_t)lane32) : 0ull;
-                        const bool lost = __any_sync(0xffffffffu, ro == obj && rw > word);
+                        uint4 rec = make_uint4(0u, 0u, SLA_DEV_NONE, 0u);
+                        if (lv) rec = lds_u128(a_lane);  // {word lo, word hi, object, flag of the previous round}
+                        const unsigned long long rw = ((unsigned long long)rec.y << 32) | rec.x;
+                        const bool lost = __any_sync(0xffffffffu, rec.z == obj && rw > word);
                         TK(6, lost);
                         if (word != 0ull && !lost) {     // word 0 == NaN bid: never wins
                             if (lane32 == 0) {
@@ -492,38 +508,34 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                         }
                         TK(7, row.c[0]);
                     }
-                    if (lane32 == 0) sts_u32(a_next + 4u * (uint32_t)warp, next_active ? 1u : 0u);
+                    if (lane32 == 0) sts_u32(a_mine + 12u, next_active ? 1u : 0u);
                     TK(8, 0);
-                    named_bar_sync(nthreads);
+                    named_bar_sync(32u * nbid);
                     TK(9, 0);
-                    const uint32_t nmask = __ballot_sync(0xffffffffu, lv && lds_u32(a_next + 4u * (uint32_t)lane32) != 0u);
-                    bids_done += (unsigned long long)__popc(mask);
-                    rounds_done += 1;
-                    const uint32_t pmask = mask;
+                    const uint32_t nmask = __ballot_sync(0xffffffffu, lv && lds_u32(a_lane + 12u) != 0u);
+                    bids_local += nbid;
                     mask = nmask;
-                    qlen = (uint32_t)__popc(mask);
-                    if (algo == ALGO_FORWARD) nits += 1;
-                    TK(10, qlen);
-                    bool finish = false;
-                    if (qlen == 0) finish = true;
-                    else if (algo == ALGO_FORWARD && nits >= max_it) { hit_limit = true; finish = true; }   // symmetric.rs:326-328
-                    else if (safety <= 1) { hit_limit = true; finish = true; }
-                    else {
-                        safety -= 1;
-                        if (rounds_done >= round_cap) finish = true;
-                    }
-                    if (finish) {
-                        // every bidder of the last round holds the same complete counters: the lowest one publishes them
-                        if (lane32 == 0 && (uint32_t)warp == (uint32_t)__ffs((int)pmask) - 1u) {
-                            s_fin.qlen = qlen; s_fin.nits = nits; s_fin.hit_limit = hit_limit ? 1u : 0u;
-                            s_fin.safety = safety; s_fin.rounds_done = rounds_done; s_fin.bids_done = bids_done;
-                        }
-                        // compact the surviving slots into the queue buffer for the write-back below
-                        if (next_active && lane32 == 0) (buf ? s_queue1 : s_queue0)[__popc(mask & ((1u << warp) - 1u))] = person;
-                        break;
-                    }
-                    if (!next_active) break;             // this slot is empty from now on: sleep until the engine is done
+                    left -= 1u;
+                    TK(10, nmask);
+                    if (nmask == 0u || left == 0u || !next_active) break;   // done / out of budget / this slot is empty from now on
                 }
+                if (mask == 0u || left == 0u) {
+                    // every bidder of the last round holds the same complete counters: one of them publishes the totals
+                    const uint32_t r = budget - left;                       // rounds this engine ran
+                    const bool hit = mask != 0u && left == 0u && budget_ends_solve;
+                    if (lane32 == 0 && s_fin_claim(&s_fin.claimed)) {
+                        s_fin.qlen = (uint32_t)__popc(mask);
+                        s_fin.nits = (algo == ALGO_FORWARD) ? nits + r : nits;
+                        s_fin.hit_limit = hit ? 1u : 0u;
+                        // the safety budget is charged for every round that neither emptied the queue nor hit a limit
+                        s_fin.safety = safety - (unsigned long long)(r - 1u) - ((mask != 0u && !hit) ? 1ull : 0ull);
+                        s_fin.rounds_done = rounds_done + r;
+                        s_fin.bids_done = bids_done + bids_local;
+                    }
+                    // compact the surviving slots into the queue buffer for the write-back below
+                    if (next_active && lane32 == 0) (buf ? s_queue1 : s_queue0)[__popc(mask & ((1u << warp) - 1u))] = person;
+                }
+                if (lane32 == 0) my_arcs += (unsigned long long)arcs_local;
             }
             __syncthreads();
             qlen = s_fin.qlen; nits = s_fin.nits; hit_limit = s_fin.hit_limit != 0u;
