@@ -64,3 +64,13 @@ for tag, cls in (("cfg2f", S.ForwardAuctionSolver), ("cfg2k", S.KhoslaSolver)):
         solver.set_option("smem_owners", 1 if sp == 3 else 0)
         st = solver.solve_resident(False, None)
         report(f"{tag} smem_prices={1 if sp else 0} smem_owners={1 if sp == 3 else 0}", solver, st)
+
+if "cfg3" in which:
+    n, m, k = 1_000_000, 4_000_000, 16
+    solver, z = S.KhoslaSolver.new(n, m, n * k)
+    G.kregular_device(solver, n, m, k, seed=1)
+    for tm in (1024, 256, 64, 24):
+        solver.set_option("tail_max", tm)
+        for _ in range(3):
+            st = solver.solve_resident(False, None)
+        report(f"cfg3 tail_max={tm} (solve {st['ms_solve']:.4f} ms, wide {st['wide_rounds']}, tail {st['tail_rounds']})", solver, st)

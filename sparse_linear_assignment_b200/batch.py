@@ -90,9 +90,15 @@ class BatchSolver:
         if self.row_off is None:
             raise _lib.SlaError(_lib.SLA_ERR_STATE, "BatchSolver.solve called before upload / generate_device")
         tr, tc = int(self.row_off[-1]), int(self.col_off[-1])
-        p2o = host_array(tr, np.uint32) if download else None
-        o2p = host_array(tc, np.uint32) if download else None
-        prices = host_array(tc, np.float64) if download else None
+        if download:
+            # page-locked result buffers are kept across solves of same-shaped batches (cudaMallocHost costs milliseconds);
+            # the returned arrays are therefore overwritten by the next solve(download=True) of this BatchSolver
+            if getattr(self, "_out_shape", None) != (tr, tc):
+                self._out = (host_array(tr, np.uint32), host_array(tc, np.uint32), host_array(tc, np.float64))
+                self._out_shape = (tr, tc)
+            p2o, o2p, prices = self._out
+        else:
+            p2o = o2p = prices = None
         per = (SlaStats * self.n_inst)() if per_instance else None
         total = SlaStats()
         mi = 0 if max_iterations is None else max(int(max_iterations), 1)
