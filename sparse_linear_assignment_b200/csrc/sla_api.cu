@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -36,6 +38,74 @@ struct GraphSlot {
 
 struct sla_batch_state;
 struct sla_part_state;
+
+// Persistent host workers of one context for the in-place negation of the caller's `values` (solver.rs:214-216):
+// chunk w of the array is negated by worker w as soon as the H2D copy of that chunk has completed (one event per chunk),
+// so the negation trails the upload by one chunk instead of starting after it.  Created lazily; the workers sleep on a
+// condition variable between jobs.
+struct NegPool {
+    static constexpr int kMax = 16;
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    uint64_t job_id = 0;
+    int pending = 0;
+    bool stop = false;
+    double* values = nullptr;
+    size_t chunk = 0, total = 0;
+    int nchunks = 0;
+    int device = 0;
+    cudaEvent_t ev[kMax] = {};
+
+    void worker(int w) {
+        cudaSetDevice(device);
+        uint64_t seen = 0;
+        while (true) {
+            double* v; size_t lo, hi; bool mine;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_job.wait(lk, [&] { return stop || job_id != seen; });
+                if (stop) return;
+                seen = job_id;
+                mine = w < nchunks;
+                v = values;
+                lo = (size_t)w * chunk;
+                hi = lo + chunk < total ? lo + chunk : total;
+            }
+            if (!mine) continue;
+            cudaEventSynchronize(ev[w]);               // the DMA engine has finished reading this chunk
+            for (size_t i = lo; i < hi; ++i) v[i] = -v[i];
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    bool start(int dev) {
+        if (!threads.empty()) return true;
+        device = dev;
+        for (int i = 0; i < kMax; ++i)
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) return false;
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = hw ? (int)hw : 4;
+        if (n > kMax) n = kMax;
+        for (int w = 0; w < n; ++w) threads.emplace_back([this, w] { worker(w); });
+        return true;
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    void shutdown() {
+        if (threads.empty()) return;
+        wait();
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv_job.notify_all();
+        for (auto& t : threads) t.join();
+        threads.clear();
+        for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    }
+};
 
 struct sla_ctx {
     int device = 0;
@@ -94,8 +164,7 @@ struct sla_ctx {
     int grid_wide = 0;
 
     std::vector<sla_round_profile> profile;
-    std::vector<std::thread> workers;      // host threads still negating the caller's `values` (sla_upload_csr_negating)
-    cudaEvent_t ev_vals_copied = nullptr;
+    NegPool neg;                           // host workers negating the caller's `values` (sla_upload_csr_negating)
 
     sla_batch_state* batch = nullptr;
     sla_part_state* part = nullptr;
@@ -103,11 +172,7 @@ struct sla_ctx {
 
 namespace {
 
-void join_workers(sla_ctx* c) {
-    for (auto& th : c->workers)
-        if (th.joinable()) th.join();
-    c->workers.clear();
-}
+void join_workers(sla_ctx* c) { c->neg.wait(); }
 
 struct WorkerJoinGuard {   // whatever path leaves a solve, the caller's host arrays are quiescent afterwards
     sla_ctx* c;
@@ -683,7 +748,6 @@ int sla_ctx_create(int device, size_t row_capacity, size_t col_capacity, size_t 
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaEventCreateWithFlags(&ctx->ev_vals_copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMallocHost((void**)&ctx->h_state, sizeof(DevState))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_csr_stats, sizeof(DevCsrStats))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMallocHost((void**)&ctx->h_scratch, 16 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -732,10 +796,9 @@ void sla_part_free(sla_ctx* ctx);
 
 void sla_ctx_destroy(sla_ctx* ctx) {
     if (!ctx) return;
-    join_workers(ctx);
     cudaSetDevice(ctx->device);
+    ctx->neg.shutdown();
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->ev_vals_copied) cudaEventDestroy(ctx->ev_vals_copied);
     sla_batch_free(ctx);
     sla_part_free(ctx);
     drop_graphs(ctx);
@@ -818,24 +881,28 @@ int sla_upload_csr_negating(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, 
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
-    CU(cudaMemcpyAsync(ctx->d_vals, values, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaEventRecord(ctx->ev_vals_copied, ctx->stream));
+    if (!ctx->neg.start(ctx->device)) return fail(ctx, SLA_ERR_CUDA, "could not start the host negation workers");
+    NegPool& np = ctx->neg;
+    if (threads < 1) threads = 1;
+    if (threads > (int)np.threads.size()) threads = (int)np.threads.size();
+    const size_t total = (size_t)nnz;
+    size_t per = (total + (size_t)threads - 1) / (size_t)threads;
+    per = (per + 511) & ~(size_t)511;                       // whole 4 KB pieces per worker
+    const int nchunks = (int)((total + per - 1) / per);
+    // `values` crosses PCIe first, chunk by chunk, each chunk followed by its event
+    for (int w = 0; w < nchunks; ++w) {
+        const size_t lo = (size_t)w * per, hi = lo + per < total ? lo + per : total;
+        CU(cudaMemcpyAsync(ctx->d_vals + lo, values + lo, (hi - lo) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaEventRecord(np.ev[w], ctx->stream));
+    }
     CU(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_cols, column_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (threads < 1) threads = 1;
-    if (threads > 32) threads = 32;
-    const size_t total = (size_t)nnz, per = (total + (size_t)threads - 1) / (size_t)threads;
-    cudaEvent_t ev = ctx->ev_vals_copied;
-    const int device = ctx->device;
-    for (int t = 0; t < threads; ++t) {
-        const size_t lo = (size_t)t * per, hi = lo + per < total ? lo + per : total;
-        if (lo >= hi) break;
-        ctx->workers.emplace_back([values, lo, hi, ev, device]() {
-            cudaSetDevice(device);
-            cudaEventSynchronize(ev);          // the DMA engine has finished reading `values`
-            for (size_t i = lo; i < hi; ++i) values[i] = -values[i];
-        });
+    {
+        std::lock_guard<std::mutex> lk(np.m);
+        np.values = values; np.chunk = per; np.total = total; np.nchunks = nchunks; np.pending = nchunks;
+        np.job_id += 1;
     }
+    np.cv_job.notify_all();
     rc = finish_csr(ctx, num_rows, num_cols, nnz);
     if (rc) join_workers(ctx);
     return rc;

@@ -35,6 +35,8 @@ def _imax(dtype) -> int:
 def host_threads() -> int:
     """Host threads one solver may use for the in-place negation: the cores of the box divided by the number of
     co-located ranks (torchrun exports LOCAL_WORLD_SIZE), at most 16."""
+    if os.environ.get("SLA_HOST_THREADS"):
+        return max(1, min(16, int(os.environ["SLA_HOST_THREADS"])))
     cores = os.cpu_count() or 1
     local_world = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1), 1)
     return max(1, min(16, cores // local_world))
