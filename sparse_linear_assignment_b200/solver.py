@@ -37,6 +37,8 @@ def host_threads() -> int:
     co-located ranks (torchrun exports LOCAL_WORLD_SIZE), at most 16."""
     if os.environ.get("SLA_HOST_THREADS"):
         return max(1, min(16, int(os.environ["SLA_HOST_THREADS"])))
+    if os.environ.get("SLA_HOST_THREADS"):
+        return max(1, min(16, int(os.environ["SLA_HOST_THREADS"])))
     cores = os.cpu_count() or 1
     local_world = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1), 1)
     return max(1, min(16, cores // local_world))
