@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
             // vote).  A Jacobi round is independent of the order of its bidders, so the results equal the compacting
             // formulation bit for bit.
             // =================================================================================================
-            constexpr int RPL = (LPR <= 8) ? 1 : 2;
+            constexpr int RPL = (LPR <= 8) ? 1 : ((LPR == 16) ? 2 : 4);
             const uint32_t* sq0 = buf ? s_queue1 : s_queue0;
             uint32_t mask = (qlen == 32u) ? 0xffffffffu : ((1u << qlen) - 1u);   // qlen <= kTailSlots <= 32
             bool active = (uint32_t)warp < qlen;
