@@ -94,10 +94,12 @@ int sla_host_alloc(size_t bytes, void **out);
 void sla_host_free(void *p);
 void sla_host_negate_f64(double *values, size_t n, int threads);
 
-/* Options: "tail_max" (bidders at or below which the tail engine runs, <= 1024), "graph" (1: CUDA-graph
- * super-rounds, 0: host-driven loop), "zero_price_skip" (1: skip the price gather while all prices are
- * exactly 0, i.e. the first round after init_solve), "profile" (1: record sla_round_profile entries),
- * "super_rounds" (rounds captured per graph). */
+/* Options: "tail_max" (bidders at or below which the single-CTA tail engine runs, <= 1024; the engine may lower it
+ * to make room for its shared-memory mirrors), "smem_prices" / "smem_owners" (1: let the tail engine mirror object
+ * prices / owners in shared memory when they fit), "graph" (1: CUDA-graph super-rounds, 0: host-driven loop),
+ * "zero_price_skip" (1: skip the price gather while all prices are exactly 0, i.e. the first round after
+ * init_solve), "regular" (1: use the uniform-degree bid kernel when every row has the same multiple-of-8 degree),
+ * "profile" (1: record sla_round_profile entries), "super_rounds" (rounds captured per graph), "timeout_s". */
 int sla_set_option(sla_ctx *ctx, const char *key, int64_t value);
 
 /* ---- CSR mirror: the host keeps ownership of i_starts_stops / column_indices / values built by
@@ -110,9 +112,10 @@ int sla_upload_csr(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uin
                    const uint32_t *column_indices, const double *values, uint64_t nnz);
 
 /* sla_upload_csr plus the in-place negation of the HOST `values` that AuctionSolver::init_solve performs
- * (solver.rs:214-216) when `maximize ^ (values[0] >= 0)`: `values` crosses PCIe first; once that copy has completed,
- * `threads` host threads negate the array while the column indices are still being uploaded and the solve runs.
- * They are joined before the next sla_*_solve / upload / destroy on this context returns.  The device keeps the
+ * (solver.rs:214-216) when `maximize ^ (values[0] >= 0)`: `values` crosses PCIe first, in `threads` chunks; a pool of
+ * host worker threads owned by the context negates chunk w as soon as the copy of chunk w has completed, while the
+ * rest is still being uploaded and the solve runs.  The work is complete before the next sla_*_solve / upload /
+ * destroy on this context returns.  The device keeps the
  * original values: the following solve still reports values_negated == 1, and the host must not negate again. */
 int sla_upload_csr_negating(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *row_ptr,
                             const uint32_t *column_indices, double *values, uint64_t nnz, int threads);

@@ -867,10 +867,10 @@ int sla_upload_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uin
 }
 
 // Same as sla_upload_csr, plus the in-place sign normalisation of AuctionSolver::init_solve (reference
-// src/solver.rs:214-216) on the HOST values: `values` is uploaded first; as soon as that copy has completed, worker
-// threads negate the host array while the column indices are still crossing PCIe and the solve runs.  The workers
-// are joined before the next solve / upload / destroy call on this context returns, so the caller observes the
-// negated values when solve() returns -- exactly the reference's post-condition.  The device holds the ORIGINAL values
+// src/solver.rs:214-216) on the HOST values: `values` is uploaded first, chunk by chunk; the context's worker pool
+// negates chunk w as soon as the copy of chunk w has completed, while the column indices are still crossing PCIe and
+// the solve runs.  The pool is drained before the next solve / upload / destroy call on this context returns, so the
+// caller observes the negated values when solve() returns -- exactly the reference's post-condition.  The device holds the ORIGINAL values
 // (the following solve reports values_negated == 1 as usual; the host must then not negate again).
 int sla_upload_csr_negating(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* row_ptr,
                             const uint32_t* column_indices, double* values, uint64_t nnz, int threads) {
