@@ -10,6 +10,10 @@
  * exercised on CPU (gloo) with this model standing in for the kernels.
  *
  * The arithmetic of one bid is the reference's: src/ksparse.rs:199-227 and src/symmetric.rs:361-378.
+ *
+ * Khosla on square instances: the device runs the rounds under an eps-schedule (c/2, x0.15, ..., the caller's eps) and
+ * falls back to the plain rounds from scratch as soon as a phase drops anybody at the price threshold; this model does
+ * the same (jm_set_khosla_scaling(0) gives the plain rounds throughout, like the library option "khosla_scaling" = 0).
  */
 #include <math.h>
 #include <stdint.h>
@@ -26,6 +30,10 @@ typedef struct {
     uint64_t rounds, bids, bid_arcs;
     uint32_t dropped, values_negated;
 } jm_stats;
+
+/* 1: Khosla rounds on square instances run under an eps-schedule (set by the tests / the bindings) */
+int jm_khosla_scaling = 1;
+void jm_set_khosla_scaling(int on) { jm_khosla_scaling = on; }
 
 static uint32_t person_bits(uint32_t num_rows) {
     uint32_t m = num_rows > 1 ? num_rows - 1 : 1;
@@ -183,13 +191,38 @@ int jm_solve(int algo, uint32_t n_rows, uint32_t n_cols, const uint32_t *row_ptr
 
     if (algo == JM_KHOSLA) {
         double m = (double)n_cols;
-        double eps = isnan(eps_in) ? 1.0 / m : eps_in;
-        st->eps = eps;
-        double threshold = (m / 2.0) * (w_max - w_min + eps);
-        while (qlen > 0) {
-            qlen = jacobi_round(algo, row_ptr, cols, vals, sign, eps, threshold, pbits, prices, p2o, o2p, best, qa,
-                                qlen, qb, slot_obj, slot_bid, st);
-            uint32_t *t = qa; qa = qb; qb = t;
+        double target = isnan(eps_in) ? 1.0 / m : eps_in;
+        st->eps = target;
+        double threshold = (m / 2.0) * (w_max - w_min + target);
+        /* eps-schedule of the device's Khosla rounds on square instances (DESIGN.md "Khosla under an eps-schedule"):
+         * phases at c/2, x0.15, ... each restarting from the kept prices, the last one at exactly the caller's eps */
+        double eps = target;
+        int scaled = jm_khosla_scaling && n_rows == n_cols && c / 2.0 > target;
+        if (scaled) eps = c / 2.0;
+        for (;;) {
+            while (qlen > 0) {
+                qlen = jacobi_round(algo, row_ptr, cols, vals, sign, eps, threshold, pbits, prices, p2o, o2p, best, qa,
+                                    qlen, qb, slot_obj, slot_bid, st);
+                uint32_t *t = qa; qa = qb; qb = t;
+            }
+            if (!scaled) break;
+            if (st->dropped != 0) {
+                /* somebody hit the price threshold under the schedule: start over with the plain rounds, which alone
+                 * define what the threshold does on an instance without a perfect matching */
+                scaled = 0;
+                eps = target;
+                st->dropped = 0;
+                for (uint32_t j = 0; j < n_cols; ++j) prices[j] = 0.0;
+            } else if (eps > target) {
+                eps *= 0.15;
+                if (eps < target) eps = target;
+                st->nreductions += 1;
+            } else {
+                break;
+            }
+            for (uint32_t i = 0; i < n_rows; ++i) { p2o[i] = JM_NONE; qa[i] = i; }
+            for (uint32_t j = 0; j < n_cols; ++j) o2p[j] = JM_NONE;
+            qlen = n_rows;
         }
         st->nits = (uint32_t)st->bids;
         st->num_unassigned = st->dropped;

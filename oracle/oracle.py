@@ -103,6 +103,8 @@ def _declare(l: C.CDLL) -> None:
     l.orc_chacha8_u64_stream.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.c_size_t]
     l.jm_pack_bid.restype = C.c_uint64
     l.jm_pack_bid.argtypes = [C.c_double, C.c_uint32, C.c_uint32]
+    l.jm_set_khosla_scaling.argtypes = [C.c_int]
+    l.jm_set_khosla_scaling.restype = None
     l.jm_solve.argtypes = [C.c_int, C.c_uint32, C.c_uint32, _u32p, _u32p, _f64p, C.c_int, C.c_double, C.c_double,
                            C.c_uint32, _u32p, _u32p, _f64p, C.POINTER(JmStats)]
 
@@ -253,8 +255,10 @@ def chacha8_u64_stream(seed, n):
 
 
 def jacobi_model(algo, num_rows, num_cols, row_ptr, cols, vals, maximize=False, eps=None, start_eps=None,
-                 max_iterations=None):
-    """CPU model of the device algorithm.  Returns dict(p2o, o2p, prices, stats)."""
+                 max_iterations=None, khosla_scaling=True):
+    """CPU model of the device algorithm.  Returns dict(p2o, o2p, prices, stats).  khosla_scaling mirrors the library
+    option of the same name (Khosla rounds under an eps-schedule on square instances)."""
+    lib().jm_set_khosla_scaling(int(bool(khosla_scaling)))
     r, c, v = _u32(row_ptr), _u32(cols), _f64(vals)
     p2o = np.zeros(num_rows, dtype=np.uint32)
     o2p = np.zeros(num_cols, dtype=np.uint32)

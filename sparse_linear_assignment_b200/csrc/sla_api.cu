@@ -32,6 +32,7 @@ struct GraphSlot {
     bool tail_only = false;
     uint32_t tail_smem_bytes = 0;
     uint32_t tail_max = 0;
+    bool khosla_phases = false;
 };
 
 }  // namespace
@@ -148,7 +149,7 @@ struct sla_ctx {
     uint32_t regular_k = 0;   // all rows have this many arcs (multiple of 8): the regular bid kernel is used
     int lpr8 = 1;
     int opt_regular = 1;
-    int opt_smem_prices = 1, opt_smem_owners = 1;
+    int opt_smem_prices = 1, opt_smem_owners = 1, opt_khosla_scaling = 1;
     // tail-engine plan of the current instance (plan_tail): what is mirrored in shared memory and how many bidders fit
     bool tail_smem_prices = false;   // object prices mirrored
     uint32_t tail_own_mode = 0;      // owners mirrored: 0 no, 1 u32, 2 u16
@@ -320,6 +321,10 @@ void launch_one(sla_ctx* c, const Params& p, int which, bool zero_first = false)
 
 // tail_only: the instance has at most tail_max persons, so the queue can never be long enough for the wide pair --
 // leave those two (no-op) launches out of the super-round.
+// Khosla rounds run under an eps-schedule on square instances (finish_if_possible): the phase kernel is then part of
+// the Khosla super-round as well.
+bool khosla_phases(const sla_ctx* c) { return c->opt_khosla_scaling && c->n_rows == c->n_cols; }
+
 void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_first, bool tail_only) {
     if (!tail_only) {
         launch_one(c, p, 0, zero_first);
@@ -331,16 +336,20 @@ void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_fir
     if (forward) {
         launch_one(c, p, 3);
         launch_one(c, p, 4);
+    } else if (khosla_phases(c)) {
+        launch_one(c, p, 4);
     }
 }
 
-int kernels_per_super_round(bool forward, bool tail_only) { return (forward ? 5 : 3) - (tail_only ? 2 : 0); }
+int kernels_per_super_round(const sla_ctx* c, bool forward, bool tail_only) {
+    return (forward ? 5 : (khosla_phases(c) ? 4 : 3)) - (tail_only ? 2 : 0);
+}
 
 bool is_tail_only(const sla_ctx* c) { return c->n_rows <= c->tail_max_eff; }
 
 // Khosla on a tail-only instance finishes inside the first tail launch: further super-rounds would be pure no-ops.
 int super_rounds_for(const sla_ctx* c, bool forward) {
-    return (!forward && is_tail_only(c)) ? 1 : c->opt_super_rounds;
+    return (!forward && is_tail_only(c) && !khosla_phases(c)) ? 1 : c->opt_super_rounds;
 }
 
 int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out) {
@@ -350,7 +359,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     const int n_super = super_rounds_for(ctx, forward);
     if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == n_super &&
         g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices && g.tail_only == tail_only &&
-        g.tail_smem_bytes == ctx->tail_smem_bytes && g.tail_max == ctx->tail_max_eff) {
+        g.tail_smem_bytes == ctx->tail_smem_bytes && g.tail_max == ctx->tail_max_eff && g.khosla_phases == khosla_phases(ctx)) {
         *out = g.exec;
         return SLA_OK;
     }
@@ -375,6 +384,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     g.smem_prices = ctx->tail_smem_prices;
     g.tail_smem_bytes = ctx->tail_smem_bytes;
     g.tail_max = ctx->tail_max_eff;
+    g.khosla_phases = khosla_phases(ctx);
     *out = g.exec;
     return SLA_OK;
 }
@@ -487,6 +497,11 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
         s.eps = std::isnan(eps_in) ? 1.0 / m : eps_in;
         s.threshold = (m / 2.0) * (w_max - w_min + s.eps);
         s.max_iterations = 0xFFFFFFFFu;
+        s.target_eps = s.eps;
+        // square instance: the rounds start at c/2 and come down to the caller's eps by factors of 0.15 (same factor
+        // and start as the Forward solver, symmetric.rs:189, 270); see finish_if_possible
+        const double c = std::fmax(std::fabs(w_min), std::fabs(w_max));
+        if (khosla_phases(ctx) && c / 2.0 > s.eps) { s.kscale = 1u; s.eps = c / 2.0; }
     } else {
         // reference src/symmetric.rs:229-273
         const double target = std::isnan(eps_in) ? 1.0 / (double)N : eps_in;
@@ -543,7 +558,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
             first = false;
             CU(cudaGraphLaunch(exec, ctx->stream));
             graph_launches += 1;
-            launches += (uint32_t)(super_rounds_for(ctx, forward) * kernels_per_super_round(forward, is_tail_only(ctx)));
+            launches += (uint32_t)(super_rounds_for(ctx, forward) * kernels_per_super_round(ctx, forward, is_tail_only(ctx)));
             if (late_init && graph_launches == 1) launches += 1;   // init_solve_late_kernel sits in the first graph
             if ((rc = poll_state(ctx))) return rc;
             done = ctx->h_state->done != 0;
@@ -609,6 +624,9 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
                 launch_one(ctx, p, 3);
                 launch_one(ctx, p, 4);
                 launches += 2;
+            } else if (khosla_phases(ctx)) {
+                launch_one(ctx, p, 4);
+                launches += 1;
             }
             int rc = poll_state(ctx);
             if (rc) return rc;
@@ -838,6 +856,8 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "smem_owners") {
         ctx->opt_smem_owners = value ? 1 : 0;
         plan_tail(ctx);
+    } else if (k == "khosla_scaling") {
+        ctx->opt_khosla_scaling = value ? 1 : 0;
     } else if (k == "regular") {
         ctx->opt_regular = value ? 1 : 0;
     } else if (k == "timeout_s") {

@@ -39,6 +39,7 @@ struct BatchParams {
     DevInstStats* stats;                    // n_inst
     uint32_t n_inst, max_rows, max_cols;
     uint32_t algo, maximize, max_iterations;
+    uint32_t khosla_scaling;                // Khosla rounds under an eps-schedule on square instances (finish_if_possible)
     double eps_in, start_eps_in;            // NaN = None
 };
 
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(kBatchThreads, SLA_BATCH_MINBLOCKS) batch_kern
             const double m = (double)M;                                            // ksparse.rs:160-181
             eps = isnan(p.eps_in) ? 1.0 / m : p.eps_in;
             threshold = (m / 2.0) * (w_max - w_min + eps);
+            target = eps;
         } else {
             target = isnan(p.eps_in) ? 1.0 / (double)N : p.eps_in;                 // symmetric.rs:229-273
             const double c = fmax(fabs(w_min), fabs(w_max));
@@ -130,6 +132,13 @@ __global__ void __launch_bounds__(kBatchThreads, SLA_BATCH_MINBLOCKS) batch_kern
             else eps = !isnan(p.start_eps_in) ? p.start_eps_in : c / 2.0;
         }
 
+        // Khosla on a square instance: rounds under the eps-schedule c/2, x0.15, ..., caller's eps; a phase that drops
+        // anybody makes the instance start over with the plain rounds (same rule as finish_if_possible)
+        bool kscale = false;
+        if (algo == ALGO_KHOSLA && p.khosla_scaling && N == M) {
+            const double c = fmax(fabs(w_min), fabs(w_max));
+            if (c / 2.0 > eps) { kscale = true; eps = c / 2.0; }
+        }
         uint32_t qlen = N, nits = 0, nreductions = 0, optimal = 0;
         unsigned long long rounds = 0, bids = 0, my_arcs = 0;
         uint32_t my_dropped = 0;
@@ -280,7 +289,31 @@ __global__ void __launch_bounds__(kBatchThreads, SLA_BATCH_MINBLOCKS) batch_kern
             { uint32_t* t = sq; sq = nq; nq = t; }
             zero = false;
             if (algo == ALGO_KHOSLA) {
-                if (qlen == 0) break;
+                if (qlen != 0) continue;
+                if (!kscale) break;
+                // end of a phase of the eps-schedule: did anybody hit the price threshold?
+                if (tid == 0) s_flag = 0;
+                __syncthreads();
+                if (my_dropped) s_flag = 1;
+                __syncthreads();
+                const bool any_dropped = s_flag != 0;
+                __syncthreads();
+                if (any_dropped) {
+                    kscale = false;
+                    eps = target;
+                    my_dropped = 0;
+                    for (uint32_t j = tid; j < M; j += kBatchThreads) s_prices[j] = 0.0;
+                } else if (eps > target) {
+                    eps *= 0.15;
+                    if (eps < target) eps = target;
+                    nreductions += 1;
+                } else {
+                    break;
+                }
+                for (uint32_t i = tid; i < N; i += kBatchThreads) { s_p2o[i] = SLA_DEV_NONE; sq[i] = i; }
+                for (uint32_t j = tid; j < M; j += kBatchThreads) s_o2p[j] = SLA_DEV_NONE;
+                qlen = N;
+                __syncthreads();
                 continue;
             }
             // ---- Forward: eps-scaling control (symmetric.rs:275-329) ----
@@ -540,6 +573,7 @@ int sla_batch_solve(sla_ctx* ctx, int algo, int maximize, double eps, double sta
     bp.algo = (algo == SLA_ALGO_FORWARD) ? sla::ALGO_FORWARD : sla::ALGO_KHOSLA;
     bp.maximize = maximize ? 1u : 0u;
     bp.max_iterations = max_iterations;
+    bp.khosla_scaling = ctx->opt_khosla_scaling ? 1u : 0u;
     bp.eps_in = eps; bp.start_eps_in = start_eps;
     const size_t smem = batch_smem_bytes(b->max_rows, b->max_cols);
     int occ = 1;

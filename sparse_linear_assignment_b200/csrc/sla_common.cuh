@@ -21,7 +21,7 @@ constexpr int kTailThreads = SLA_TAIL_THREADS;   // block size of the tail engin
 constexpr uint32_t kTailSlots = kTailThreads / 32;   // bidders of a "small" round: one warp per slot
 
 enum : uint32_t { ALGO_KHOSLA = 0, ALGO_FORWARD = 1 };
-enum : uint32_t { ACTION_NONE = 0, ACTION_RESET = 1 };
+enum : uint32_t { ACTION_NONE = 0, ACTION_RESET = 1, ACTION_RESET_ALL = 2 };   // RESET: wipe the assignment; RESET_ALL: and the prices
 
 // Device-resident control block of one solve.  Only single threads write it (see the kernels).
 // The first 112 bytes are the fields every kernel needs at start-up; HotState mirrors them so that a kernel can
@@ -59,6 +59,8 @@ struct DevState {
     uint32_t dropped;
     uint32_t max_iterations;
     uint32_t tail_round_cap; // rounds one tail launch may run before handing control back to the host
+    uint32_t kscale;         // Khosla rounds currently run under the eps-schedule (square instances)
+    uint32_t cold_pad[3];
     unsigned long long rounds, bids, bid_arcs, wide_rounds, tail_rounds;
     unsigned long long safety_rounds_left;
     unsigned long long dbg[24];  // cycle counters of the tail engine when built with -DSLA_TAIL_TIMING

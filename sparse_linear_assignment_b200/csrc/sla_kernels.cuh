@@ -240,11 +240,31 @@ __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params 
 // =============================================================================================================
 // Control helpers (executed by exactly one thread)
 // =============================================================================================================
-// Queue ran empty: Khosla is finished (ksparse.rs:186 loop exit); Forward is finished without an eps-CS check
-// when start_from_optimal_eps holds (symmetric.rs:279-288).  Otherwise the ecs kernel decides.
+// Queue ran empty.  Forward is finished without an eps-CS check when start_from_optimal_eps holds
+// (symmetric.rs:279-288); otherwise the ecs kernel decides.  Khosla is finished (ksparse.rs:186 loop exit) unless
+// its rounds run under the eps-schedule (square instances): then a phase in which nobody was dropped is followed by
+// the next, smaller eps (the assignment is wiped, the prices are kept, the last phase runs at exactly the caller's
+// eps), and a phase that dropped anybody -- the instance is not known to have a perfect matching, and only the plain
+// rounds define what the reference's price threshold does then -- makes the solve start over without a schedule.
 __device__ __forceinline__ void finish_if_possible(DevState* st) {
     if (st->algo == ALGO_KHOSLA) {
-        st->done = 1;
+        if (!st->kscale) { st->done = 1; return; }
+        if (st->dropped != 0) {
+            st->kscale = 0;
+            st->eps = st->target_eps;
+            st->dropped = 0;
+            st->action = ACTION_RESET_ALL;
+        } else if (st->eps > st->target_eps) {
+            double e = st->eps * 0.15;
+            st->eps = (e < st->target_eps) ? st->target_eps : e;
+            st->nreductions += 1;
+            st->action = ACTION_RESET;
+        } else {
+            st->done = 1;
+            return;
+        }
+        st->qlen[st->cur] = st->n_rows;
+        st->identity = 1;
     } else if (st->start_opt) {
         st->optimal = 1;
         st->done = 1;
@@ -772,14 +792,19 @@ __global__ void __launch_bounds__(kWideThreads) ecs_kernel(const Params p) {
     }
 }
 
-// Forward phase restart: wipe both assignment vectors, keep prices (reference src/symmetric.rs:299-321).
+// Phase restart: wipe both assignment vectors, keep prices (reference src/symmetric.rs:299-321; also the phases of
+// the Khosla eps-schedule).  ACTION_RESET_ALL zeroes the prices as well (Khosla starting over without a schedule).
 __global__ void __launch_bounds__(kWideThreads) phase_apply_kernel(const Params p) {
     const HotState h = load_hot(p.st);
-    if (h.action != ACTION_RESET) return;
+    if (h.action != ACTION_RESET && h.action != ACTION_RESET_ALL) return;
+    const bool all = h.action == ACTION_RESET_ALL;
     const uint32_t n_rows = h.n_rows, n_cols = h.n_cols;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     for (uint32_t i = tid; i < n_rows; i += stride) p.p2o[i] = SLA_DEV_NONE;
-    for (uint32_t j = tid; j < n_cols; j += stride) p.o2p[j] = SLA_DEV_NONE;
+    for (uint32_t j = tid; j < n_cols; j += stride) {
+        p.o2p[j] = SLA_DEV_NONE;
+        if (all) p.prices[j] = 0.0;
+    }
 }
 
 // =============================================================================================================

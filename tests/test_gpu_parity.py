@@ -341,6 +341,65 @@ def test_cfg3_khosla_1Mx4M_k16(sla, oracle):
     assert dev.device_objective() == o.get_objective()
 
 
+def _symmetric_instance(n, mean_degree, seed, planted, lo, hi):
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(n)
+    rows = []
+    for i in range(n):
+        cc = rng.choice(n, size=max(int(rng.binomial(n, mean_degree / n)), 1), replace=False)
+        rows.append(np.unique(np.append(cc, perm[i]) if planted else cc))
+    rp = np.zeros(n + 1, dtype=np.uint32)
+    rp[1:] = np.cumsum([len(r) for r in rows])
+    c = np.concatenate(rows).astype(np.uint32)
+    return rp, c, rng.uniform(lo, hi, size=c.size)
+
+
+def test_khosla_eps_schedule_on_square_instances(sla, oracle):
+    """Khosla rounds on square instances run under an eps-schedule that ends at the caller's eps: same
+    eps-CS guarantee as the reference's fixed-eps loop, an order of magnitude fewer rounds.  A phase that drops anybody
+    at the price threshold makes the solve start over with the plain rounds, so instances without a perfect matching
+    behave exactly as before.  Both paths equal the CPU model bit for bit; objectives are judged against the oracle."""
+    n = 1200
+    rp, c, v = _symmetric_instance(n, 12, 3, True, 500.0, 1000.0)           # the reference's symmetric bench shape
+    o = oracle.OracleSolver("khosla", n, n, len(c))
+    o.load_csr(n, n, rp, c, v)
+    o.solve()
+    solver, z = gpu_solve(sla, "KhoslaSolver", n, n, rp, c, v)
+    assert z.num_unassigned == o.num_unassigned == 0 and z.eps == o.eps
+    assert abs(solver.get_objective(z) - o.get_objective()) <= n * z.eps    # n * eps_final (non-integer weights)
+    assert solver.last_stats["nreductions"] >= 5
+    assert_equals_model(oracle, "khosla", solver, z, n, n, rp, c, v)
+    scaled_rounds = solver.last_stats["rounds"]
+    plain, zp = gpu_solve(sla, "KhoslaSolver", n, n, rp, c, v, options=dict(khosla_scaling=0))
+    assert zp.num_unassigned == 0 and plain.last_stats["nreductions"] == 0
+    assert abs(plain.get_objective(zp) - o.get_objective()) <= n * zp.eps
+    assert_equals_model(oracle, "khosla", plain, zp, n, n, rp, c, v, khosla_scaling=False)
+    assert scaled_rounds * 3 < plain.last_stats["rounds"]
+    # integer weights, eps < 1/n: bit-exact objective either way
+    vi = np.floor(v)
+    o.load_csr(n, n, rp, c, vi)
+    o.solve(eps=1.0 / (n + 1))
+    solver, z = gpu_solve(sla, "KhoslaSolver", n, n, rp, c, vi, eps=1.0 / (n + 1))
+    assert z.num_unassigned == 0 and solver.get_objective(z) == o.get_objective()
+    assert_equals_model(oracle, "khosla", solver, z, n, n, rp, c, vi, eps=1.0 / (n + 1))
+    # no perfect matching: the schedule is abandoned, results equal the plain rounds' and the oracle's num_unassigned
+    infeasible = 0
+    for nn, seed in ((9, 5), (60, 6), (150, 7), (40, 8)):
+        rp, c, v = _symmetric_instance(nn, 3, seed, False, 0.0, 10.0)
+        o = oracle.OracleSolver("khosla", nn, nn, len(c))
+        o.load_csr(nn, nn, rp, c, v)
+        o.solve()
+        solver, z = gpu_solve(sla, "KhoslaSolver", nn, nn, rp, c, v)
+        assert z.num_unassigned == o.num_unassigned
+        check_matching(nn, nn, rp, c, z.person_to_object, z.object_to_person, o.num_unassigned)
+        r = assert_equals_model(oracle, "khosla", solver, z, nn, nn, rp, c, v)
+        if o.num_unassigned:
+            infeasible += 1
+            plain = oracle.jacobi_model("khosla", nn, nn, rp, c, v, khosla_scaling=False)
+            assert np.array_equal(r["p2o"], plain["p2o"]) and np.array_equal(r["prices"], plain["prices"])
+    assert infeasible >= 2
+
+
 # ---- edge cases of the reference's input space ------------------------------------------------------------------------
 @pytest.mark.parametrize("kind,cls_name", SOLVERS)
 def test_edge_cases_match_model_and_oracle(sla, oracle, kind, cls_name):
