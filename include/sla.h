@@ -99,6 +99,8 @@ void sla_host_negate_f64(double *values, size_t n, int threads);
  * prices / owners in shared memory when they fit), "graph" (1: CUDA-graph super-rounds, 0: host-driven loop),
  * "zero_price_skip" (1: skip the price gather while all prices are exactly 0, i.e. the first round after
  * init_solve), "regular" (1: use the uniform-degree bid kernel when every row has the same multiple-of-8 degree),
+ * "khosla_scaling" (1: Khosla rounds on square instances run under an eps-schedule that ends at the caller's eps
+ * and fall back to the plain rounds when a phase drops anybody; 0: plain fixed-eps rounds),
  * "profile" (1: record sla_round_profile entries), "super_rounds" (rounds captured per graph), "timeout_s". */
 int sla_set_option(sla_ctx *ctx, const char *key, int64_t value);
 

@@ -162,3 +162,60 @@ def test_jacobi_model_agrees_with_oracle(oracle, algo):
         r = oracle.jacobi_model(algo, n, m, rp, c, v)
         assert objective_of(rp, c, v, r["p2o"]) == case["objective"]
         assert r["stats"]["num_unassigned"] == 0
+
+
+def test_model_khosla_eps_schedule_keeps_parity_with_the_oracle():
+    """The device's Khosla rounds on square instances run under an eps-schedule (oracle/jacobi_model.c
+    is the CPU model of exactly that).  Against the restated reference (sla_oracle.c): same num_unassigned, objective
+    within n * eps (identical for integer weights with eps < 1/n); an instance without a perfect matching falls back to
+    the plain rounds and returns what they return."""
+    from oracle import oracle as O
+
+    def instance(n, mean_degree, seed, planted, lo, hi, integer=False):
+        rng = np.random.default_rng(seed)
+        perm = rng.permutation(n)
+        rows = []
+        for i in range(n):
+            cc = rng.choice(n, size=max(int(rng.binomial(n, mean_degree / n)), 1), replace=False)
+            rows.append(np.unique(np.append(cc, perm[i]) if planted else cc))
+        rp = np.zeros(n + 1, dtype=np.uint32)
+        rp[1:] = np.cumsum([len(r) for r in rows])
+        c = np.concatenate(rows).astype(np.uint32)
+        v = rng.uniform(lo, hi, size=c.size)
+        return rp, c, (np.floor(v) if integer else v)
+
+    def objective(rp, c, v, p2o):
+        total = 0.0
+        for i, j in enumerate(p2o):
+            if j != 0xFFFFFFFF:
+                a, b = int(rp[i]), int(rp[i + 1])
+                total += v[a + int(np.nonzero(c[a:b] == j)[0][0])]
+        return total
+
+    for n, seed, integer in ((200, 1, False), (200, 2, True), (600, 3, False)):
+        rp, c, v = instance(n, 10, seed, True, 500.0, 1000.0, integer)
+        eps = 1.0 / (n + 1) if integer else None
+        o = O.OracleSolver("khosla", n, n, len(c))
+        o.load_csr(n, n, rp, c, v)
+        o.solve(eps=eps)
+        scaled = O.jacobi_model("khosla", n, n, rp, c, v, eps=eps)
+        plain = O.jacobi_model("khosla", n, n, rp, c, v, eps=eps, khosla_scaling=False)
+        assert scaled["stats"]["num_unassigned"] == plain["stats"]["num_unassigned"] == o.num_unassigned == 0
+        assert scaled["stats"]["nreductions"] >= 4 and scaled["stats"]["eps"] == o.eps
+        if n >= 600:
+            assert scaled["stats"]["rounds"] * 2 < plain["stats"]["rounds"]      # what the schedule is for
+        got = objective(rp, c, v, scaled["p2o"])
+        assert got == o.get_objective() if integer else abs(got - o.get_objective()) <= n * o.eps
+    fallbacks = 0
+    for n, seed in ((9, 5), (60, 6), (40, 8), (150, 7)):
+        rp, c, v = instance(n, 3, seed, False, 0.0, 10.0)
+        o = O.OracleSolver("khosla", n, n, len(c))
+        o.load_csr(n, n, rp, c, v)
+        o.solve()
+        scaled = O.jacobi_model("khosla", n, n, rp, c, v)
+        assert scaled["stats"]["num_unassigned"] == o.num_unassigned
+        if o.num_unassigned:
+            fallbacks += 1
+            plain = O.jacobi_model("khosla", n, n, rp, c, v, khosla_scaling=False)
+            assert np.array_equal(scaled["p2o"], plain["p2o"]) and np.array_equal(scaled["prices"], plain["prices"])
+    assert fallbacks >= 2
