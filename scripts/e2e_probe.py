@@ -8,7 +8,7 @@ sys.path.insert(0, ".")
 import sparse_linear_assignment_b200 as S
 from sparse_linear_assignment_b200 import generators as G, solver as SV
 
-n, m, k = 1_000_000, 4_000_000, 16
+n, m, k = (1_000, 10_000, 32) if (len(sys.argv) > 1 and sys.argv[1] == "cfg1") else (1_000_000, 4_000_000, 16)
 rp, c, v = G.kregular_host(n, m, k, seed=1)
 solver, z = S.KhoslaSolver.new(n, m, n * k)
 solver.load_csr(n, m, rp, c, v)
@@ -46,7 +46,7 @@ class LibProxy:
 
 
 SV._lib.load = lambda: LibProxy()
-reps = 8
+reps = 200 if n < 10_000 else 8
 tot = 0.0
 for it in range(reps + 2):
     if hv[0] < 0:
