@@ -20,7 +20,7 @@ import sparse_linear_assignment_b200 as S
 from sparse_linear_assignment_b200 import generators as G
 
 SEG = ["lane scan (price + keys)", "REDUX agreement", "owner", "prefetch issue + bid", "STS", "barrier 1", "resolve (LDS + any)",
-       "stores + row move", "atomicOr", "barrier 2", "mask read + loop"]
+       "stores + row move", "still-active flag", "barrier 2", "flag vote + loop"]
 
 
 def report(name, solver, st):

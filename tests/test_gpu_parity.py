@@ -462,3 +462,29 @@ def test_randomized_sweep_matches_model(sla, oracle):
         solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v, maximize=maximize, eps=eps)
         assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v, maximize=maximize, eps=eps)
         check_matching(n, m, rp, c, z.person_to_object, z.object_to_person, z.num_unassigned)
+
+
+def test_randomized_square_sweep_matches_model(sla, oracle):
+    """Square instances of every size class of the engines (<= 24 rows: slot-stable rounds from the start; <= 1024:
+    single-CTA engine only; larger: wide rounds first), rows from 1 to 200 arcs (register rows of 32 / 64 / 128 arcs
+    and the streaming fallback), planted (perfect matching: Khosla rounds under the eps-schedule) and unplanted
+    (possibly none: the schedule is abandoned) -- both solvers against the CPU model, bit for bit."""
+    rng = np.random.default_rng(77)
+    for trial in range(48):
+        kind, cls_name = SOLVERS[trial % 2]
+        n = int((rng.integers(1, 25), rng.integers(25, 1025), rng.integers(1025, 3000))[trial % 3])
+        kmax = int(min(n, (4, 20, 70, 140, 200)[trial % 5]))
+        integer = bool(trial % 4)
+        if trial % 6 == 5 and n <= 1024:
+            nn = min(n, 60)                                      # unplanted and sparse: often without a perfect matching
+            rp, c, v = _symmetric_instance(nn, 3, 100 + trial, False, 0.0, 10.0)
+            n = nn
+            if kind == "forward":
+                continue                                         # the Forward solver runs to max_iterations there
+        else:
+            rp, c, v = ragged_instance(rng, n, n, 1 if n == 1 else min(2, kmax), max(kmax, min(2, n)), integer=integer)
+        maximize = bool(trial % 3 == 0)
+        eps = None if trial % 2 else float(rng.uniform(1e-4, 0.5))
+        solver, z = gpu_solve(sla, cls_name, n, n, rp, c, v, maximize=maximize, eps=eps)
+        assert_equals_model(oracle, kind, solver, z, n, n, rp, c, v, maximize=maximize, eps=eps)
+        check_matching(n, n, rp, c, z.person_to_object, z.object_to_person, z.num_unassigned)
