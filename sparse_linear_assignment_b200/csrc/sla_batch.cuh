@@ -215,14 +215,33 @@ __global__ void __launch_bounds__(kBatchThreads, SLA_BATCH_MINBLOCKS) batch_kern
                     const unsigned long long w = bidding ? s_word[q] : 0ull;
                     const double bid = bidding ? s_bid[q] : 0.0;
                     const uint32_t prev = bidding ? s_prev[q] : SLA_DEV_NONE;
-                    const uint32_t peers = __match_any_sync(0xffffffffu, bidding ? j : (0xFFFFFF00u + (uint32_t)lane32));
+// Conflict detection among the <= 32 bidders of a small round.  MATCH.ANY walks the distinct keys one by one, so the idle
+// lanes share one key (variant 1: cfg4 42.5 -> 40.5 ms against unique keys per idle lane, variant 0; an all-pairs
+// shuffle loop, variant 2, is no faster).
+#ifndef SLA_BATCH_RESOLVE
+#define SLA_BATCH_RESOLVE 1
+#endif
                     bool won = bidding && (w != 0ull);
+#if SLA_BATCH_RESOLVE == 2
+                    // all-pairs comparison over the (few) bidders of the round: two shuffles per bidder, all independent
+                    for (uint32_t r = 0; r < qlen; ++r) {
+                        const uint32_t oj = __shfl_sync(0xffffffffu, j, (int)r);
+                        const unsigned long long ow = __shfl_sync(0xffffffffu, w, (int)r);
+                        won = won && !(oj == j && ow > w);
+                    }
+#else
+#if SLA_BATCH_RESOLVE == 1
+                    const uint32_t peers = __match_any_sync(0xffffffffu, j);   // idle lanes share the key SLA_DEV_NONE
+#else
+                    const uint32_t peers = __match_any_sync(0xffffffffu, bidding ? j : (0xFFFFFF00u + (uint32_t)lane32));
+#endif
                     if (__any_sync(0xffffffffu, bidding && (peers & (peers - 1u)) != 0u)) {
                         for (uint32_t r = 0; r < qlen; ++r) {
                             const unsigned long long ow = __shfl_sync(0xffffffffu, w, (int)r);
                             won = won && !(((peers >> r) & 1u) && ow > w);
                         }
                     }
+#endif
                     uint32_t emit = SLA_DEV_NONE;
                     if (bidding) {
                         if (won) {
