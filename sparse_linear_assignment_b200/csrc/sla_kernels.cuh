@@ -457,6 +457,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                 bool next_active = false;
                 while (true) {
                     const uint32_t nbid = (uint32_t)__popc(mask);
+                    // Solo chain: this warp is the only bidder left, and the set of bidders never grows, so every
+                    // remaining round of this launch has exactly one bid (two thirds of all rounds of the eps-scaled
+                    // solvers are like that: an eviction chain running to its end).  Nothing to exchange, nobody to
+                    // wait for: no packed word, no exchange record, no barriers, no vote.
+                    const bool solo = nbid == 1u;
 #ifdef SLA_TAIL_TIMING
                     if (tk1 == 0) tk1 = clock64();
                     act_rounds += 1;
@@ -496,21 +501,27 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                     } else {
                         obj = r.obj;
                         bid = r.bid;
-                        word = (r.bid == r.bid) ? pack_bid(r.bid, person, pbits) : 0ull;   // NaN never bids
+                        if (solo) word = (r.bid == r.bid) ? 1ull : 0ull;                   // a lone bid wins unless it is NaN
+                        else word = (r.bid == r.bid) ? pack_bid(r.bid, person, pbits) : 0ull;   // NaN never bids
                     }
                     TK(3, (uint32_t)word);
-                    if (lane32 == 0) { sts_u64(a_mine, word); sts_u32(a_mine + 8u, obj); }
-                    TK(4, 0);
-                    named_bar_sync(32u * nbid);
-                    TK(5, 0);
-                    // ---- resolve + assign ----
                     const bool lv = ((mask >> lane32) & 1u) != 0u;
+                    if (!solo) {
+                        if (lane32 == 0) { sts_u64(a_mine, word); sts_u32(a_mine + 8u, obj); }
+                        TK(4, 0);
+                        named_bar_sync(32u * nbid);
+                        TK(5, 0);
+                    }
+                    // ---- resolve + assign ----
                     next_active = false;
                     if (obj != SLA_DEV_NONE) {
-                        uint4 rec = make_uint4(0u, 0u, SLA_DEV_NONE, 0u);
-                        if (lv) rec = lds_u128(a_lane);  // {word lo, word hi, object, flag of the previous round}
-                        const unsigned long long rw = ((unsigned long long)rec.y << 32) | rec.x;
-                        const bool lost = __any_sync(0xffffffffu, rec.z == obj && rw > word);
+                        bool lost = false;
+                        if (!solo) {
+                            uint4 rec = make_uint4(0u, 0u, SLA_DEV_NONE, 0u);
+                            if (lv) rec = lds_u128(a_lane);  // {word lo, word hi, object, flag of the previous round}
+                            const unsigned long long rw = ((unsigned long long)rec.y << 32) | rec.x;
+                            lost = __any_sync(0xffffffffu, rec.z == obj && rw > word);
+                        }
                         TK(6, lost);
                         if (word != 0ull && !lost) {     // word 0 == NaN bid: never wins
                             if (lane32 == 0) {
@@ -528,11 +539,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
                         }
                         TK(7, row.c[0]);
                     }
-                    if (lane32 == 0) sts_u32(a_mine + 12u, next_active ? 1u : 0u);
-                    TK(8, 0);
-                    named_bar_sync(32u * nbid);
-                    TK(9, 0);
-                    const uint32_t nmask = __ballot_sync(0xffffffffu, lv && lds_u32(a_lane + 12u) != 0u);
+                    uint32_t nmask;
+                    if (solo) {
+                        nmask = next_active ? mask : 0u;
+                        __syncwarp();                    // lane 0's mirror stores before the next round's gather
+                    } else {
+                        if (lane32 == 0) sts_u32(a_mine + 12u, next_active ? 1u : 0u);
+                        TK(8, 0);
+                        named_bar_sync(32u * nbid);
+                        TK(9, 0);
+                        nmask = __ballot_sync(0xffffffffu, lv && lds_u32(a_lane + 12u) != 0u);
+                    }
                     bids_local += nbid;
                     mask = nmask;
                     left -= 1u;
