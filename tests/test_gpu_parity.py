@@ -177,6 +177,8 @@ def test_engine_options_do_not_change_results(sla, oracle, kind, cls_name):
         dict(graph=1, tail_max=1024, zero_price_skip=1, regular=0),
         dict(graph=1, tail_max=1024, zero_price_skip=1, smem_prices=0),
         dict(graph=0, tail_max=16, zero_price_skip=0, regular=0),
+        dict(graph=1, tail_max=1024, zero_price_skip=1, smem_owners=0),
+        dict(graph=1, tail_max=300, zero_price_skip=1, smem_prices=0, smem_owners=0, regular=0),
     ]
     for opt in combos:
         solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v, eps=1.0 / (m + 1), options=opt)
@@ -352,6 +354,24 @@ def _symmetric_instance(n, mean_degree, seed, planted, lo, hi):
     rp[1:] = np.cumsum([len(r) for r in rows])
     c = np.concatenate(rows).astype(np.uint32)
     return rp, c, rng.uniform(lo, hi, size=c.size)
+
+
+def test_khosla_schedule_is_engine_independent(sla, oracle):
+    """The Khosla eps-schedule on a square instance through every engine split (wide only / single-CTA only / with and
+    without the shared-memory mirrors / host loop): identical bits, equal to the model."""
+    rng = np.random.default_rng(11)
+    n, k = 2500, 24
+    rp, c, v = random_sparse_instance(rng, n, n, k, integer=True, lo=0, hi=500)      # plants a perfect matching
+    eps = 1.0 / (n + 1)
+    ref = oracle.jacobi_model("khosla", n, n, rp, c, v, eps=eps)
+    assert ref["stats"]["num_unassigned"] == 0 and ref["stats"]["nreductions"] >= 5
+    for opt in (dict(), dict(graph=0), dict(tail_max=0), dict(tail_max=40, super_rounds=3),
+                dict(smem_prices=0), dict(smem_owners=0), dict(regular=0, tail_max=700)):
+        solver, z = gpu_solve(sla, "KhoslaSolver", n, n, rp, c, v, eps=eps, options=opt)
+        assert np.array_equal(z.person_to_object, ref["p2o"]), opt
+        assert np.array_equal(solver.prices(), ref["prices"]), opt
+        for key in ("num_unassigned", "nits", "nreductions", "rounds", "bids", "bid_arcs"):
+            assert solver.last_stats[key] == ref["stats"][key], (opt, key)
 
 
 def test_khosla_eps_schedule_on_square_instances(sla, oracle):
