@@ -1,5 +1,5 @@
 """ncu target: cfg3 (Khosla 1M x 4M, k=16) generated in HBM; 2 warm-up solves + 1 solve, host-driven loop so every
-round is a separate launch.  argv[1] = zero_price_skip (1/0)."""
+round is a separate launch.  argv[1] = zero_price_skip (1/0), argv[2] = stream_scan (1/0)."""
 import sys
 
 sys.path.insert(0, ".")
@@ -12,6 +12,8 @@ solver, z = S.KhoslaSolver.new(n, m, n * k)
 G.kregular_device(solver, n, m, k, seed=1)
 solver.set_option("graph", 0)
 solver.set_option("zero_price_skip", skip)
+if len(sys.argv) > 2:
+    solver.set_option("stream_scan", int(sys.argv[2]))
 for _ in range(3):
     st = solver.solve_resident(False, None)
 print("ok", st["rounds"], st["bid_arcs"], st["ms_solve"])

@@ -149,6 +149,7 @@ struct sla_ctx {
     uint32_t regular_k = 0;   // all rows have this many arcs (multiple of 8): the regular bid kernel is used
     int lpr8 = 1;
     int opt_regular = 1;
+    int opt_stream_scan = 0;   // first-round scan through the TMA pipeline (bid_stream_kernel): opt-in, measured 4 % slower
     int opt_smem_prices = 1, opt_smem_owners = 1, opt_khosla_scaling = 1;
     // tail-engine plan of the current instance (plan_tail): what is mirrored in shared memory and how many bidders fit
     bool tail_smem_prices = false;   // object prices mirrored
@@ -158,7 +159,7 @@ struct sla_ctx {
     uint32_t tail_smem_bytes = 0;    // dynamic shared memory of a tail launch
 
     // options
-    int opt_graph = 1, opt_tail_max = 1024, opt_skip_zero = 1, opt_profile = 0, opt_super_rounds = 6;
+    int opt_graph = 1, opt_tail_max = 1024, opt_skip_zero = 1, opt_profile = 0, opt_super_rounds = 6, opt_profile_repeat = 1;
     double opt_timeout_s = 900.0;   // wall-clock guard of one solve ("timeout_s" option / SLA_TIMEOUT_S)
     uint64_t generation = 1;   // bumped whenever a device buffer is reallocated
     GraphSlot graphs[4];   // [forward * 2 + first-launch-of-a-solve]
@@ -271,15 +272,34 @@ int pick_lpr(uint64_t nnz, uint32_t n_rows) {
 }
 
 // ---- kernel dispatch on lanes-per-row -----------------------------------------------------------------
+#ifndef SLA_REG_OCC_ZERO
+#define SLA_REG_OCC_ZERO 3
+#endif
+// First round of a solve on a regular CSR with K <= 256: the TMA pipeline (rows of a tile are one contiguous range).
+bool use_stream_scan(const sla_ctx* c) { return c->opt_stream_scan && c->regular_k != 0 && c->regular_k <= 256u; }
+
 template <int MODE>
 void launch_bid_regular_m(sla_ctx* c, const Params& p) {
+    if (MODE == PRICE_ZERO && use_stream_scan(c)) {
+        const int grid = c->num_sms * 2;
+        switch (c->lpr8) {
+            case 1: bid_stream_kernel<1><<<grid, kStreamThreads + 32, kStreamSmemBytes, c->stream>>>(p); break;
+            case 2: bid_stream_kernel<2><<<grid, kStreamThreads + 32, kStreamSmemBytes, c->stream>>>(p); break;
+            case 4: bid_stream_kernel<4><<<grid, kStreamThreads + 32, kStreamSmemBytes, c->stream>>>(p); break;
+            case 8: bid_stream_kernel<8><<<grid, kStreamThreads + 32, kStreamSmemBytes, c->stream>>>(p); break;
+            case 16: bid_stream_kernel<16><<<grid, kStreamThreads + 32, kStreamSmemBytes, c->stream>>>(p); break;
+            default: bid_stream_kernel<32><<<grid, kStreamThreads + 32, kStreamSmemBytes, c->stream>>>(p); break;
+        }
+        return;
+    }
+    const int grid_wide = (MODE == PRICE_ZERO) ? c->num_sms * SLA_REG_OCC_ZERO : c->grid_wide;
     switch (c->lpr8) {
-        case 1: bid_regular_kernel<1, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
-        case 2: bid_regular_kernel<2, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
-        case 4: bid_regular_kernel<4, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
-        case 8: bid_regular_kernel<8, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
-        case 16: bid_regular_kernel<16, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
-        default: bid_regular_kernel<32, MODE><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 1: bid_regular_kernel<1, MODE><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 2: bid_regular_kernel<2, MODE><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 4: bid_regular_kernel<4, MODE><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 8: bid_regular_kernel<8, MODE><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 16: bid_regular_kernel<16, MODE><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        default: bid_regular_kernel<32, MODE><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
     }
 }
 
@@ -571,8 +591,15 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
         bool first = true;
         while (!done) {
             const bool wide = !prev.done && prev.qlen[prev.cur] > prev.tail_max;
-            if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+            if (ctx->opt_profile) {
+                profile_fence_kernel<<<1, 32, 0, ctx->stream>>>();
+                CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+            }
             launch_one(ctx, p, 0, first && ctx->opt_skip_zero != 0);
+            // "profile_repeat" (development): the scan is idempotent (same slots, same maxima), so it can be launched
+            // several times between the two events to separate its duration from the event overhead
+            if (ctx->opt_profile && wide)
+                for (int r = 1; r < ctx->opt_profile_repeat; ++r) launch_one(ctx, p, 0, first && ctx->opt_skip_zero != 0);
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
             const bool late_now = first && late_init;
             if (late_now) {
@@ -787,6 +814,17 @@ int sla_ctx_create(int device, size_t row_capacity, size_t col_capacity, size_t 
         };
         for (cudaError_t x : ea)
             if (x != cudaSuccess) return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", x);
+        const int sdyn = (int)kStreamSmemBytes;
+        cudaError_t eb[6] = {
+            cudaFuncSetAttribute(bid_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sdyn),
+            cudaFuncSetAttribute(bid_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sdyn),
+            cudaFuncSetAttribute(bid_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sdyn),
+            cudaFuncSetAttribute(bid_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sdyn),
+            cudaFuncSetAttribute(bid_stream_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sdyn),
+            cudaFuncSetAttribute(bid_stream_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sdyn),
+        };
+        for (cudaError_t x : eb)
+            if (x != cudaSuccess) return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", x);
     }
     // blocks per SM of the widest kernel decide the persistent grid
     int occ = 0;
@@ -862,6 +900,12 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
         ctx->opt_regular = value ? 1 : 0;
     } else if (k == "timeout_s") {
         ctx->opt_timeout_s = (double)value;
+    } else if (k == "profile_repeat") {
+        if (value < 1 || value > 64) return fail(ctx, SLA_ERR_INVALID, "profile_repeat must be in [1, 64]");
+        ctx->opt_profile_repeat = (int)value;
+    } else if (k == "stream_scan") {
+        ctx->opt_stream_scan = value ? 1 : 0;
+        drop_graphs(ctx);
     } else if (k == "super_rounds") {
         if (value < 1 || value > 64) return fail(ctx, SLA_ERR_INVALID, "super_rounds must be in [1, 64]");
         ctx->opt_super_rounds = (int)value;

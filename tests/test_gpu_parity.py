@@ -179,6 +179,8 @@ def test_engine_options_do_not_change_results(sla, oracle, kind, cls_name):
         dict(graph=0, tail_max=16, zero_price_skip=0, regular=0),
         dict(graph=1, tail_max=1024, zero_price_skip=1, smem_owners=0),
         dict(graph=1, tail_max=300, zero_price_skip=1, smem_prices=0, smem_owners=0, regular=0),
+        dict(graph=1, tail_max=1024, zero_price_skip=1, stream_scan=1),
+        dict(graph=0, tail_max=0, zero_price_skip=1, stream_scan=1, profile=1),
     ]
     for opt in combos:
         solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v, eps=1.0 / (m + 1), options=opt)
@@ -193,6 +195,22 @@ def test_engine_options_do_not_change_results(sla, oracle, kind, cls_name):
             assert sum(p["arcs"] for p in prof) == ref["stats"]["bid_arcs"]
         if opt["tail_max"] == 0:
             assert solver.last_stats["tail_rounds"] == 0
+
+
+@pytest.mark.parametrize("k", [8, 16, 24, 40, 64, 136, 256])
+@pytest.mark.parametrize("stream", [0, 1])
+def test_first_round_scans_equal_model(sla, oracle, k, stream):
+    """First-round scan of a regular CSR, both implementations -- the two-rows-in-flight LDG.256 kernel (default) and the
+    TMA pipeline (bid_stream_kernel, option stream_scan): every lanes-per-row class, row counts that leave a ragged last
+    pass / tile, both sign conventions; bit-identical to the sequential model."""
+    rng = np.random.default_rng(100 + k)
+    n = 2500 + k + 3                                   # not a multiple of any tile height
+    m = 3 * n
+    rp, c, v = random_sparse_instance(rng, n, m, k, integer=True, lo=0, hi=500)
+    for maximize in (False, True):
+        solver, z = gpu_solve(sla, "KhoslaSolver", n, m, rp, c, v, maximize=maximize, options=dict(stream_scan=stream, tail_max=256))
+        assert solver.last_stats["wide_rounds"] >= 1
+        assert_equals_model(oracle, "khosla", solver, z, n, m, rp, c, v, maximize=maximize)
 
 
 @pytest.mark.parametrize("kind,cls_name", SOLVERS)
