@@ -1,6 +1,9 @@
 // sla_api.cu -- host side of libsla_b200.so: context, CSR mirror, solve drivers (CUDA-graph super-rounds or a
 // host-driven loop), post-processing, and the extern "C" boundary declared in include/sla.h.
 #include <cmath>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
@@ -134,6 +137,12 @@ struct sla_ctx {
     uint32_t* d_scratch = nullptr;   // 16 words
     double* d_partial = nullptr;     // objective partial sums, one per block
     // pinned staging
+    unsigned char* h_small = nullptr;     // small instances: one block for the CSR on its way up and the results on their way down
+    size_t h_small_cap = 0;
+    cudaEvent_t ev_small = nullptr;       // the last H2D copy out of h_small has completed
+    bool small_pending = false;
+    unsigned char* h_dl = nullptr;        // small instances: results land here behind each graph launch (one sync per launch)
+    size_t h_dl_cap = 0;
     DevState* h_state = nullptr;
     DevCsrStats* h_csr_stats = nullptr;
     uint32_t* h_scratch = nullptr;
@@ -149,6 +158,10 @@ struct sla_ctx {
     uint32_t regular_k = 0;   // all rows have this many arcs (multiple of 8): the regular bid kernel is used
     int lpr8 = 1;
     int opt_regular = 1;
+    int opt_small_path = 1;    // small instances: host-side statistics on the way up, results behind the graph on the way down
+    int opt_wide_first = 1;    // first round of a small plain-Khosla solve on the wide kernels (solve_tail_max)
+    int opt_l2_persist = 0;    // development: access-policy window (persisting) over the bid words
+    size_t l2_persist_max = 0, l2_window_max = 0;
     int opt_stream_scan = 0;   // first-round scan through the TMA pipeline (bid_stream_kernel): opt-in, measured 4 % slower
     int opt_smem_prices = 1, opt_smem_owners = 1, opt_khosla_scaling = 1;
     // tail-engine plan of the current instance (plan_tail): what is mirrored in shared memory and how many bidders fit
@@ -365,21 +378,64 @@ int kernels_per_super_round(const sla_ctx* c, bool forward, bool tail_only) {
     return (forward ? 5 : (khosla_phases(c) ? 4 : 3)) - (tail_only ? 2 : 0);
 }
 
-bool is_tail_only(const sla_ctx* c) { return c->n_rows <= c->tail_max_eff; }
+// Plain Khosla rounds (no eps-schedule) finish in a handful of rounds whose first one has all N bidders: when N is
+// within the tail engine's reach but large (cfg1: 1,000 persons x 32 arcs), that first round is better spread over
+// the whole GPU -- the tail engine takes over from round 2 (a few per cent of N).  "wide_first" = 0 turns this off.
+constexpr uint32_t kWideFirstMinRows = 640;
+uint32_t solve_tail_max(const sla_ctx* c, bool forward) {
+    if (!forward && !khosla_phases(c) && c->opt_wide_first && c->n_rows > kWideFirstMinRows && c->n_rows <= c->tail_max_eff)
+        return c->n_rows / 2u;
+    return c->tail_max_eff;
+}
+
+bool is_tail_only(const sla_ctx* c, bool forward) { return c->n_rows <= solve_tail_max(c, forward); }
 
 // Khosla on a tail-only instance finishes inside the first tail launch: further super-rounds would be pure no-ops.
+// Small rectangular Khosla instances need one wide round before the tail engine finishes them: two super-rounds.
 int super_rounds_for(const sla_ctx* c, bool forward) {
-    return (!forward && is_tail_only(c) && !khosla_phases(c)) ? 1 : c->opt_super_rounds;
+    if (!forward && !khosla_phases(c)) {
+        if (is_tail_only(c, forward)) return 1;
+        if (c->n_rows <= 4u * c->tail_max_eff && c->opt_super_rounds > 2) return 2;
+    }
+    return c->opt_super_rounds;
+}
+
+// Development option "l2_persist": mark the bid words (8 B per object, RED.MAX target of every bid) as persisting in
+// the L2 (set-aside carve-out + access-policy window on the stream and on the captured kernel nodes).
+bool l2_window(const sla_ctx* c, cudaAccessPolicyWindow* w) {
+    if (!c->opt_l2_persist || !c->d_best || !c->l2_persist_max || !c->l2_window_max || !c->has_csr) return false;
+    size_t bytes = (size_t)c->n_cols * 8u;
+    if (bytes > c->l2_window_max) bytes = c->l2_window_max;
+    const size_t aside = bytes < c->l2_persist_max ? bytes : c->l2_persist_max;
+    w->base_ptr = c->d_best;
+    w->num_bytes = bytes;
+    w->hitRatio = (float)((double)aside / (double)bytes);
+    w->hitProp = cudaAccessPropertyPersisting;
+    w->missProp = cudaAccessPropertyNormal;
+    return true;
+}
+void apply_l2_policy(sla_ctx* c) {
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    if (l2_window(c, &v.accessPolicyWindow)) {
+        const size_t aside = v.accessPolicyWindow.num_bytes < c->l2_persist_max ? v.accessPolicyWindow.num_bytes : c->l2_persist_max;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, aside);
+    } else {
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();
 }
 
 int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out) {
     GraphSlot& g = ctx->graphs[(forward ? 2 : 0) + (zero_first ? 1 : 0)];
     const uint32_t reg_key = use_regular(ctx) ? ctx->regular_k : 0u;
-    const bool tail_only = is_tail_only(ctx);
+    const bool tail_only = is_tail_only(ctx, forward);
     const int n_super = super_rounds_for(ctx, forward);
     if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == n_super &&
         g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices && g.tail_only == tail_only &&
-        g.tail_smem_bytes == ctx->tail_smem_bytes && g.tail_max == ctx->tail_max_eff && g.khosla_phases == khosla_phases(ctx)) {
+        g.tail_smem_bytes == ctx->tail_smem_bytes && g.tail_max == solve_tail_max(ctx, forward) && g.khosla_phases == khosla_phases(ctx)) {
         *out = g.exec;
         return SLA_OK;
     }
@@ -390,6 +446,22 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     for (int r = 0; r < n_super; ++r) launch_super_round(ctx, p, forward, zero_first && r == 0, tail_only);
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (e != cudaSuccess) return fail(ctx, SLA_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    {
+        cudaKernelNodeAttrValue av;
+        memset(&av, 0, sizeof av);
+        if (l2_window(ctx, &av.accessPolicyWindow)) {
+            size_t nn = 0;
+            cudaGraphGetNodes(graph, nullptr, &nn);
+            std::vector<cudaGraphNode_t> nodes(nn);
+            if (nn) cudaGraphGetNodes(graph, nodes.data(), &nn);
+            for (cudaGraphNode_t nd : nodes) {
+                cudaGraphNodeType t;
+                if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeKernel)
+                    cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &av);
+            }
+            cudaGetLastError();
+        }
+    }
     e = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) {
@@ -403,7 +475,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     g.regular_k = reg_key;
     g.smem_prices = ctx->tail_smem_prices;
     g.tail_smem_bytes = ctx->tail_smem_bytes;
-    g.tail_max = ctx->tail_max_eff;
+    g.tail_max = solve_tail_max(ctx, forward);
     g.khosla_phases = khosla_phases(ctx);
     *out = g.exec;
     return SLA_OK;
@@ -501,7 +573,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
     s.zero_prices = 1;
     s.algo = forward ? ALGO_FORWARD : ALGO_KHOSLA;
     s.pbits = person_bits(N);
-    s.tail_max = ctx->tail_max_eff;
+    s.tail_max = solve_tail_max(ctx, forward);
     s.own_mode = ctx->tail_own_mode;
     s.tail_cap = ctx->tail_cap;
     s.skip_zero = (uint32_t)ctx->opt_skip_zero;
@@ -547,7 +619,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
 
     // The initialisation of prices / owners / assignment (solver.rs:218-229) runs BEHIND the first bid scan when that
     // scan does not read them (all prices zero, wide first round); otherwise up front.
-    const bool late_init = ctx->opt_skip_zero != 0 && !is_tail_only(ctx);
+    const bool late_init = ctx->opt_skip_zero != 0 && !is_tail_only(ctx, forward);
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_state, ctx->h_state, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
     if (late_init) {
@@ -559,6 +631,15 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
     ctx->best_dirty = true;   // until the solve ends at a round boundary
 
     const bool use_graph = ctx->opt_graph && !ctx->opt_profile;
+    const size_t dl_o2p = h_p2o ? (((size_t)N * 4 + 15) & ~(size_t)15) : 0;
+    const size_t dl_prices = dl_o2p + (h_o2p ? (((size_t)M * 4 + 15) & ~(size_t)15) : 0);
+    const size_t dl_bytes = dl_prices + (h_prices ? (size_t)M * 8 : 0);
+    constexpr size_t kSmallDownloadBytes = (size_t)1 << 20;
+    const bool small_dl = use_graph && ctx->opt_small_path && dl_bytes > 0 && dl_bytes <= kSmallDownloadBytes;
+    if (small_dl && !ctx->h_dl) {
+        CU(cudaMallocHost((void**)&ctx->h_dl, kSmallDownloadBytes));
+        ctx->h_dl_cap = kSmallDownloadBytes;
+    }
     bool done = false;
     const auto t_start = std::chrono::steady_clock::now();
     auto timed_out = [&]() {
@@ -578,7 +659,16 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
             first = false;
             CU(cudaGraphLaunch(exec, ctx->stream));
             graph_launches += 1;
-            launches += (uint32_t)(super_rounds_for(ctx, forward) * kernels_per_super_round(ctx, forward, is_tail_only(ctx)));
+            if (small_dl) {
+                // small results ride behind every graph launch into page-locked staging: when the poll below reports
+                // `done`, they are already on the host (one synchronisation per launch instead of three)
+                CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+                if (h_p2o) CU(cudaMemcpyAsync(ctx->h_dl, ctx->d_p2o, (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                if (h_o2p) CU(cudaMemcpyAsync(ctx->h_dl + dl_o2p, ctx->d_o2p, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                if (h_prices) CU(cudaMemcpyAsync(ctx->h_dl + dl_prices, ctx->d_prices, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+            }
+            launches += (uint32_t)(super_rounds_for(ctx, forward) * kernels_per_super_round(ctx, forward, is_tail_only(ctx, forward)));
             if (late_init && graph_launches == 1) launches += 1;   // init_solve_late_kernel sits in the first graph
             if ((rc = poll_state(ctx))) return rc;
             done = ctx->h_state->done != 0;
@@ -662,18 +752,25 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
             if (!done && timed_out()) return fail(ctx, SLA_ERR_STATE, "solve exceeded the wall-clock guard (timeout_s)");
         }
     }
-    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (!small_dl) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
 
     const DevState f = *ctx->h_state;
     if (f.safety_rounds_left <= 1) return fail(ctx, SLA_ERR_STATE, "safety round limit reached");
     ctx->best_dirty = false;
     ctx->has_solution = true;
 
-    if (h_p2o) CU(cudaMemcpyAsync(h_p2o, ctx->d_p2o, (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (h_o2p) CU(cudaMemcpyAsync(h_o2p, ctx->d_o2p, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (h_prices) CU(cudaMemcpyAsync(h_prices, ctx->d_prices, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (small_dl) {
+        // already downloaded behind the last graph launch (events 1 and 2 recorded there, completed by the poll's sync)
+        if (h_p2o) memcpy(h_p2o, ctx->h_dl, (size_t)N * 4);
+        if (h_o2p) memcpy(h_o2p, ctx->h_dl + dl_o2p, (size_t)M * 4);
+        if (h_prices) memcpy(h_prices, ctx->h_dl + dl_prices, (size_t)M * 8);
+    } else {
+        if (h_p2o) CU(cudaMemcpyAsync(h_p2o, ctx->d_p2o, (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_o2p) CU(cudaMemcpyAsync(h_o2p, ctx->d_o2p, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_prices) CU(cudaMemcpyAsync(h_prices, ctx->d_prices, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
 
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -742,6 +839,162 @@ int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz)
     return SLA_OK;
 }
 
+// ---- small instances: no device round trip on the way up ----------------------------------------------------------
+// The statistics csr_stats_kernel would compute (value range, column bound, monotone extents, uniform degree) are taken
+// on the host in the same pass that copies the three arrays into one page-locked block; the copies to the device are
+// only enqueued.  With `negate_host` the caller's values are negated in place in that pass (solver.rs:214-216); the
+// device receives the original values, as with sla_upload_csr_negating.  The caller's arrays are not referenced after
+// the call returns.
+constexpr size_t kSmallCsrBytes = (size_t)1 << 20;
+
+bool small_csr(uint32_t num_rows, uint64_t nnz) { return ((size_t)num_rows + 1) * 4 + (size_t)nnz * 12 <= kSmallCsrBytes; }
+
+int small_block(sla_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->h_small_cap) return SLA_OK;
+    if (ctx->small_pending) { CU(cudaEventSynchronize(ctx->ev_small)); ctx->small_pending = false; }
+    if (ctx->h_small) { cudaFreeHost(ctx->h_small); ctx->h_small = nullptr; ctx->h_small_cap = 0; }
+    size_t cap = (size_t)64 << 10;
+    while (cap < bytes) cap <<= 1;
+    CU(cudaMallocHost((void**)&ctx->h_small, cap));
+    ctx->h_small_cap = cap;
+    if (!ctx->ev_small) CU(cudaEventCreateWithFlags(&ctx->ev_small, cudaEventDisableTiming));
+    return SLA_OK;
+}
+
+// Copy `values` into the staging block, take their range, optionally negate the caller's copy in place.  Returns true
+// when a zero or a NaN was seen: the caller then recomputes the range in the exact total order of csr_stats_kernel.
+bool stage_values(double* values, double* stage, uint64_t nnz, bool negate, double* omn, double* omx) {
+    uint64_t g = 0;
+    double mn = values[0], mx = values[0];
+    bool special = false;
+#if defined(__SSE2__)
+    if (nnz >= 8) {
+        __m128d mn0 = _mm_set1_pd(mn), mn1 = mn0, mx0 = mn0, mx1 = mn0;
+        __m128d sp = _mm_setzero_pd();
+        const __m128d zero = _mm_setzero_pd(), sign = _mm_set1_pd(-0.0);
+        for (; g + 4 <= nnz; g += 4) {
+            const __m128d a = _mm_loadu_pd(values + g), b = _mm_loadu_pd(values + g + 2);
+            _mm_storeu_pd(stage + g, a);
+            _mm_storeu_pd(stage + g + 2, b);
+            mn0 = _mm_min_pd(a, mn0); mx0 = _mm_max_pd(a, mx0);
+            mn1 = _mm_min_pd(b, mn1); mx1 = _mm_max_pd(b, mx1);
+            sp = _mm_or_pd(sp, _mm_or_pd(_mm_cmpeq_pd(a, zero), _mm_cmpunord_pd(a, a)));
+            sp = _mm_or_pd(sp, _mm_or_pd(_mm_cmpeq_pd(b, zero), _mm_cmpunord_pd(b, b)));
+            if (negate) {
+                _mm_storeu_pd(values + g, _mm_xor_pd(a, sign));
+                _mm_storeu_pd(values + g + 2, _mm_xor_pd(b, sign));
+            }
+        }
+        mn0 = _mm_min_pd(mn0, mn1);
+        mx0 = _mm_max_pd(mx0, mx1);
+        double t[2];
+        _mm_storeu_pd(t, mn0); mn = t[0] < t[1] ? t[0] : t[1];
+        _mm_storeu_pd(t, mx0); mx = t[0] > t[1] ? t[0] : t[1];
+        special = _mm_movemask_pd(sp) != 0;
+    }
+#endif
+    for (; g < nnz; ++g) {
+        const double v = values[g];
+        stage[g] = v;
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+        special |= !(v == v) || v == 0.0;
+        if (negate) values[g] = -v;
+    }
+    *omn = mn;
+    *omx = mx;
+    return special;
+}
+
+// Copy the column indices into the staging block; true when one of them is >= num_cols.
+bool stage_cols(const uint32_t* cols, uint32_t* stage, uint64_t nnz, uint32_t num_cols) {
+    uint64_t g = 0;
+    bool bad = false;
+#if defined(__SSE2__)
+    const __m128i bias = _mm_set1_epi32((int)0x80000000u), lim = _mm_set1_epi32((int)((num_cols - 1u) ^ 0x80000000u));
+    __m128i acc = _mm_setzero_si128();
+    for (; g + 8 <= nnz; g += 8) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(cols + g)), b = _mm_loadu_si128((const __m128i*)(cols + g + 4));
+        _mm_storeu_si128((__m128i*)(stage + g), a);
+        _mm_storeu_si128((__m128i*)(stage + g + 4), b);
+        acc = _mm_or_si128(acc, _mm_or_si128(_mm_cmpgt_epi32(_mm_xor_si128(a, bias), lim), _mm_cmpgt_epi32(_mm_xor_si128(b, bias), lim)));
+    }
+    bad = _mm_movemask_epi8(acc) != 0;
+#endif
+    for (; g < nnz; ++g) {
+        stage[g] = cols[g];
+        bad |= cols[g] >= num_cols;
+    }
+    return bad;
+}
+
+int upload_small(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* row_ptr, const uint32_t* column_indices,
+                 double* values, uint64_t nnz, bool negate_host) {
+    const size_t b_rp = (((size_t)num_rows + 1) * 4 + 15) & ~(size_t)15, b_cols = ((size_t)nnz * 4 + 15) & ~(size_t)15;
+    int rc = small_block(ctx, b_rp + b_cols + (size_t)nnz * 8);
+    if (rc) return rc;
+    if (ctx->small_pending) { CU(cudaEventSynchronize(ctx->ev_small)); ctx->small_pending = false; }
+    uint32_t* s_rp = reinterpret_cast<uint32_t*>(ctx->h_small);
+    uint32_t* s_cols = reinterpret_cast<uint32_t*>(ctx->h_small + b_rp);
+    double* s_vals = reinterpret_cast<double*>(ctx->h_small + b_rp + b_cols);
+    ctx->has_csr = false;
+    // extents
+    if (row_ptr[0] != 0 || (uint64_t)row_ptr[num_rows] != nnz)
+        return fail(ctx, SLA_ERR_INVALID, "row_ptr[0] must be 0 and row_ptr[num_rows] must equal nnz");
+    const uint32_t k0 = row_ptr[1] - row_ptr[0];
+    uint32_t bad_r = 0, irr = 0;
+    s_rp[0] = row_ptr[0];
+    for (uint32_t i = 0; i < num_rows; ++i) {
+        const uint32_t a = row_ptr[i], b = row_ptr[i + 1];
+        s_rp[i + 1] = b;
+        bad_r |= (b < a || (uint64_t)b > nnz) ? 1u : 0u;
+        irr |= (b - a != k0) ? 1u : 0u;
+    }
+    if (bad_r) return fail(ctx, SLA_ERR_INVALID, "row extents are not monotone");
+    // columns, values: one vectorised pass each (copy + bound check, copy + range [+ in-place negation])
+    if (stage_cols(column_indices, s_cols, nnz, num_cols)) return fail(ctx, SLA_ERR_INVALID, "column index out of range (>= num_cols)");
+    const double first = values[0];
+    double vmin, vmax;
+    if (stage_values(values, s_vals, nnz, negate_host, &vmin, &vmax)) {
+        // zeros or NaNs present: the range in csr_stats_kernel's total order (-0.0 < +0.0, NaNs at the ends), from the
+        // staged copy of the original values
+        unsigned long long kmin = ~0ull, kmax = 0ull;
+        for (uint64_t g = 0; g < nnz; ++g) {
+            unsigned long long u;
+            __builtin_memcpy(&u, s_vals + g, 8);
+            const unsigned long long k = u ^ ((u >> 63) ? ~0ull : (1ull << 63));
+            kmin = k < kmin ? k : kmin;
+            kmax = k > kmax ? k : kmax;
+        }
+        vmin = order_key_to_f64_host(kmin);
+        vmax = order_key_to_f64_host(kmax);
+    }
+    CU(cudaMemcpyAsync(ctx->d_row_ptr, s_rp, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_cols, s_cols, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_vals, s_vals, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_small, ctx->stream));
+    ctx->small_pending = true;
+    ctx->n_rows = num_rows;
+    ctx->n_cols = num_cols;
+    ctx->nnz = nnz;
+    ctx->v_min = vmin;
+    ctx->v_max = vmax;
+    ctx->first_value = first;
+    ctx->dev_sign = 1;
+    ctx->lpr = pick_lpr(nnz, num_rows);
+    ctx->regular_k = 0;
+    if (!irr && nnz == (uint64_t)num_rows * (nnz / num_rows) && (nnz / num_rows) % 8 == 0) {
+        ctx->regular_k = (uint32_t)(nnz / num_rows);
+        int l = 1;
+        while (l < 32 && (uint32_t)(l * 8) < ctx->regular_k) l *= 2;
+        ctx->lpr8 = l;
+    }
+    ctx->has_csr = true;
+    ctx->has_solution = false;
+    plan_tail(ctx);
+    return SLA_OK;
+}
+
 int check_shape(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz) {
     // reference src/solver.rs:192-193 (init) and 232-240 (validate_input), for I = u32
     if (!(num_rows <= num_cols)) return fail(ctx, SLA_ERR_INVALID, "num_rows must be <= num_cols");
@@ -784,6 +1037,8 @@ int sla_ctx_create(int device, size_t row_capacity, size_t col_capacity, size_t 
     sla_ctx* ctx = new sla_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     if (const char* t = getenv("SLA_TIMEOUT_S")) ctx->opt_timeout_s = atof(t);
     auto bail = [&](const char* what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
@@ -862,6 +1117,9 @@ void sla_ctx_destroy(sla_ctx* ctx) {
     cudaFree(ctx->d_p2o); cudaFree(ctx->d_o2p); cudaFree(ctx->d_best); cudaFree(ctx->d_queue[0]);
     cudaFree(ctx->d_queue[1]); cudaFree(ctx->d_slot_obj); cudaFree(ctx->d_slot_bid); cudaFree(ctx->d_state);
     cudaFree(ctx->d_csr_stats); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    if (ctx->h_dl) cudaFreeHost(ctx->h_dl);
+    if (ctx->ev_small) cudaEventDestroy(ctx->ev_small);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_csr_stats) cudaFreeHost(ctx->h_csr_stats);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
@@ -903,6 +1161,14 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "profile_repeat") {
         if (value < 1 || value > 64) return fail(ctx, SLA_ERR_INVALID, "profile_repeat must be in [1, 64]");
         ctx->opt_profile_repeat = (int)value;
+    } else if (k == "l2_persist") {
+        ctx->opt_l2_persist = value ? 1 : 0;
+        drop_graphs(ctx);
+        apply_l2_policy(ctx);
+    } else if (k == "small_path") {
+        ctx->opt_small_path = value ? 1 : 0;
+    } else if (k == "wide_first") {
+        ctx->opt_wide_first = value ? 1 : 0;
     } else if (k == "stream_scan") {
         ctx->opt_stream_scan = value ? 1 : 0;
         drop_graphs(ctx);
@@ -924,6 +1190,8 @@ int sla_upload_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uin
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
+    if (ctx->opt_small_path && small_csr(num_rows, nnz))
+        return upload_small(ctx, num_rows, num_cols, row_ptr, column_indices, const_cast<double*>(values), nnz, false);
     CU(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_cols, column_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_vals, values, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -945,6 +1213,8 @@ int sla_upload_csr_negating(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, 
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
+    if (ctx->opt_small_path && small_csr(num_rows, nnz))
+        return upload_small(ctx, num_rows, num_cols, row_ptr, column_indices, values, nnz, true);
     if (!ctx->neg.start(ctx->device)) return fail(ctx, SLA_ERR_CUDA, "could not start the host negation workers");
     NegPool& np = ctx->neg;
     if (threads < 1) threads = 1;

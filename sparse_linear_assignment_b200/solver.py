@@ -37,8 +37,6 @@ def host_threads() -> int:
     co-located ranks (torchrun exports LOCAL_WORLD_SIZE), at most 16."""
     if os.environ.get("SLA_HOST_THREADS"):
         return max(1, min(16, int(os.environ["SLA_HOST_THREADS"])))
-    if os.environ.get("SLA_HOST_THREADS"):
-        return max(1, min(16, int(os.environ["SLA_HOST_THREADS"])))
     cores = os.cpu_count() or 1
     local_world = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1), 1)
     return max(1, min(16, cores // local_world))
@@ -419,7 +417,8 @@ class AuctionSolver:
             vals = self._values.view
             _ensure(row_ptr.size == n + 1, "fewer rows populated than num_rows")
             flip = maximize is not None and (bool(maximize) ^ bool((vals[0] if vals.size else 0.0) >= 0.0))
-            self._pre_negated = bool(flip and vals.size >= (1 << 16))
+            # any size: small instances are negated in the library's single staging pass, large ones by its worker pool
+            self._pre_negated = bool(flip)
             if self._pre_negated:
                 rc = _lib.load().sla_upload_csr_negating(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
                                                          vals.ctypes.data, nnz, host_threads())

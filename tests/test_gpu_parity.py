@@ -214,6 +214,46 @@ def test_first_round_scans_equal_model(sla, oracle, k, stream):
 
 
 @pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_small_instance_path_equals_device_statistics_path(sla, oracle, kind, cls_name):
+    """Small instances take their statistics on the host while staging the upload and download their results behind
+    the graph launch (option small_path, default on); the device-statistics path (small_path = 0) must see the same
+    value range, sign, regularity and errors: ragged and regular rows, zeros of both signs, mixed signs, both
+    objectives, repeated solves with the in-place negation observable on the host copy."""
+    rng = np.random.default_rng(11)
+    cases = []
+    for n, m, k, regular in ((7, 7, 3, False), (60, 90, 8, True), (700, 2100, 16, True), (900, 900, 5, False), (1500, 4000, 32, True)):
+        if kind == "forward":
+            m = n if n in (7, 900) else m
+        rp, c, v = random_sparse_instance(rng, n, m, k, integer=True, lo=0, hi=50)
+        if not regular:
+            v = v - 20.0                      # mixed signs
+            v[::7] = 0.0
+            v[3::11] = -0.0
+        cases.append((n, m, rp, c, v))
+    for n, m, rp, c, v in cases:
+        for maximize in (False, True):
+            out = []
+            for small in (1, 0):
+                solver, z = getattr(sla, cls_name).new(n, m, len(c))
+                solver.set_option("small_path", small)
+                solver.load_csr(n, m, rp, c, v.copy())
+                solver.solve(z, maximize, None)
+                first = (z.person_to_object.copy(), z.object_to_person.copy(), solver.prices().copy(), solver.values().copy(),
+                         dict(solver.last_stats))
+                solver.solve(z, not maximize, None)          # second solve on the (possibly negated) host copy
+                out.append((first, z.person_to_object.copy(), solver.prices().copy(), solver.values().copy()))
+            a, b = out
+            for x, y in zip(a[0][:4], b[0][:4]):
+                assert np.array_equal(x, y)
+            for key in ("num_unassigned", "nits", "nreductions", "rounds", "bids", "bid_arcs", "dropped", "values_negated", "eps"):
+                assert a[0][4][key] == b[0][4][key], key
+            for x, y in zip(a[1:], b[1:]):
+                assert np.array_equal(x, y)
+            solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v.copy(), maximize=maximize)
+            assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v.copy(), maximize=maximize)
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
 def test_u16_index_type(sla, oracle, kind, cls_name):
     rng = np.random.default_rng(3)
     n, m, k = 300, 300 if kind == "forward" else 400, 6
