@@ -451,7 +451,8 @@ def main_ours(args):
         torch.cuda.synchronize(device)
         e2e_s += time.perf_counter() - t0
         e2e_arcs += solver.last_stats["bid_arcs"]
-    h2d = 4 * (n + 1) + 12 * n * k
+    h2d, value_bytes = solver.last_upload()        # bytes the library actually moved: integer costs cross PCIe as u16
+                                                   # and are widened to f64 in HBM (sla_last_upload)
     d2h = 4 * n + 4 * m                            # person_to_object + object_to_person (prices stay resident until read)
     objective = solver.get_objective(solution)
 
@@ -505,7 +506,7 @@ def main_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_value / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "clocks": clocks,
-            "e2e": {"value": e2e_arcs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_arcs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "h2d_value_bytes": value_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
             "roofline": roof.get("roofline"),

@@ -101,7 +101,13 @@ void sla_host_negate_f64(double *values, size_t n, int threads);
  * init_solve), "regular" (1: use the uniform-degree bid kernel when every row has the same multiple-of-8 degree),
  * "khosla_scaling" (1: Khosla rounds on square instances run under an eps-schedule that ends at the caller's eps
  * and fall back to the plain rounds when a phase drops anybody; 0: plain fixed-eps rounds),
- * "profile" (1: record sla_round_profile entries), "super_rounds" (rounds captured per graph), "timeout_s". */
+ * "profile" (1: record sla_round_profile entries), "super_rounds" (rounds captured per graph), "timeout_s",
+ * "small_path" (1: instances of up to 1 MB take their statistics on the host while they are staged for upload and
+ * download their results behind each graph launch: one device round trip per solve), "wide_first" (1: plain Khosla
+ * solves with 641 .. tail_max persons run their first round on the grid-wide kernels), "narrow_upload" (1: see
+ * sla_last_upload), "stream_scan" (1: first-round scan of a uniform-degree CSR through the TMA pipeline
+ * bid_stream_kernel instead of the LDG.256 kernel; identical results), "l2_persist" (1: access-policy window that
+ * keeps the bid words persisting in the L2), "profile_repeat" (development: launches of the scan per profile bracket). */
 int sla_set_option(sla_ctx *ctx, const char *key, int64_t value);
 
 /* ---- CSR mirror: the host keeps ownership of i_starts_stops / column_indices / values built by
@@ -114,13 +120,21 @@ int sla_upload_csr(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uin
                    const uint32_t *column_indices, const double *values, uint64_t nnz);
 
 /* sla_upload_csr plus the in-place negation of the HOST `values` that AuctionSolver::init_solve performs
- * (solver.rs:214-216) when `maximize ^ (values[0] >= 0)`: `values` crosses PCIe first, in `threads` chunks; a pool of
- * host worker threads owned by the context negates chunk w as soon as the copy of chunk w has completed, while the
- * rest is still being uploaded and the solve runs.  The work is complete before the next sla_*_solve / upload /
- * destroy on this context returns.  The device keeps the
- * original values: the following solve still reports values_negated == 1, and the host must not negate again. */
+ * (solver.rs:214-216) when `maximize ^ (values[0] >= 0)`, done by up to `threads` host worker threads owned by the
+ * context while the upload and the solve run: in the pass that stages a narrow (u16 / f32) copy of the values for the
+ * wire when they allow it (sla_last_upload), else chunk by chunk behind the f64 copies; small instances: in the single
+ * staging pass of the calling thread.  The work is complete before the next sla_*_solve / upload / destroy on this
+ * context returns.  The device keeps the original values: the following solve still reports values_negated == 1,
+ * and the host must not negate again. */
 int sla_upload_csr_negating(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *row_ptr,
                             const uint32_t *column_indices, double *values, uint64_t nnz, int threads);
+
+/* Bytes the last sla_upload_csr / sla_upload_csr_negating call moved from host to device, and the width (2, 4 or 8
+ * bytes) the values crossed PCIe with.  Large uploads whose values all survive a round trip through u16 (non-negative
+ * integers below 65,536) or f32 are staged narrow by the context's host workers and widened to f64 again in HBM, bit
+ * for bit; option "narrow_upload" = 0 turns this off.  No counterpart in the reference (its Vecs never leave the
+ * host, solver.rs:41-101). */
+int sla_last_upload(const sla_ctx *ctx, uint64_t *bytes, uint32_t *value_bytes);
 
 /* Same, source arrays already in device memory (device-side generators, multi-GPU shards). */
 int sla_upload_csr_device(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *d_row_ptr,

@@ -49,36 +49,139 @@ struct sla_part_state;
 // condition variable between jobs.
 struct NegPool {
     static constexpr int kMax = 16;
+    static constexpr int kMaxPieces = 4096;
+    enum Mode : int { NEGATE_AFTER_COPY = 0, NARROW = 1 };
     std::vector<std::thread> threads;
     std::mutex m;
     std::condition_variable cv_job, cv_done;
     uint64_t job_id = 0;
     int pending = 0;
     bool stop = false;
+    int mode = NEGATE_AFTER_COPY;
     double* values = nullptr;
     size_t chunk = 0, total = 0;
     int nchunks = 0;
     int device = 0;
     cudaEvent_t ev[kMax] = {};
+    // NARROW: lossless narrowing of `values` into `stage` (tier 2: u16, tier 4: f32), piece by piece in array order;
+    // done[p] is set (release) when piece p is staged, `narrow_fail` when a value does not survive the round trip
+    void* stage = nullptr;
+    int tier = 0;
+    size_t piece = 0;
+    int npieces = 0;
+    bool narrow_negate = false;  // NARROW: negate each piece in place in the very pass that stages it
+    int narrow_workers = kMax;   // workers 0 .. narrow_workers-1 take pieces (co-located ranks share the cores)
+    std::atomic<int> next_piece{0};
+    std::atomic<int> narrow_fail{0};
+    std::atomic<unsigned char> done[kMaxPieces];
+
+    // true when every value of [lo, hi) is an integer in [0, 65535] with a clear sign bit (so that widening restores the
+    // exact bit pattern); out = the values as u16 (streaming stores: the staging block is only read by the DMA engine).
+    // With `negate` the values are negated in place in the same pass (and restored if the piece turns out not to be
+    // representable).
+    static bool narrow_u16(double* v, uint16_t* out, size_t lo, size_t hi, bool negate) {
+        size_t i = lo;
+        bool good = true;
+#if defined(__SSE2__)
+        if ((((uintptr_t)(out + lo)) & 15u) == 0) {
+            __m128i bad = _mm_setzero_si128();
+            __m128d ok = _mm_castsi128_pd(_mm_set1_epi32(-1)), sgn = _mm_setzero_pd();
+            const __m128d sign = _mm_set1_pd(-0.0);
+            for (; i + 8 <= hi; i += 8) {
+                const __m128d a = _mm_loadu_pd(v + i), b = _mm_loadu_pd(v + i + 2), c = _mm_loadu_pd(v + i + 4), d = _mm_loadu_pd(v + i + 6);
+                const __m128i ia = _mm_cvttpd_epi32(a), ib = _mm_cvttpd_epi32(b), ic = _mm_cvttpd_epi32(c), id = _mm_cvttpd_epi32(d);
+                ok = _mm_and_pd(ok, _mm_and_pd(_mm_and_pd(_mm_cmpeq_pd(_mm_cvtepi32_pd(ia), a), _mm_cmpeq_pd(_mm_cvtepi32_pd(ib), b)),
+                                               _mm_and_pd(_mm_cmpeq_pd(_mm_cvtepi32_pd(ic), c), _mm_cmpeq_pd(_mm_cvtepi32_pd(id), d))));
+                sgn = _mm_or_pd(sgn, _mm_or_pd(_mm_or_pd(a, b), _mm_or_pd(c, d)));
+                const __m128i lo4 = _mm_unpacklo_epi64(ia, ib), hi4 = _mm_unpacklo_epi64(ic, id);   // 4 + 4 int32
+                bad = _mm_or_si128(bad, _mm_or_si128(lo4, hi4));
+                const __m128i p = _mm_packs_epi32(_mm_srai_epi32(_mm_slli_epi32(lo4, 16), 16), _mm_srai_epi32(_mm_slli_epi32(hi4, 16), 16));
+                _mm_stream_si128((__m128i*)(out + i), p);
+                if (negate) {
+                    _mm_storeu_pd(v + i, _mm_xor_pd(a, sign)); _mm_storeu_pd(v + i + 2, _mm_xor_pd(b, sign));
+                    _mm_storeu_pd(v + i + 4, _mm_xor_pd(c, sign)); _mm_storeu_pd(v + i + 6, _mm_xor_pd(d, sign));
+                }
+            }
+            _mm_sfence();
+            const bool range_ok = _mm_movemask_epi8(_mm_cmpeq_epi32(_mm_and_si128(bad, _mm_set1_epi32((int)0xFFFF0000u)), _mm_setzero_si128())) == 0xFFFF;
+            good = range_ok && _mm_movemask_pd(ok) == 3 && _mm_movemask_pd(sgn) == 0;
+        }
+#endif
+        for (; good && i < hi; ++i) {
+            const double x = v[i];
+            if (!(x >= 0.0 && x <= 65535.0)) { good = false; break; }
+            const uint16_t q = (uint16_t)x;
+            const double back = (double)q;
+            if (__builtin_memcmp(&back, &x, 8) != 0) { good = false; break; }
+            out[i] = q;
+            if (negate) v[i] = -x;
+        }
+        if (!good && negate) for (size_t j = lo; j < i; ++j) v[j] = -v[j];   // put the piece back as it was
+        return good;
+    }
+    // same for f32: bit-exact round trip
+    static bool narrow_f32(double* v, float* out, size_t lo, size_t hi, bool negate) {
+        size_t i = lo;
+        bool good = true;
+#if defined(__SSE2__)
+        if ((((uintptr_t)(out + lo)) & 15u) == 0) {
+            __m128i same = _mm_set1_epi32(-1);
+            const __m128d sign = _mm_set1_pd(-0.0);
+            for (; i + 4 <= hi; i += 4) {
+                const __m128d a = _mm_loadu_pd(v + i), b = _mm_loadu_pd(v + i + 2);
+                const __m128 fa = _mm_cvtpd_ps(a), fb = _mm_cvtpd_ps(b);
+                same = _mm_and_si128(same, _mm_and_si128(_mm_cmpeq_epi32(_mm_castpd_si128(_mm_cvtps_pd(fa)), _mm_castpd_si128(a)),
+                                                         _mm_cmpeq_epi32(_mm_castpd_si128(_mm_cvtps_pd(fb)), _mm_castpd_si128(b))));
+                _mm_stream_ps(out + i, _mm_movelh_ps(fa, fb));
+                if (negate) { _mm_storeu_pd(v + i, _mm_xor_pd(a, sign)); _mm_storeu_pd(v + i + 2, _mm_xor_pd(b, sign)); }
+            }
+            _mm_sfence();
+            good = _mm_movemask_epi8(same) == 0xFFFF;
+        }
+#endif
+        for (; good && i < hi; ++i) {
+            const double x = v[i];
+            const float q = (float)x;
+            const double back = (double)q;
+            if (__builtin_memcmp(&back, &x, 8) != 0) { good = false; break; }
+            out[i] = q;
+            if (negate) v[i] = -x;
+        }
+        if (!good && negate) for (size_t j = lo; j < i; ++j) v[j] = -v[j];   // put the piece back as it was
+        return good;
+    }
 
     void worker(int w) {
         cudaSetDevice(device);
         uint64_t seen = 0;
         while (true) {
-            double* v; size_t lo, hi; bool mine;
+            double* v; size_t lo, hi; bool mine; int md;
             {
                 std::unique_lock<std::mutex> lk(m);
                 cv_job.wait(lk, [&] { return stop || job_id != seen; });
                 if (stop) return;
                 seen = job_id;
-                mine = w < nchunks;
+                md = mode;
+                mine = md == NARROW ? w < narrow_workers : w < nchunks;
                 v = values;
                 lo = (size_t)w * chunk;
                 hi = lo + chunk < total ? lo + chunk : total;
             }
             if (!mine) continue;
-            cudaEventSynchronize(ev[w]);               // the DMA engine has finished reading this chunk
-            for (size_t i = lo; i < hi; ++i) v[i] = -v[i];
+            if (md == NARROW) {
+                while (!narrow_fail.load(std::memory_order_relaxed)) {
+                    const int pc = next_piece.fetch_add(1, std::memory_order_relaxed);
+                    if (pc >= npieces) break;
+                    const size_t plo = (size_t)pc * piece, phi = plo + piece < total ? plo + piece : total;
+                    const bool ok = tier == 2 ? narrow_u16(v, (uint16_t*)stage, plo, phi, narrow_negate)
+                                              : narrow_f32(v, (float*)stage, plo, phi, narrow_negate);
+                    if (!ok) { narrow_fail.store(1, std::memory_order_release); break; }
+                    done[pc].store(1, std::memory_order_release);
+                }
+            } else {
+                cudaEventSynchronize(ev[w]);               // the DMA engine has finished reading this chunk
+                for (size_t i = lo; i < hi; ++i) v[i] = -v[i];
+            }
             {
                 std::lock_guard<std::mutex> lk(m);
                 if (--pending == 0) cv_done.notify_all();
@@ -141,6 +244,14 @@ struct sla_ctx {
     size_t h_small_cap = 0;
     cudaEvent_t ev_small = nullptr;       // the last H2D copy out of h_small has completed
     bool small_pending = false;
+    // large uploads: values that survive a round trip through u16 / f32 cross PCIe narrow and are widened on the device
+    void* h_narrow = nullptr;             // page-locked staging (tier bytes per value)
+    size_t h_narrow_cap = 0;
+    void* d_narrow = nullptr;
+    size_t d_narrow_cap = 0;
+    int opt_narrow_upload = 1;
+    uint64_t last_upload_bytes = 0;       // bytes the last upload moved host -> device
+    uint32_t last_upload_value_bytes = 8; // 2 / 4 / 8: width the values crossed PCIe with
     unsigned char* h_dl = nullptr;        // small instances: results land here behind each graph launch (one sync per launch)
     size_t h_dl_cap = 0;
     DevState* h_state = nullptr;
@@ -1005,6 +1116,151 @@ int check_shape(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz
     return SLA_OK;
 }
 
+// Large uploads.  `values` first tries to cross PCIe narrow: when every value survives a round trip through u16
+// (non-negative integers below 65,536: the integer costs of the BASELINE configs) or through f32, the context's workers
+// stage the narrow copy piece by piece while the column indices are on the wire, the pieces follow them, and
+// widen_values_kernel restores the f64 array in HBM bit for bit (cfg3: 196 MB -> 100 MB over PCIe).  The first value
+// that does not survive ends the attempt; the f64 values then go up as they are.  With `negate` the caller's copy is
+// negated in place (solver.rs:214-216) by the same workers -- each piece right after it has been staged narrow (the
+// original values are then no longer needed on the host) or, chunk by chunk, behind the f64 copies; the pool is drained before the next solve /
+// upload / destroy call on this context returns.  The device always receives the ORIGINAL values.
+int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* row_ptr, const uint32_t* column_indices,
+                 double* values, uint64_t nnz, bool negate, int threads) {
+    const size_t total = (size_t)nnz;
+    const bool dbg = getenv("SLA_DEBUG_UPLOAD") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    double t_first = 0, t_half = 0;
+    ctx->last_upload_bytes = ((size_t)num_rows + 1) * 4 + total * 4;
+    ctx->last_upload_value_bytes = 8;
+    const bool want_pool = negate || (ctx->opt_narrow_upload && total >= ((size_t)1 << 20));
+    const bool pool_ok = want_pool && ctx->neg.start(ctx->device);
+    if (negate && !pool_ok) return fail(ctx, SLA_ERR_CUDA, "could not start the host negation workers");
+    NegPool& np = ctx->neg;
+    if (threads < 1) {
+        // default: the cores of the box divided by the ranks torchrun co-located on it
+        unsigned hw = std::thread::hardware_concurrency();
+        int lw = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) lw = atoi(e) > 0 ? atoi(e) : 1;
+        threads = (int)(hw ? hw : 4) / lw;
+        if (const char* e = getenv("SLA_HOST_THREADS")) threads = atoi(e);
+        if (threads < 1) threads = 1;
+    }
+    if (pool_ok && threads > (int)np.threads.size()) threads = (int)np.threads.size();
+
+    // ---- tier: what do the first values look like? ---------------------------------------------------------------
+    int tier = 0;
+    if (ctx->opt_narrow_upload && pool_ok && total >= ((size_t)1 << 20)) {
+        const size_t probe = 4096;
+        std::vector<uint16_t> t16(probe);
+        std::vector<float> t32(probe);
+        if (NegPool::narrow_u16(values, t16.data(), 0, probe, false)) tier = 2;
+        else if (NegPool::narrow_f32(values, t32.data(), 0, probe, false)) tier = 4;
+    }
+    if (tier) {
+        const size_t need = total * (size_t)tier;
+        if (need > ctx->h_narrow_cap) {
+            if (ctx->h_narrow) { cudaFreeHost(ctx->h_narrow); ctx->h_narrow = nullptr; ctx->h_narrow_cap = 0; }
+            if (cudaMallocHost(&ctx->h_narrow, need) == cudaSuccess) ctx->h_narrow_cap = need; else { cudaGetLastError(); tier = 0; }
+        }
+        if (tier && need > ctx->d_narrow_cap) {
+            if (ctx->d_narrow) { cudaFree(ctx->d_narrow); ctx->d_narrow = nullptr; ctx->d_narrow_cap = 0; }
+            if (cudaMalloc(&ctx->d_narrow, need) == cudaSuccess) ctx->d_narrow_cap = need; else { cudaGetLastError(); tier = 0; }
+        }
+    }
+
+    CU(cudaMemcpyAsync(ctx->d_cols, column_indices, total * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+
+    bool narrowed = false;
+    if (tier) {
+        size_t piece = (size_t)1 << 16;                                    // 64 Ki values: 128 / 256 KB per copy
+        while ((total + piece - 1) / piece > (size_t)NegPool::kMaxPieces) piece <<= 1;
+        const int npieces = (int)((total + piece - 1) / piece);
+        {
+            std::lock_guard<std::mutex> lk(np.m);
+            np.mode = NegPool::NARROW;
+            np.values = values; np.total = total; np.stage = ctx->h_narrow; np.tier = tier; np.piece = piece; np.npieces = npieces;
+            np.next_piece.store(0); np.narrow_fail.store(0);
+            for (int q = 0; q < npieces; ++q) np.done[q].store(0, std::memory_order_relaxed);
+            np.narrow_workers = threads;
+            np.narrow_negate = negate;
+            np.pending = threads;
+            np.job_id += 1;
+        }
+        np.cv_job.notify_all();
+        // pieces follow the column indices over PCIe in array order, each as soon as it is staged
+        int sent = 0;
+        constexpr int kMinRun = 16;
+        cudaError_t ce = cudaSuccess;
+        while (sent < npieces && ce == cudaSuccess) {
+            if (np.done[sent].load(std::memory_order_acquire)) {
+                int run = 1;                                              // one copy for every run of staged neighbours
+                while (sent + run < npieces && np.done[sent + run].load(std::memory_order_acquire)) run += 1;
+                if (run < kMinRun && sent + run < npieces) { std::this_thread::yield(); continue; }   // copies of >= 2 MB
+                const size_t lo = (size_t)sent * piece, end = (size_t)(sent + run) * piece, hi = end < total ? end : total;
+                ce = cudaMemcpyAsync((char*)ctx->d_narrow + lo * tier, (const char*)ctx->h_narrow + lo * tier, (hi - lo) * tier,
+                                     cudaMemcpyHostToDevice, ctx->stream);
+                if (dbg && sent == 0) t_first = ms_since();
+                if (dbg && sent < npieces / 2 && sent + run >= npieces / 2) t_half = ms_since();
+                sent += run;
+            } else if (np.narrow_fail.load(std::memory_order_acquire)) {
+                break;
+            } else {
+                std::this_thread::yield();
+            }
+        }
+        if (dbg) fprintf(stderr, "[sla] narrow tier %d: first piece sent %.3f ms, half %.3f ms, all %.3f ms\n", tier, t_first, t_half, ms_since());
+        np.wait();                                                        // the staging pass is over (or was abandoned)
+        if (ce != cudaSuccess) return fail(ctx, SLA_ERR_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(ce));
+        narrowed = sent == npieces && !np.narrow_fail.load();
+        if (!narrowed && negate) {
+            // abandoned late: the pieces staged so far were already negated in place -- restore them, the f64 path below
+            // needs the original values on the host
+            for (int q = 0; q < npieces; ++q)
+                if (np.done[q].load(std::memory_order_acquire)) {
+                    const size_t lo = (size_t)q * piece, hi = lo + piece < total ? lo + piece : total;
+                    for (size_t i = lo; i < hi; ++i) values[i] = -values[i];
+                }
+        }
+    }
+
+    if (narrowed) {
+        const int grid = ctx->num_sms * 8;
+        if (tier == 2) widen_values_kernel<uint16_t><<<grid, kWideThreads, 0, ctx->stream>>>((const uint16_t*)ctx->d_narrow, ctx->d_vals, total);
+        else           widen_values_kernel<float><<<grid, kWideThreads, 0, ctx->stream>>>((const float*)ctx->d_narrow, ctx->d_vals, total);
+        ctx->last_upload_bytes += total * (size_t)tier;
+        ctx->last_upload_value_bytes = (uint32_t)tier;
+        // (with `negate` every piece was negated in place right after it was staged)
+    } else if (negate) {
+        // f64 values, chunk by chunk, each chunk followed by its event; worker w negates chunk w behind its copy
+        size_t per = (total + (size_t)threads - 1) / (size_t)threads;
+        per = (per + 511) & ~(size_t)511;                       // whole 4 KB pieces per worker
+        const int nchunks = (int)((total + per - 1) / per);
+        for (int w = 0; w < nchunks; ++w) {
+            const size_t lo = (size_t)w * per, hi = lo + per < total ? lo + per : total;
+            CU(cudaMemcpyAsync(ctx->d_vals + lo, values + lo, (hi - lo) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaEventRecord(np.ev[w], ctx->stream));
+        }
+        {
+            std::lock_guard<std::mutex> lk(np.m);
+            np.mode = NegPool::NEGATE_AFTER_COPY;
+            np.values = values; np.chunk = per; np.total = total; np.nchunks = nchunks; np.pending = nchunks;
+            np.job_id += 1;
+        }
+        np.cv_job.notify_all();
+        ctx->last_upload_bytes += total * 8;
+    } else {
+        CU(cudaMemcpyAsync(ctx->d_vals, values, total * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->last_upload_bytes += total * 8;
+    }
+    if (dbg) fprintf(stderr, "[sla] upload enqueued at %.3f ms\n", ms_since());
+    int rc = finish_csr(ctx, num_rows, num_cols, nnz);
+    if (dbg) fprintf(stderr, "[sla] upload complete (statistics read back) at %.3f ms\n", ms_since());
+    if (rc) join_workers(ctx);
+    return rc;
+}
+
 }  // namespace
 
 // =============================================================================================================
@@ -1119,6 +1375,8 @@ void sla_ctx_destroy(sla_ctx* ctx) {
     cudaFree(ctx->d_csr_stats); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->h_dl) cudaFreeHost(ctx->h_dl);
+    if (ctx->h_narrow) cudaFreeHost(ctx->h_narrow);
+    if (ctx->d_narrow) cudaFree(ctx->d_narrow);
     if (ctx->ev_small) cudaEventDestroy(ctx->ev_small);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_csr_stats) cudaFreeHost(ctx->h_csr_stats);
@@ -1165,6 +1423,8 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
         ctx->opt_l2_persist = value ? 1 : 0;
         drop_graphs(ctx);
         apply_l2_policy(ctx);
+    } else if (k == "narrow_upload") {
+        ctx->opt_narrow_upload = value ? 1 : 0;
     } else if (k == "small_path") {
         ctx->opt_small_path = value ? 1 : 0;
     } else if (k == "wide_first") {
@@ -1190,20 +1450,20 @@ int sla_upload_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uin
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
-    if (ctx->opt_small_path && small_csr(num_rows, nnz))
+    if (ctx->opt_small_path && small_csr(num_rows, nnz)) {
+        ctx->last_upload_bytes = ((size_t)num_rows + 1) * 4 + (size_t)nnz * 12;
+        ctx->last_upload_value_bytes = 8;
         return upload_small(ctx, num_rows, num_cols, row_ptr, column_indices, const_cast<double*>(values), nnz, false);
-    CU(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_cols, column_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_vals, values, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
-    return finish_csr(ctx, num_rows, num_cols, nnz);
+    }
+    return upload_large(ctx, num_rows, num_cols, row_ptr, column_indices, const_cast<double*>(values), nnz, false, 0);
 }
 
 // Same as sla_upload_csr, plus the in-place sign normalisation of AuctionSolver::init_solve (reference
-// src/solver.rs:214-216) on the HOST values: `values` is uploaded first, chunk by chunk; the context's worker pool
-// negates chunk w as soon as the copy of chunk w has completed, while the column indices are still crossing PCIe and
-// the solve runs.  The pool is drained before the next solve / upload / destroy call on this context returns, so the
-// caller observes the negated values when solve() returns -- exactly the reference's post-condition.  The device holds the ORIGINAL values
-// (the following solve reports values_negated == 1 as usual; the host must then not negate again).
+// src/solver.rs:214-216) on the HOST values, done by the context's workers while the upload and the solve run (small
+// instances: in the staging pass).  The pool is drained before the next solve / upload / destroy call on this context
+// returns, so the caller observes the negated values when solve() returns -- exactly the reference's post-condition.
+// The device holds the ORIGINAL values (the following solve reports values_negated == 1 as usual; the host must then
+// not negate again).
 int sla_upload_csr_negating(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* row_ptr,
                             const uint32_t* column_indices, double* values, uint64_t nnz, int threads) {
     if (!ctx) return SLA_ERR_INVALID;
@@ -1213,33 +1473,20 @@ int sla_upload_csr_negating(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, 
     if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
-    if (ctx->opt_small_path && small_csr(num_rows, nnz))
+    if (ctx->opt_small_path && small_csr(num_rows, nnz)) {
+        ctx->last_upload_bytes = ((size_t)num_rows + 1) * 4 + (size_t)nnz * 12;
+        ctx->last_upload_value_bytes = 8;
         return upload_small(ctx, num_rows, num_cols, row_ptr, column_indices, values, nnz, true);
-    if (!ctx->neg.start(ctx->device)) return fail(ctx, SLA_ERR_CUDA, "could not start the host negation workers");
-    NegPool& np = ctx->neg;
-    if (threads < 1) threads = 1;
-    if (threads > (int)np.threads.size()) threads = (int)np.threads.size();
-    const size_t total = (size_t)nnz;
-    size_t per = (total + (size_t)threads - 1) / (size_t)threads;
-    per = (per + 511) & ~(size_t)511;                       // whole 4 KB pieces per worker
-    const int nchunks = (int)((total + per - 1) / per);
-    // `values` crosses PCIe first, chunk by chunk, each chunk followed by its event
-    for (int w = 0; w < nchunks; ++w) {
-        const size_t lo = (size_t)w * per, hi = lo + per < total ? lo + per : total;
-        CU(cudaMemcpyAsync(ctx->d_vals + lo, values + lo, (hi - lo) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaEventRecord(np.ev[w], ctx->stream));
     }
-    CU(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_cols, column_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-    {
-        std::lock_guard<std::mutex> lk(np.m);
-        np.values = values; np.chunk = per; np.total = total; np.nchunks = nchunks; np.pending = nchunks;
-        np.job_id += 1;
-    }
-    np.cv_job.notify_all();
-    rc = finish_csr(ctx, num_rows, num_cols, nnz);
-    if (rc) join_workers(ctx);
-    return rc;
+    return upload_large(ctx, num_rows, num_cols, row_ptr, column_indices, values, nnz, true, threads);
+}
+
+// Bytes the last upload moved from host to device and the width (2 / 4 / 8) the values crossed PCIe with.
+int sla_last_upload(const sla_ctx* ctx, uint64_t* bytes, uint32_t* value_bytes) {
+    if (!ctx) return SLA_ERR_INVALID;
+    if (bytes) *bytes = ctx->last_upload_bytes;
+    if (value_bytes) *value_bytes = ctx->last_upload_value_bytes;
+    return SLA_OK;
 }
 
 int sla_upload_csr_device(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* d_row_ptr,

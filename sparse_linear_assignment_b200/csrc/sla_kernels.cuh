@@ -155,6 +155,26 @@ __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t
     // arcs of a regular round = bidders * K: accounted in control step A
 }
 
+// Values that crossed PCIe as u16 / f32 (upload_large): restore the f64 array, 8 values per thread and pass.
+template <class T>
+__global__ void __launch_bounds__(kWideThreads) widen_values_kernel(const T* __restrict__ src, double* __restrict__ dst,
+                                                                    const size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 8u;
+    for (size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8u; g < n; g += stride) {
+        if (g + 8u <= n) {
+            T t[8];
+            if (sizeof(T) == 2) *reinterpret_cast<uint4*>(t) = *reinterpret_cast<const uint4*>(src + g);
+            else { *reinterpret_cast<uint4*>(t) = *reinterpret_cast<const uint4*>(src + g);
+                   *reinterpret_cast<uint4*>(t + 4) = *reinterpret_cast<const uint4*>(src + g + 4); }
+#pragma unroll
+            for (int u = 0; u < 8; u += 2)
+                *reinterpret_cast<double2*>(dst + g + u) = make_double2((double)t[u], (double)t[u + 1]);
+        } else {
+            for (size_t u = g; u < n; ++u) dst[u] = (double)src[u];
+        }
+    }
+}
+
 // Empty kernel: the "profile" mode launches it in front of an event so that the event is recorded by the compute
 // front-end right before the kernel it times (and not behind the copy engine's upload of the control block).
 __global__ void profile_fence_kernel() {}

@@ -401,6 +401,13 @@ class AuctionSolver:
         """The context's cudaStream_t as an integer (for torch.cuda.ExternalStream / event timing)."""
         return int(_lib.load().sla_ctx_stream(self._context()) or 0)
 
+    def last_upload(self) -> Tuple[int, int]:
+        """(bytes the last upload moved host -> device, bytes per value on the wire: 2, 4 or 8)."""
+        ctx = self._context()
+        b, w = C.c_uint64(), C.c_uint32()
+        _lib.check(ctx, _lib.load().sla_last_upload(ctx, C.byref(b), C.byref(w)))
+        return int(b.value), int(w.value)
+
     def set_option(self, key: str, value: int) -> None:
         ctx = self._context()
         _lib.check(ctx, _lib.load().sla_set_option(ctx, key.encode(), int(value)))

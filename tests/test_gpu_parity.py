@@ -253,6 +253,46 @@ def test_small_instance_path_equals_device_statistics_path(sla, oracle, kind, cl
             assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v.copy(), maximize=maximize)
 
 
+@pytest.mark.parametrize("flavour", ["u16", "f32", "u16_then_fraction", "f64", "negative_ints", "minus_zero"])
+def test_narrow_upload_is_lossless(sla, oracle, flavour):
+    """Large uploads whose values survive a round trip through u16 / f32 cross PCIe narrow and are widened in HBM
+    (sla_last_upload reports the width); anything else goes up as f64 -- also when the first non-representable value
+    sits late in the array.  Either way the device sees the original bits: results equal those with narrow_upload = 0,
+    and the caller's values end up negated in place exactly once."""
+    rng = np.random.default_rng(5)
+    n, m, k = 70_000, 200_000, 16                                   # 1.12 M arcs: above the narrowing threshold
+    rp, c, v = sla.generators.kregular_host(n, m, k, seed=9)
+    v = v.astype(np.float64)
+    expect = {"u16": 2, "f32": 4, "u16_then_fraction": 8, "f64": 8, "negative_ints": 4, "minus_zero": 4}[flavour]
+    if flavour == "f32":
+        v = v + 0.5
+    elif flavour == "u16_then_fraction":
+        v[-12345] += 0.1                                            # passes the probe, fails u16 (and f32) late
+    elif flavour == "f64":
+        v = v + rng.uniform(0.0, 1.0, size=v.size)
+    elif flavour == "negative_ints":
+        v = -v                                                      # negative: not u16, exact in f32
+    elif flavour == "minus_zero":
+        v[5::97] = -0.0                                             # the sign of zero must survive: f32 keeps it
+    out = []
+    for narrow in (1, 0):
+        solver, z = sla.KhoslaSolver.new(n, m, n * k)
+        solver.set_option("narrow_upload", narrow)
+        solver.load_csr(n, m, rp, c, v.copy())
+        maximize = flavour == "negative_ints"                       # both cases need the sign flip (host negation)
+        solver.solve(z, maximize, None)
+        nbytes, width = solver.last_upload()
+        assert width == (expect if narrow else 8), (flavour, narrow, width)
+        assert nbytes == 4 * (n + 1) + 4 * n * k + width * n * k
+        assert solver.last_stats["values_negated"] == 1
+        assert np.array_equal(solver.values(), -v)                  # negated in place, exactly once
+        out.append((z.person_to_object.copy(), z.object_to_person.copy(), solver.prices().copy(),
+                    {q: solver.last_stats[q] for q in ("rounds", "bids", "bid_arcs", "num_unassigned", "eps")}))
+    for x, y in zip(out[0][:3], out[1][:3]):
+        assert np.array_equal(x, y)
+    assert out[0][3] == out[1][3]
+
+
 @pytest.mark.parametrize("kind,cls_name", SOLVERS)
 def test_u16_index_type(sla, oracle, kind, cls_name):
     rng = np.random.default_rng(3)
