@@ -479,6 +479,20 @@ def main_ours(args):
                 if prof:
                     rec = prof[0]
                     ts.append(rec["bid_ms"])
+            # the same bracket around 8 back-to-back launches of the (idempotent) scan: the bracket itself -- event, launch
+            # latency of a host-launched kernel, event -- costs several microseconds that the graph-launched solve does
+            # not pay; reported beside the single-launch figure, which stays the headline
+            b2b = None
+            if skip and rec:
+                resident.set_option("profile_repeat", 8)
+                tb = []
+                for _ in range(5):
+                    resident.solve_resident(False, eps)
+                    prof = [p for p in resident.round_profile() if p["engine"] == 0]
+                    if prof:
+                        tb.append(prof[0]["bid_ms"] / 8.0)
+                resident.set_option("profile_repeat", 1)
+                b2b = sorted(tb)[len(tb) // 2] if tb else None
             resident.set_option("profile", 0)
             resident.set_option("zero_price_skip", 1)
             if rec:
@@ -490,6 +504,9 @@ def main_ours(args):
                              "traffic": ncu_traffic(kname), "kernel": kname, "launch": "round 1 (all persons bid)",
                              "bidders": rec["bidders"], "arcs": rec["arcs"], "algorithmic_bytes": alg,
                              "launch_us": t_ms * 1e3, "peak_source": peak_src}
+                if b2b:
+                    roof[key]["launch_us_back_to_back"] = b2b * 1e3
+                    roof[key]["frac_back_to_back"] = alg / (b2b * 1e-3) / 1e9 / peak
         whole = (12 * stats["bid_arcs"] + 8 * stats["bids"]) / (stats["ms_solve"] * 1e-3) / 1e9
 
         cpu = None

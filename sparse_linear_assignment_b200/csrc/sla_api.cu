@@ -746,8 +746,10 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
     const size_t dl_prices = dl_o2p + (h_o2p ? (((size_t)M * 4 + 15) & ~(size_t)15) : 0);
     const size_t dl_bytes = dl_prices + (h_prices ? (size_t)M * 8 : 0);
     constexpr size_t kSmallDownloadBytes = (size_t)1 << 20;
-    const bool small_dl = use_graph && ctx->opt_small_path && dl_bytes > 0 && dl_bytes <= kSmallDownloadBytes;
-    if (small_dl && !ctx->h_dl) {
+    // also with nothing to download (resident solves): the events are then recorded behind the graph launch and the
+    // poll of the control block is the only synchronisation of the solve
+    const bool small_dl = use_graph && ctx->opt_small_path && dl_bytes <= kSmallDownloadBytes;
+    if (small_dl && dl_bytes > 0 && !ctx->h_dl) {
         CU(cudaMallocHost((void**)&ctx->h_dl, kSmallDownloadBytes));
         ctx->h_dl_cap = kSmallDownloadBytes;
     }
@@ -799,7 +801,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
             launch_one(ctx, p, 0, first && ctx->opt_skip_zero != 0);
             // "profile_repeat" (development): the scan is idempotent (same slots, same maxima), so it can be launched
             // several times between the two events to separate its duration from the event overhead
-            if (ctx->opt_profile && wide)
+            if (ctx->opt_profile && wide && first)
                 for (int r = 1; r < ctx->opt_profile_repeat; ++r) launch_one(ctx, p, 0, first && ctx->opt_skip_zero != 0);
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
             const bool late_now = first && late_init;
