@@ -44,6 +44,9 @@ extern "C" {
     pub fn sla_host_negate_f64(values: *mut f64, n: usize, threads: c_int);
     pub fn sla_upload_csr(ctx: *mut sla_ctx, num_rows: u32, num_cols: u32, row_ptr: *const u32,
                           column_indices: *const u32, values: *const f64, nnz: u64) -> c_int;
+    pub fn sla_upload_csr_negating(ctx: *mut sla_ctx, num_rows: u32, num_cols: u32, row_ptr: *const u32,
+                                   column_indices: *const u32, values: *mut f64, nnz: u64, threads: c_int) -> c_int;
+    pub fn sla_last_upload(ctx: *const sla_ctx, bytes: *mut u64, value_bytes: *mut u32) -> c_int;
     pub fn sla_khosla_solve(ctx: *mut sla_ctx, maximize: c_int, eps: f64, person_to_object: *mut u32,
                             object_to_person: *mut u32, prices: *mut f64, stats: *mut sla_stats) -> c_int;
     pub fn sla_forward_solve(ctx: *mut sla_ctx, maximize: c_int, eps: f64, start_eps: f64, max_iterations: u32,
