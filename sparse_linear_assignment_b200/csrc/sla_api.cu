@@ -36,6 +36,7 @@ struct GraphSlot {
     uint32_t tail_smem_bytes = 0;
     uint32_t tail_max = 0;
     bool khosla_phases = false;
+    size_t l2_bytes = 0;
 };
 
 }  // namespace
@@ -271,7 +272,9 @@ struct sla_ctx {
     int opt_regular = 1;
     int opt_small_path = 1;    // small instances: host-side statistics on the way up, results behind the graph on the way down
     int opt_wide_first = 1;    // first round of a small plain-Khosla solve on the wide kernels (solve_tail_max)
-    int opt_l2_persist = 0;    // development: access-policy window (persisting) over the bid words
+    int opt_l2_persist = 1;    // access-policy window (persisting) over the bid words when they fit the carve-out
+    bool l2_active = false;    // this context holds a share of the device's persisting-L2 carve-out
+    size_t l2_bytes = 0;       // window size the stream attribute / captured graphs were set up with
     size_t l2_persist_max = 0, l2_window_max = 0;
     int opt_stream_scan = 0;   // first-round scan through the TMA pipeline (bid_stream_kernel): opt-in, measured 4 % slower
     int opt_smem_prices = 1, opt_smem_owners = 1, opt_khosla_scaling = 1;
@@ -443,7 +446,7 @@ void launch_one_t(sla_ctx* c, const Params& p, int which, bool zero_first) {
                 bid_wide_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
             }
             break;
-        case 1: assign_wide_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 1: assign_wide_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p, zero_first ? 1 : 0); break;
         case 2:
             if (c->tail_smem_prices) tail_kernel<LPR, true><<<1, kTailThreads, c->tail_smem_bytes, c->stream>>>(p);
             else tail_kernel<LPR, false><<<1, kTailThreads, c->tail_smem_bytes, c->stream>>>(p);
@@ -473,8 +476,8 @@ void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_fir
     if (!tail_only) {
         launch_one(c, p, 0, zero_first);
         // first round with all prices zero: prices / owners / assignment are initialised behind the scan
-        if (zero_first) init_solve_late_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
-        launch_one(c, p, 1);
+        if (zero_first) first_assign_objects_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
+        launch_one(c, p, 1, zero_first);
     }
     launch_one(c, p, 2);
     if (forward) {
@@ -511,27 +514,59 @@ int super_rounds_for(const sla_ctx* c, bool forward) {
     return c->opt_super_rounds;
 }
 
-// Development option "l2_persist": mark the bid words (8 B per object, RED.MAX target of every bid) as persisting in
-// the L2 (set-aside carve-out + access-policy window on the stream and on the captured kernel nodes).
+// The bid words (8 B per object) are the RED.MAX target of every bid and are swept once by the first-round object
+// pass, while 12 B per arc of CSR stream past them: when they are too large to survive that stream in the L2 by
+// themselves but small enough for the set-aside carve-out (8 MB .. persistingL2CacheMaxSize, i.e. 1 M .. 9.9 M objects on
+// B200), they are marked persisting (access-policy window on the stream and on the captured kernel nodes).  cfg3: bid
+// scan 49 -> 42 us, first-round assignment 36 -> 32 us, solve 0.203 -> 0.195 ms.  The carve-out is a device-wide
+// setting: it is raised only as far as needed, and the last context that used it on a device restores the previous
+// limit and resets the persisting lines.  Option "l2_persist" = 0 turns it off.
+std::mutex g_l2_mutex;
+int g_l2_users[64] = {};
+size_t g_l2_prev_limit[64] = {};
+
 bool l2_window(const sla_ctx* c, cudaAccessPolicyWindow* w) {
     if (!c->opt_l2_persist || !c->d_best || !c->l2_persist_max || !c->l2_window_max || !c->has_csr) return false;
-    size_t bytes = (size_t)c->n_cols * 8u;
-    if (bytes > c->l2_window_max) bytes = c->l2_window_max;
-    const size_t aside = bytes < c->l2_persist_max ? bytes : c->l2_persist_max;
+    const size_t bytes = (size_t)c->n_cols * 8u;
+    if (bytes < ((size_t)8 << 20) || bytes > c->l2_persist_max || bytes > c->l2_window_max) return false;
     w->base_ptr = c->d_best;
     w->num_bytes = bytes;
-    w->hitRatio = (float)((double)aside / (double)bytes);
+    w->hitRatio = 1.0f;
     w->hitProp = cudaAccessPropertyPersisting;
     w->missProp = cudaAccessPropertyNormal;
     return true;
 }
+
+void release_l2_policy(sla_ctx* c) {
+    if (!c->l2_active) return;
+    c->l2_active = false;
+    std::lock_guard<std::mutex> lk(g_l2_mutex);
+    const int d = c->device & 63;
+    if (--g_l2_users[d] == 0) {
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, g_l2_prev_limit[d]);
+        cudaGetLastError();
+    }
+}
+
+// Called whenever the instance (n_cols), the buffers or the option change.
 void apply_l2_policy(sla_ctx* c) {
     cudaStreamAttrValue v;
     memset(&v, 0, sizeof v);
     if (l2_window(c, &v.accessPolicyWindow)) {
-        const size_t aside = v.accessPolicyWindow.num_bytes < c->l2_persist_max ? v.accessPolicyWindow.num_bytes : c->l2_persist_max;
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, aside);
+        std::lock_guard<std::mutex> lk(g_l2_mutex);
+        const int d = c->device & 63;
+        size_t cur = 0;
+        cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+        if (!c->l2_active) {
+            if (g_l2_users[d]++ == 0) g_l2_prev_limit[d] = cur;
+            c->l2_active = true;
+        }
+        if (cur < v.accessPolicyWindow.num_bytes) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, v.accessPolicyWindow.num_bytes);
+        c->l2_bytes = v.accessPolicyWindow.num_bytes;
     } else {
+        release_l2_policy(c);
+        c->l2_bytes = 0;
         v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
         v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     }
@@ -546,7 +581,8 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     const int n_super = super_rounds_for(ctx, forward);
     if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == n_super &&
         g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices && g.tail_only == tail_only &&
-        g.tail_smem_bytes == ctx->tail_smem_bytes && g.tail_max == solve_tail_max(ctx, forward) && g.khosla_phases == khosla_phases(ctx)) {
+        g.tail_smem_bytes == ctx->tail_smem_bytes && g.tail_max == solve_tail_max(ctx, forward) && g.khosla_phases == khosla_phases(ctx) &&
+        g.l2_bytes == ctx->l2_bytes) {
         *out = g.exec;
         return SLA_OK;
     }
@@ -588,6 +624,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     g.tail_smem_bytes = ctx->tail_smem_bytes;
     g.tail_max = solve_tail_max(ctx, forward);
     g.khosla_phases = khosla_phases(ctx);
+    g.l2_bytes = ctx->l2_bytes;
     *out = g.exec;
     return SLA_OK;
 }
@@ -806,12 +843,11 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
             const bool late_now = first && late_init;
             if (late_now) {
-                init_solve_late_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p);
+                first_assign_objects_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p);
                 launches += 1;
-                if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[4], ctx->stream));   // assign time excludes the init
             }
             first = false;
-            launch_one(ctx, p, 1);
+            launch_one(ctx, p, 1, late_now);
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
             launches += 2;
             if (ctx->opt_profile) {
@@ -826,7 +862,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
                     r.rounds_covered = 1;
                     r.arcs = prev.regular_k ? (uint64_t)r.bidders * prev.regular_k : ctx->h_state->bid_arcs - prev.bid_arcs;
                     cudaEventElapsedTime(&r.bid_ms, ctx->ev[1], ctx->ev[2]);
-                    cudaEventElapsedTime(&r.assign_ms, late_now ? ctx->ev[4] : ctx->ev[2], ctx->ev[3]);
+                    cudaEventElapsedTime(&r.assign_ms, ctx->ev[2], ctx->ev[3]);   // first round: object pass + person pass
                     ctx->profile.push_back(r);
                 }
                 CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -949,6 +985,7 @@ int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz)
     ctx->has_csr = true;
     ctx->has_solution = false;
     plan_tail(ctx);
+    apply_l2_policy(ctx);
     return SLA_OK;
 }
 
@@ -1105,6 +1142,7 @@ int upload_small(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
     ctx->has_csr = true;
     ctx->has_solution = false;
     plan_tail(ctx);
+    apply_l2_policy(ctx);
     return SLA_OK;
 }
 
@@ -1368,6 +1406,7 @@ void sla_ctx_destroy(sla_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->neg.shutdown();
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    release_l2_policy(ctx);
     sla_batch_free(ctx);
     sla_part_free(ctx);
     drop_graphs(ctx);

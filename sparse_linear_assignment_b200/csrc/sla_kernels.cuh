@@ -351,7 +351,11 @@ constexpr int kAssignChunk = 2048;   // queue slots one block stages before it r
 #endif
 constexpr int kAssignUnroll = SLA_ASSIGN_UNROLL;   // slots per thread whose dependent loads are issued together
 
-__global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params p) {
+// `first` = 1: first round of a solve behind first_assign_objects_kernel -- the objects have already installed their
+// winners (price, owner, cleared word), so a bidder only has to look up whether it is the owner of its object: it
+// records the match or goes back into the queue.  Every person is a bidder in that round, so this pass also is the
+// initialisation of person_to_object.
+__global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params p, const int first) {
     DevState* st = p.st;
     const HotState h = load_hot(st);
     const uint32_t cur = h.cur;
@@ -395,14 +399,24 @@ __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params 
             for (int u = 0; u < kAssignUnroll; ++u) {
                 word[u] = 0ull; prev[u] = SLA_DEV_NONE;
                 if (j[u] != SLA_DEV_NONE) {
-                    word[u] = __ldcg(p.best + j[u]);
-                    if (!nobody_owns) prev[u] = __ldcg(p.o2p + j[u]);   // speculative: only the winner uses it
+                    if (first) prev[u] = __ldcg(p.o2p + j[u]);          // the owner the object pass installed
+                    else {
+                        word[u] = __ldcg(p.best + j[u]);
+                        if (!nobody_owns) prev[u] = __ldcg(p.o2p + j[u]);   // speculative: only the winner uses it
+                    }
                 }
             }
 #pragma unroll
             for (int u = 0; u < kAssignUnroll; ++u) {
                 uint32_t emit = SLA_DEV_NONE;
-                if (j[u] != SLA_DEV_NONE) {
+                if (first) {
+                    const uint32_t q = t0 + u * kWideThreads + threadIdx.x;
+                    if (q < stop) {
+                        const bool won = j[u] != SLA_DEV_NONE && prev[u] == i[u];
+                        p.p2o[i[u]] = won ? j[u] : SLA_DEV_NONE;
+                        if (!won && j[u] != SLA_DEV_NONE) emit = i[u];      // dropped persons (no object) leave the auction
+                    }
+                } else if (j[u] != SLA_DEV_NONE) {
                     const bool won = (bid[u] == bid[u]) && (word[u] == pack_bid(bid[u], i[u], pbits));
                     if (won) {
                         p.prices[j[u]] = bid[u];
@@ -1047,6 +1061,39 @@ __global__ void __launch_bounds__(kWideThreads) init_solve_late_kernel(const Par
         p.o2p[j] = SLA_DEV_NONE;
     }
     for (uint32_t i = tid; i < h.n_rows; i += stride) p.p2o[i] = SLA_DEV_NONE;
+}
+
+// First round of a solve, object side (replaces init_solve_late_kernel + the object half of assign_wide_kernel when the
+// first scan ran with all prices zero): one coalesced sweep over the objects.  An object whose bid word is set takes
+// the exact f64 bid of the person the word elected (first round: slot index == person) as its price, records that
+// person as its owner and clears the word; every other object gets price 0 and no owner (solver.rs:218-229).  All
+// stores are coalesced; the only scattered access is the winner's 8-byte bid, still in the L2 behind the scan.
+__global__ void __launch_bounds__(kWideThreads) first_assign_objects_kernel(const Params p) {
+    const HotState h = load_hot(p.st);
+    if (h.done) return;
+    const uint32_t M = h.n_cols;
+    const unsigned long long pmask = (1ull << h.pbits) - 1ull;
+    const uint32_t base = h.person_base;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    const uint32_t pairs = M / 2u;
+    for (uint32_t t = tid; t < pairs; t += stride) {
+        const ulonglong2 w = __ldcg(reinterpret_cast<const ulonglong2*>(p.best) + t);
+        double2 pr = make_double2(0.0, 0.0);
+        uint2 ow = make_uint2(SLA_DEV_NONE, SLA_DEV_NONE);
+        if (w.x) { ow.x = (uint32_t)(pmask - (w.x & pmask)) - base; pr.x = __ldcg(p.slot_bid + ow.x); }
+        if (w.y) { ow.y = (uint32_t)(pmask - (w.y & pmask)) - base; pr.y = __ldcg(p.slot_bid + ow.y); }
+        reinterpret_cast<double2*>(p.prices)[t] = pr;
+        reinterpret_cast<uint2*>(p.o2p)[t] = ow;
+        if (w.x | w.y) reinterpret_cast<ulonglong2*>(p.best)[t] = make_ulonglong2(0ull, 0ull);
+    }
+    if (tid == 0 && (M & 1u)) {
+        const uint32_t j = M - 1u;
+        const unsigned long long w = __ldcg(p.best + j);
+        if (w) {
+            const uint32_t i = (uint32_t)(pmask - (w & pmask)) - base;
+            p.prices[j] = __ldcg(p.slot_bid + i); p.o2p[j] = i; p.best[j] = 0ull;
+        } else { p.prices[j] = 0.0; p.o2p[j] = SLA_DEV_NONE; }
+    }
 }
 
 // Value range + structural validation of an uploaded CSR (ksparse.rs:171-179, symmetric.rs:246, solver.rs:241).
