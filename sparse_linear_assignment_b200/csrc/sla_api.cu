@@ -824,7 +824,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
                 CU(cudaEventRecord(ctx->ev[2], ctx->stream));
             }
             launches += (uint32_t)(super_rounds_for(ctx, forward) * kernels_per_super_round(ctx, forward, is_tail_only(ctx, forward)));
-            if (late_init && graph_launches == 1) launches += 1;   // init_solve_late_kernel sits in the first graph
+            if (late_init && graph_launches == 1) launches += 1;   // first_assign_objects_kernel sits in the first graph
             if ((rc = poll_state(ctx))) return rc;
             done = ctx->h_state->done != 0;
             if (!done && timed_out()) return fail(ctx, SLA_ERR_STATE, "solve exceeded the wall-clock guard (timeout_s)");

@@ -1048,23 +1048,8 @@ __global__ void __launch_bounds__(kWideThreads) init_solve_kernel(const Params p
     for (uint32_t i = tid; i < n_rows; i += stride) p.p2o[i] = SLA_DEV_NONE;
 }
 
-// Same, placed BEHIND the first bid scan of a solve (sizes from the control block so that it can live in a captured
-// graph).  In PRICE_ZERO mode the first scan reads neither prices nor owners, so running the initialisation after it
-// keeps 52 MB (cfg3) of dirty lines out of the L2 while the scan streams, and hands them to the assign kernel hot.
-// The bid words are never touched here: the scan has just deposited its maxima in them.
-__global__ void __launch_bounds__(kWideThreads) init_solve_late_kernel(const Params p) {
-    const HotState h = load_hot(p.st);
-    if (h.done) return;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (uint32_t j = tid; j < h.n_cols; j += stride) {
-        p.prices[j] = 0.0;
-        p.o2p[j] = SLA_DEV_NONE;
-    }
-    for (uint32_t i = tid; i < h.n_rows; i += stride) p.p2o[i] = SLA_DEV_NONE;
-}
-
-// First round of a solve, object side (replaces init_solve_late_kernel + the object half of assign_wide_kernel when the
-// first scan ran with all prices zero): one coalesced sweep over the objects.  An object whose bid word is set takes
+// First round of a solve, object side (initialisation of solver.rs:218-229 + the object half of the assignment when the
+// first scan ran with all prices zero: it read neither prices nor owners, so they are only written now, behind it): one coalesced sweep over the objects.  An object whose bid word is set takes
 // the exact f64 bid of the person the word elected (first round: slot index == person) as its price, records that
 // person as its owner and clears the word; every other object gets price 0 and no owner (solver.rs:218-229).  All
 // stores are coalesced; the only scattered access is the winner's 8-byte bid, still in the L2 behind the scan.
