@@ -136,6 +136,12 @@ int sla_upload_csr_negating(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, 
  * host, solver.rs:41-101). */
 int sla_last_upload(const sla_ctx *ctx, uint64_t *bytes, uint32_t *value_bytes);
 
+/* The narrowing step of that upload on its own (host only, no device): tries to narrow values[0..n) to `tier` bytes
+ * each (2: u16, 4: f32) into `out`.  Returns 1 when every value survives the round trip bit for bit (then, with
+ * `negate`, `values` has also been negated in place, solver.rs:214-216), 0 when some value does not (`values` is left
+ * unchanged), -1 on bad arguments. */
+int sla_host_narrow(double *values, size_t n, int tier, void *out, int negate);
+
 /* Same, source arrays already in device memory (device-side generators, multi-GPU shards). */
 int sla_upload_csr_device(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t *d_row_ptr,
                           const uint32_t *d_column_indices, const double *d_values, uint64_t nnz);

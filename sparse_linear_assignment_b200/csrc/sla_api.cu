@@ -1528,6 +1528,18 @@ int sla_upload_csr_negating(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, 
     return upload_large(ctx, num_rows, num_cols, row_ptr, column_indices, values, nnz, true, threads);
 }
 
+// Host helper behind the narrow upload, exposed for the wrappers' tests: tries to narrow values[0..n) to `tier` bytes
+// each (2: u16, 4: f32) into `out`; returns 1 when every value survives the round trip bit for bit (then `out` holds the
+// narrow copy and, with `negate`, `values` has been negated in place), 0 otherwise (`values` unchanged), -1 on bad
+// arguments.  No device is involved.
+int sla_host_narrow(double* values, size_t n, int tier, void* out, int negate) {
+    if (!values || !out || (tier != 2 && tier != 4)) return -1;
+    if (n == 0) return 1;
+    const bool ok = tier == 2 ? NegPool::narrow_u16(values, (uint16_t*)out, 0, n, negate != 0)
+                              : NegPool::narrow_f32(values, (float*)out, 0, n, negate != 0);
+    return ok ? 1 : 0;
+}
+
 // Bytes the last upload moved from host to device and the width (2 / 4 / 8) the values crossed PCIe with.
 int sla_last_upload(const sla_ctx* ctx, uint64_t* bytes, uint32_t* value_bytes) {
     if (!ctx) return SLA_ERR_INVALID;

@@ -137,3 +137,52 @@ def test_get_objective_ecs_and_toleration_match_oracle(sla, oracle):
         assert solver.ecs_satisfied(z.person_to_object, eps, tol) == o.ecs_satisfied(eps, tol)
     for cost in (0.0, 0.5, 1.0, 999.0, 1000.0, 1e6):
         assert solver.get_toleration(cost) == oracle.get_toleration(cost)
+
+
+def test_host_narrowing_is_lossless_or_refuses(sla):
+    """sla_host_narrow (the host half of the narrow upload): accepts exactly the arrays whose every value survives the
+    round trip through u16 / f32 bit for bit, leaves the input untouched when it refuses, and negates in place only
+    when it accepts.  Lengths around the SIMD width, values around the representable range, zeros of both signs, NaN."""
+    import ctypes as C
+    from sparse_linear_assignment_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+
+    def run(v, tier, negate):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        work = v.copy()
+        out = np.zeros(max(v.size, 1), dtype=np.uint16 if tier == 2 else np.float32)
+        rc = lib.sla_host_narrow(work.ctypes.data, v.size, tier, out.ctypes.data, int(negate))
+        with np.errstate(invalid="ignore", over="ignore"):
+            if tier == 2:
+                ok = bool(np.all((v >= 0) & (v <= 65535) & (np.floor(v) == v) & ~np.signbit(v)))
+            else:
+                ok = bool(np.array_equal(v.astype(np.float32).astype(np.float64).view(np.uint64), v.view(np.uint64)))
+        assert rc == (1 if ok else 0), (tier, negate, v[:8], rc, ok)
+        if ok:
+            assert np.array_equal(out[: v.size].astype(np.float64).view(np.uint64), v.view(np.uint64))
+            assert np.array_equal(work.view(np.uint64), (-v if negate else v).view(np.uint64))
+        else:
+            assert np.array_equal(work.view(np.uint64), v.view(np.uint64))      # untouched (NaN payloads included)
+
+    for n in (1, 3, 7, 8, 9, 15, 16, 17, 31, 1000, 4099):
+        ints = rng.integers(0, 65536, size=n).astype(np.float64)
+        halves = ints + 0.5
+        for negate in (False, True):
+            run(ints, 2, negate)
+            run(ints, 4, negate)
+            run(halves, 2, negate)
+            run(halves, 4, negate)
+            run(-ints - 1.0, 2, negate)
+            run(-ints - 1.0, 4, negate)
+            for pos in {0, n // 2, n - 1}:
+                for bad in (65536.0, -0.0, -1.0, 0.1, float("nan"), float("inf"), 2.0 ** 40, 1e300, 5e-324):
+                    w = ints.copy()
+                    w[pos] = bad
+                    run(w, 2, negate)
+                    run(w, 4, negate)
+            run(rng.uniform(0, 1000, size=n), 4, negate)
+            edge = ints.copy()
+            edge[0] = 65535.0
+            edge[-1] = 0.0
+            run(edge, 2, negate)
