@@ -1242,7 +1242,11 @@ int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
             if (np.done[sent].load(std::memory_order_acquire)) {
                 int run = 1;                                              // one copy for every run of staged neighbours
                 while (sent + run < npieces && np.done[sent + run].load(std::memory_order_acquire)) run += 1;
-                if (run < kMinRun && sent + run < npieces) { std::this_thread::yield(); continue; }   // copies of >= 2 MB
+                if (run < kMinRun && sent + run < npieces) {                 // copies of >= 2 MB
+                    if (np.narrow_fail.load(std::memory_order_acquire)) break;  // abandoned: no more pieces will follow
+                    std::this_thread::yield();
+                    continue;
+                }
                 const size_t lo = (size_t)sent * piece, end = (size_t)(sent + run) * piece, hi = end < total ? end : total;
                 ce = cudaMemcpyAsync((char*)ctx->d_narrow + lo * tier, (const char*)ctx->h_narrow + lo * tier, (hi - lo) * tier,
                                      cudaMemcpyHostToDevice, ctx->stream);

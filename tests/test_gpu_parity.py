@@ -253,7 +253,8 @@ def test_small_instance_path_equals_device_statistics_path(sla, oracle, kind, cl
             assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v.copy(), maximize=maximize)
 
 
-@pytest.mark.parametrize("flavour", ["u16", "f32", "u16_then_fraction", "f64", "negative_ints", "minus_zero"])
+@pytest.mark.parametrize("flavour", ["u16", "f32", "u16_then_fraction", "u16_then_fraction_early", "u16_then_fraction_middle",
+                                     "f64", "negative_ints", "minus_zero"])
 def test_narrow_upload_is_lossless(sla, oracle, flavour):
     """Large uploads whose values survive a round trip through u16 / f32 cross PCIe narrow and are widened in HBM
     (sla_last_upload reports the width); anything else goes up as f64 -- also when the first non-representable value
@@ -263,11 +264,16 @@ def test_narrow_upload_is_lossless(sla, oracle, flavour):
     n, m, k = 70_000, 200_000, 16                                   # 1.12 M arcs: above the narrowing threshold
     rp, c, v = sla.generators.kregular_host(n, m, k, seed=9)
     v = v.astype(np.float64)
-    expect = {"u16": 2, "f32": 4, "u16_then_fraction": 8, "f64": 8, "negative_ints": 4, "minus_zero": 4}[flavour]
+    expect = {"u16": 2, "f32": 4, "u16_then_fraction": 8, "u16_then_fraction_early": 8, "u16_then_fraction_middle": 8,
+              "f64": 8, "negative_ints": 4, "minus_zero": 4}[flavour]
     if flavour == "f32":
         v = v + 0.5
     elif flavour == "u16_then_fraction":
         v[-12345] += 0.1                                            # passes the probe, fails u16 (and f32) late
+    elif flavour == "u16_then_fraction_early":
+        v[70_001] += 0.1                                            # second 64 Ki-value piece: the copy loop has sent nothing yet
+    elif flavour == "u16_then_fraction_middle":
+        v[v.size // 2 + 3] += 0.1
     elif flavour == "f64":
         v = v + rng.uniform(0.0, 1.0, size=v.size)
     elif flavour == "negative_ints":
