@@ -1306,7 +1306,11 @@ int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
     if (dbg) fprintf(stderr, "[sla] upload enqueued at %.3f ms\n", ms_since());
     int rc = finish_csr(ctx, num_rows, num_cols, nnz);
     if (dbg) fprintf(stderr, "[sla] upload complete (statistics read back) at %.3f ms\n", ms_since());
-    if (rc) join_workers(ctx);
+    if (rc) {
+        // rejected (validate_input / column bound): no solve will follow, so the caller's values go back to what they were
+        join_workers(ctx);
+        if (negate) for (size_t i = 0; i < total; ++i) values[i] = -values[i];
+    }
     return rc;
 }
 

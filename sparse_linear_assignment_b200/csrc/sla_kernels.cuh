@@ -1091,7 +1091,22 @@ __global__ void __launch_bounds__(kWideThreads) csr_stats_kernel(const uint32_t*
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long kmin = ~0ull, kmax = 0ull, bad_c = 0, bad_r = 0, irr = 0;
     const uint32_t k0 = row_ptr[1] - row_ptr[0];
-    for (unsigned long long g = tid; g < nnz; g += stride) {
+    // 4 arcs per thread and step: one 128-bit load of column indices, two of values (the arrays are 256 B-aligned)
+    const unsigned long long quads = nnz / 4ull;
+    for (unsigned long long t = tid; t < quads; t += stride) {
+        const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(cols) + t);
+        const double2 v01 = __ldg(reinterpret_cast<const double2*>(vals) + 2ull * t);
+        const double2 v23 = __ldg(reinterpret_cast<const double2*>(vals) + 2ull * t + 1ull);
+        const unsigned long long k0_ = f64_order_key(v01.x), k1_ = f64_order_key(v01.y), k2_ = f64_order_key(v23.x),
+                                 k3_ = f64_order_key(v23.y);
+        const unsigned long long lo01 = k0_ < k1_ ? k0_ : k1_, lo23 = k2_ < k3_ ? k2_ : k3_;
+        const unsigned long long hi01 = k0_ > k1_ ? k0_ : k1_, hi23 = k2_ > k3_ ? k2_ : k3_;
+        const unsigned long long lo = lo01 < lo23 ? lo01 : lo23, hi = hi01 > hi23 ? hi01 : hi23;
+        kmin = lo < kmin ? lo : kmin;
+        kmax = hi > kmax ? hi : kmax;
+        bad_c += (c4.x >= n_cols ? 1u : 0u) + (c4.y >= n_cols ? 1u : 0u) + (c4.z >= n_cols ? 1u : 0u) + (c4.w >= n_cols ? 1u : 0u);
+    }
+    for (unsigned long long g = quads * 4ull + tid; g < nnz; g += stride) {
         const unsigned long long k = f64_order_key(vals[g]);
         kmin = k < kmin ? k : kmin;
         kmax = k > kmax ? k : kmax;

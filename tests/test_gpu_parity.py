@@ -370,6 +370,30 @@ def test_invalid_inputs_fail_loudly(sla):
         solver.set_option("tail_max", 4096)                  # the tail engine's smem queue holds 1024 bidders
 
 
+@pytest.mark.parametrize("where", ["first", "middle", "last_odd_tail"])
+@pytest.mark.parametrize("narrow", [1, 0])
+def test_invalid_large_upload_fails_loudly_and_leaves_values_alone(sla, where, narrow):
+    """The device-side validation of a large upload (csr_stats_kernel, 4 arcs per thread + a scalar tail): an out-of-range
+    column anywhere in a 1.12 M-arc array is reported, the solve does not run, and the host `values` are back to (or
+    still at) what the caller handed in -- the negation belongs to a solve that happens."""
+    n, m, k = 70_001, 200_000, 16
+    rp, c, v = sla.generators.kregular_host(n, m, k, seed=2)
+    c = c.copy()
+    pos = {"first": 0, "middle": c.size // 2 + 1, "last_odd_tail": c.size - 1}[where]
+    c[pos] = m
+    solver, z = sla.KhoslaSolver.new(n, m, n * k)
+    solver.set_option("narrow_upload", narrow)
+    solver.load_csr(n, m, rp, c, v)
+    with pytest.raises(sla.SlaError) as e:
+        solver.solve(z, False, None)
+    assert e.value.code == 1 and "column" in e.value.message
+    assert np.array_equal(solver.values(), v)                 # not negated: the solve never happened
+    good, z2 = sla.KhoslaSolver.new(n, m, n * k)
+    good.load_csr(n, m, rp, sla.generators.kregular_host(n, m, k, seed=2)[1], v)
+    good.solve(z2, False, None)
+    assert z2.num_unassigned == 0
+
+
 # ---- BASELINE.json configurations -----------------------------------------------------------------------------------
 def test_cfg1_khosla_1000x10000_k32(sla, oracle):
     from sparse_linear_assignment_b200 import generators as G
