@@ -14,6 +14,9 @@ solver.set_option("graph", 0)
 solver.set_option("zero_price_skip", skip)
 if len(sys.argv) > 2:
     solver.set_option("stream_scan", int(sys.argv[2]))
+for kv in sys.argv[3:]:                      # further options as key=value
+    key, val = kv.split("=")
+    solver.set_option(key, int(val))
 for _ in range(3):
     st = solver.solve_resident(False, None)
 print("ok", st["rounds"], st["bid_arcs"], st["ms_solve"])

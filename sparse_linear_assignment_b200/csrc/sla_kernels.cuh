@@ -107,7 +107,10 @@ __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t
 #define SLA_REG_ADJ 0
 #endif
     // rows per group and pass: all their loads are in flight before the first reduction (streaming variant only)
-    constexpr int U = (MODE == PRICE_ZERO) ? SLA_REG_UNROLL : 1;
+#ifndef SLA_REG_UNROLL_LDG
+#define SLA_REG_UNROLL_LDG 1
+#endif
+    constexpr int U = (MODE == PRICE_ZERO) ? SLA_REG_UNROLL : SLA_REG_UNROLL_LDG;
     constexpr bool ADJ = SLA_REG_ADJ != 0;   // the U rows of a group are neighbours in the queue
     for (uint32_t base = 0; base < qlen; base += ngroups * U) {
         if (base + (ADJ ? warp_group0 * U : warp_group0) >= qlen) break;   // warp-uniform: the whole warp is past the end
