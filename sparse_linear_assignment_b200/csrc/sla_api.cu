@@ -282,6 +282,7 @@ struct sla_ctx {
     bool tail_smem_prices = false;   // object prices mirrored
     uint32_t tail_own_mode = 0;      // owners mirrored: 0 no, 1 u32, 2 u16
     uint32_t tail_cap = 1024;        // capacity of the queue arrays (power of two)
+    bool super_rounds_user = false;  // "super_rounds" was set through sla_set_option
     bool tail_max_user = false;      // "tail_max" was set through sla_set_option
     uint32_t tail_max_eff = 1024;    // bidders at or below which the tail engine runs (min(option tail_max, tail_cap))
     uint32_t tail_smem_bytes = 0;    // dynamic shared memory of a tail launch
@@ -512,6 +513,9 @@ int super_rounds_for(const sla_ctx* c, bool forward) {
         if (is_tail_only(c, forward)) return 1;
         if (c->n_rows <= 4u * c->tail_max_eff && c->opt_super_rounds > 2) return 2;
     }
+    // very large instances need more wide rounds before the tail engine can take over (cfg5: 10): a spare super-round
+    // costs 3.5 us of control-step launches, a second graph launch a host round trip
+    if (!c->super_rounds_user && c->n_rows > (1u << 22) && c->opt_super_rounds < 12) return 12;
     return c->opt_super_rounds;
 }
 
@@ -1490,6 +1494,7 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "super_rounds") {
         if (value < 1 || value > 64) return fail(ctx, SLA_ERR_INVALID, "super_rounds must be in [1, 64]");
         ctx->opt_super_rounds = (int)value;
+        ctx->super_rounds_user = true;
     } else {
         return fail(ctx, SLA_ERR_INVALID, "unknown option: " + k);
     }
