@@ -511,6 +511,9 @@ bool is_tail_only(const sla_ctx* c, bool forward) { return c->n_rows <= solve_ta
 int super_rounds_for(const sla_ctx* c, bool forward) {
     if (!forward && !khosla_phases(c)) {
         if (is_tail_only(c, forward)) return 1;
+        // wide first round (solve_tail_max = N / 2): the tail engine finishes the solve behind it unless more than half of
+        // the persons lost round 1 -- then the continuation graph takes over
+        if (c->n_rows <= c->tail_max_eff) return 1;
         if (c->n_rows <= 4u * c->tail_max_eff && c->opt_super_rounds > 2) return 2;
     }
     // very large instances need more wide rounds before the tail engine can take over (cfg5: 10): a spare super-round

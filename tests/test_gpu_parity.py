@@ -394,6 +394,28 @@ def test_invalid_large_upload_fails_loudly_and_leaves_values_alone(sla, where, n
     assert z2.num_unassigned == 0
 
 
+def test_wide_first_round_with_most_persons_losing(sla, oracle):
+    """Plain Khosla with 641 .. 1,024 persons runs its first round on the grid-wide kernels inside a one-super-round
+    graph; when more than half of the persons lose that round (everybody prefers the same few objects) the queue is still
+    too long for the tail engine and continuation graphs have to take over -- same bits as the model either way."""
+    rng = np.random.default_rng(21)
+    n, m, k = 900, 2000, 8
+    rp, c, v = random_sparse_instance(rng, n, m, k, integer=True, lo=0, hi=50)
+    v = v.reshape(n, k)
+    c2 = c.reshape(n, k).copy()
+    c2[:, 0] = np.arange(n) % 3                       # three hot objects in everybody's row ...
+    c2.sort(axis=1)
+    for i in range(n):                                # (keep rows duplicate-free and sorted)
+        while len(set(c2[i])) < k:
+            c2[i] = np.sort(np.unique(np.concatenate([np.unique(c2[i]), rng.choice(m, size=k, replace=False)]))[:k])
+    hot = c2 < 3
+    v[hot] = 1000.0                                   # ... and far more valuable than anything else (maximize)
+    c, v = c2.reshape(-1).astype(np.uint32), v.reshape(-1)
+    solver, z = gpu_solve(sla, "KhoslaSolver", n, m, rp, c, v, maximize=True)
+    assert solver.last_stats["wide_rounds"] >= 2 and solver.last_stats["graph_launches"] >= 2
+    assert_equals_model(oracle, "khosla", solver, z, n, m, rp, c, v, maximize=True)
+
+
 # ---- BASELINE.json configurations -----------------------------------------------------------------------------------
 def test_cfg1_khosla_1000x10000_k32(sla, oracle):
     from sparse_linear_assignment_b200 import generators as G
