@@ -497,16 +497,24 @@ def main_ours(args):
             resident.set_option("zero_price_skip", 1)
             if rec:
                 t_ms = sorted(ts)[len(ts) // 2]
-                alg = 12 * rec["arcs"] + 8 * rec["bidders"]
+                # bytes per arc the scan must read: 4 (column index) + the width the values are resident with -- 8 (f64,
+                # 12*A + 8*B) or 2 when a u16 upload left its lossless copy in HBM and the scan reads that
+                vb = resident.scan_value_bytes()
+                survey = 12 * rec["arcs"] + 8 * rec["bidders"]
+                alg = (4 + vb) * rec["arcs"] + 8 * rec["bidders"]
                 ach = alg / (t_ms * 1e-3) / 1e9
                 kname = "bid_regular_kernel<PRICE_ZERO>" if skip else "bid_regular_kernel<PRICE_LDG>"
+                if vb == 2:
+                    kname = kname[:-1] + ",u16>"
                 roof[key] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "traffic": ncu_traffic(kname), "kernel": kname, "launch": "round 1 (all persons bid)",
                              "bidders": rec["bidders"], "arcs": rec["arcs"], "algorithmic_bytes": alg,
-                             "launch_us": t_ms * 1e3, "peak_source": peak_src}
+                             "launch_us": t_ms * 1e3, "peak_source": peak_src, "value_bytes_in_hbm": vb,
+                             "bytes_at_f64_values": survey, "equivalent_f64_gbs": survey / (t_ms * 1e-3) / 1e9}
                 if b2b:
                     roof[key]["launch_us_back_to_back"] = b2b * 1e3
                     roof[key]["frac_back_to_back"] = alg / (b2b * 1e-3) / 1e9 / peak
+        # whole solve: SURVEY 8(d)'s f64 bytes over the solve time, whatever width the wide scans read the values at
         whole = (12 * stats["bid_arcs"] + 8 * stats["bids"]) / (stats["ms_solve"] * 1e-3) / 1e9
 
         cpu = None
@@ -529,7 +537,7 @@ def main_ours(args):
             "roofline": roof.get("roofline"),
             "roofline_general_gather": roof.get("roofline_general_gather"),
             "roofline_whole_solve": {"achieved": whole, "unit": "GB/s", "frac": whole / peak,
-                                     "note": "sum over rounds of 12*A + 8*B over the whole solve time (tail rounds included)"},
+                                     "note": "sum over rounds of 12*A + 8*B (values counted as f64) over the whole solve time, tail rounds included"},
             "cpu_baseline": cpu,
             "solve": {k_: stats[k_] for k_ in ("rounds", "wide_rounds", "tail_rounds", "bids", "bid_arcs", "num_unassigned",
                                                "kernel_launches", "graph_launches", "ms_solve")},

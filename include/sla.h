@@ -105,7 +105,7 @@ void sla_host_negate_f64(double *values, size_t n, int threads);
  * "small_path" (1: instances of up to 1 MB take their statistics on the host while they are staged for upload and
  * download their results behind each graph launch: one device round trip per solve), "wide_first" (1: plain Khosla
  * solves with 641 .. tail_max persons run their first round on the grid-wide kernels), "narrow_upload" (1: see
- * sla_last_upload), "stream_scan" (1: first-round scan of a uniform-degree CSR through the TMA pipeline
+ * sla_last_upload), "narrow_scan" (1: see sla_scan_value_bytes), "stream_scan" (1: first-round scan of a uniform-degree CSR through the TMA pipeline
  * bid_stream_kernel instead of the LDG.256 kernel; identical results), "l2_persist" (1: access-policy window that
  * keeps the bid words persisting in the L2), "profile_repeat" (development: launches of the scan per profile bracket). */
 int sla_set_option(sla_ctx *ctx, const char *key, int64_t value);
@@ -135,6 +135,13 @@ int sla_upload_csr_negating(sla_ctx *ctx, uint32_t num_rows, uint32_t num_cols, 
  * for bit; option "narrow_upload" = 0 turns this off.  No counterpart in the reference (its Vecs never leave the
  * host, solver.rs:41-101). */
 int sla_last_upload(const sla_ctx *ctx, uint64_t *bytes, uint32_t *value_bytes);
+
+/* Width (2 or 8 bytes) with which the uniform-degree bid scans read each value of the resident CSR.  After a narrow
+ * upload at 2 bytes per value the u16 copy stays in HBM beside the widened f64 array, and the grid-wide scans of a CSR
+ * whose rows all have the same multiple-of-8 degree read it: 6 instead of 12 bytes per arc, the same doubles after the
+ * exact conversion, so the same choices as the reference's f64 scan (ksparse.rs:199-214, symmetric.rs:361-376) bit
+ * for bit.  Every other kernel reads the f64 array.  Option "narrow_scan" = 0 turns this off. */
+int sla_scan_value_bytes(const sla_ctx *ctx, uint32_t *value_bytes);
 
 /* The narrowing step of that upload on its own (host only, no device): tries to narrow values[0..n) to `tier` bytes
  * each (2: u16, 4: f32) into `out`.  Returns 1 when every value survives the round trip bit for bit (then, with

@@ -48,6 +48,7 @@ extern "C" {
                                    column_indices: *const u32, values: *mut f64, nnz: u64, threads: c_int) -> c_int;
     pub fn sla_host_narrow(values: *mut f64, n: usize, tier: c_int, out: *mut c_void, negate: c_int) -> c_int;
     pub fn sla_last_upload(ctx: *const sla_ctx, bytes: *mut u64, value_bytes: *mut u32) -> c_int;
+    pub fn sla_scan_value_bytes(ctx: *const sla_ctx, value_bytes: *mut u32) -> c_int;
     pub fn sla_khosla_solve(ctx: *mut sla_ctx, maximize: c_int, eps: f64, person_to_object: *mut u32,
                             object_to_person: *mut u32, prices: *mut f64, stats: *mut sla_stats) -> c_int;
     pub fn sla_forward_solve(ctx: *mut sla_ctx, maximize: c_int, eps: f64, start_eps: f64, max_iterations: u32,

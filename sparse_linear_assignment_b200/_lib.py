@@ -96,6 +96,7 @@ SIGNATURES = {
     "sla_upload_csr_negating": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint64, C.c_int]),
     "sla_host_narrow": (C.c_int, [_vp, C.c_size_t, C.c_int, _vp, C.c_int]),
     "sla_last_upload": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "sla_scan_value_bytes": (C.c_int, [_vp, C.POINTER(C.c_uint32)]),
     "sla_upload_csr_device": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint64]),
     "sla_generate_device": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32,
                                       C.c_int]),

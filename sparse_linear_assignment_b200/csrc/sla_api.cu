@@ -37,6 +37,7 @@ struct GraphSlot {
     uint32_t tail_max = 0;
     bool khosla_phases = false;
     size_t l2_bytes = 0;
+    const void* vals16 = nullptr;   // u16 value mirror the regular bid kernels were captured with (nullptr: f64 values)
 };
 
 }  // namespace
@@ -251,6 +252,8 @@ struct sla_ctx {
     void* d_narrow = nullptr;
     size_t d_narrow_cap = 0;
     int opt_narrow_upload = 1;
+    int opt_narrow_scan = 1;       // regular bid kernels read the u16 mirror a narrow upload left in HBM (6 B per arc)
+    bool vals16_valid = false;     // d_narrow holds the u16 image of every value in d_vals
     uint64_t last_upload_bytes = 0;       // bytes the last upload moved host -> device
     uint32_t last_upload_value_bytes = 8; // 2 / 4 / 8: width the values crossed PCIe with
     unsigned char* h_dl = nullptr;        // small instances: results land here behind each graph launch (one sync per launch)
@@ -339,6 +342,7 @@ Params make_params(const sla_ctx* c) {
     p.prices = c->d_prices; p.p2o = c->d_p2o; p.o2p = c->d_o2p; p.best = c->d_best;
     p.queue[0] = c->d_queue[0]; p.queue[1] = c->d_queue[1];
     p.slot_obj = c->d_slot_obj; p.slot_bid = c->d_slot_bid; p.st = c->d_state;
+    p.vals16 = c->vals16_valid ? static_cast<const uint16_t*>(c->d_narrow) : nullptr;
     return p;
 }
 
@@ -406,6 +410,11 @@ int pick_lpr(uint64_t nnz, uint32_t n_rows) {
 #endif
 // First round of a solve on a regular CSR with K <= 256: the TMA pipeline (rows of a tile are one contiguous range).
 bool use_stream_scan(const sla_ctx* c) { return c->opt_stream_scan && c->regular_k != 0 && c->regular_k <= 256u; }
+// The values crossed PCIe as u16 and that copy is still in HBM: the uniform-degree scans read it instead of the
+// widened f64 array (same doubles after conversion, half the bytes per arc).
+const void* narrow_scan_ptr(const sla_ctx* c) {
+    return (c->opt_narrow_scan && c->vals16_valid && c->regular_k != 0 && c->regular_k <= 32768u && c->opt_regular) ? c->d_narrow : nullptr;
+}
 
 template <int MODE>
 void launch_bid_regular_m(sla_ctx* c, const Params& p) {
@@ -422,6 +431,18 @@ void launch_bid_regular_m(sla_ctx* c, const Params& p) {
         return;
     }
     const int grid_wide = (MODE == PRICE_ZERO) ? c->num_sms * SLA_REG_OCC_ZERO : c->grid_wide;
+    if (narrow_scan_ptr(c) && p.vals16) {
+        const int grid_wide = (MODE == PRICE_ZERO) ? c->num_sms * SLA_KEY_OCC : c->grid_wide;
+        switch (c->lpr8) {
+            case 1: bid_regular_kernel<1, MODE, true><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+            case 2: bid_regular_kernel<2, MODE, true><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+            case 4: bid_regular_kernel<4, MODE, true><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+            case 8: bid_regular_kernel<8, MODE, true><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+            case 16: bid_regular_kernel<16, MODE, true><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+            default: bid_regular_kernel<32, MODE, true><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        }
+        return;
+    }
     switch (c->lpr8) {
         case 1: bid_regular_kernel<1, MODE><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
         case 2: bid_regular_kernel<2, MODE><<<grid_wide, kWideThreads, 0, c->stream>>>(p); break;
@@ -590,7 +611,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == n_super &&
         g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices && g.tail_only == tail_only &&
         g.tail_smem_bytes == ctx->tail_smem_bytes && g.tail_max == solve_tail_max(ctx, forward) && g.khosla_phases == khosla_phases(ctx) &&
-        g.l2_bytes == ctx->l2_bytes) {
+        g.l2_bytes == ctx->l2_bytes && g.vals16 == narrow_scan_ptr(ctx)) {
         *out = g.exec;
         return SLA_OK;
     }
@@ -633,6 +654,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     g.tail_max = solve_tail_max(ctx, forward);
     g.khosla_phases = khosla_phases(ctx);
     g.l2_bytes = ctx->l2_bytes;
+    g.vals16 = narrow_scan_ptr(ctx);
     *out = g.exec;
     return SLA_OK;
 }
@@ -975,6 +997,7 @@ int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz)
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     ctx->has_csr = false;
+    ctx->vals16_valid = false;       // upload_large sets it again when the values it just sent went up as u16
     if (ctx->h_scratch[0] != 0 || (uint64_t)ctx->h_scratch[1] != nnz)
         return fail(ctx, SLA_ERR_INVALID, "row_ptr[0] must be 0 and row_ptr[num_rows] must equal nnz");
     if (ctx->h_csr_stats->bad_rows) return fail(ctx, SLA_ERR_INVALID, "row extents are not monotone");
@@ -1100,6 +1123,7 @@ int upload_small(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
     uint32_t* s_cols = reinterpret_cast<uint32_t*>(ctx->h_small + b_rp);
     double* s_vals = reinterpret_cast<double*>(ctx->h_small + b_rp + b_cols);
     ctx->has_csr = false;
+    ctx->vals16_valid = false;
     // extents
     if (row_ptr[0] != 0 || (uint64_t)row_ptr[num_rows] != nnz)
         return fail(ctx, SLA_ERR_INVALID, "row_ptr[0] must be 0 and row_ptr[num_rows] must equal nnz");
@@ -1185,6 +1209,7 @@ int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
     double t_first = 0, t_half = 0;
     ctx->last_upload_bytes = ((size_t)num_rows + 1) * 4 + total * 4;
     ctx->last_upload_value_bytes = 8;
+    ctx->vals16_valid = false;
     const bool want_pool = negate || (ctx->opt_narrow_upload && total >= ((size_t)1 << 20));
     const bool pool_ok = want_pool && ctx->neg.start(ctx->device);
     if (negate && !pool_ok) return fail(ctx, SLA_ERR_CUDA, "could not start the host negation workers");
@@ -1317,6 +1342,8 @@ int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
         // rejected (validate_input / column bound): no solve will follow, so the caller's values go back to what they were
         join_workers(ctx);
         if (negate) for (size_t i = 0; i < total; ++i) values[i] = -values[i];
+    } else {
+        ctx->vals16_valid = narrowed && tier == 2;   // d_narrow keeps the u16 image of d_vals until the next upload
     }
     return rc;
 }
@@ -1487,6 +1514,8 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
         apply_l2_policy(ctx);
     } else if (k == "narrow_upload") {
         ctx->opt_narrow_upload = value ? 1 : 0;
+    } else if (k == "narrow_scan") {
+        ctx->opt_narrow_scan = value ? 1 : 0;
     } else if (k == "small_path") {
         ctx->opt_small_path = value ? 1 : 0;
     } else if (k == "wide_first") {
@@ -1561,6 +1590,13 @@ int sla_last_upload(const sla_ctx* ctx, uint64_t* bytes, uint32_t* value_bytes) 
     if (!ctx) return SLA_ERR_INVALID;
     if (bytes) *bytes = ctx->last_upload_bytes;
     if (value_bytes) *value_bytes = ctx->last_upload_value_bytes;
+    return SLA_OK;
+}
+
+// Width (2 or 8 bytes) the uniform-degree bid scans read each value with on the resident CSR.
+int sla_scan_value_bytes(const sla_ctx* ctx, uint32_t* value_bytes) {
+    if (!ctx || !value_bytes) return SLA_ERR_INVALID;
+    *value_bytes = (ctx->has_csr && narrow_scan_ptr(ctx) && !use_stream_scan(ctx)) ? 2u : 8u;
     return SLA_OK;
 }
 

@@ -103,6 +103,7 @@ struct Params {
     const uint32_t* __restrict__ row_ptr;
     const uint32_t* __restrict__ cols;
     const double* __restrict__ vals;
+    const uint16_t* __restrict__ vals16;   // lossless u16 mirror of `vals` left by a narrow upload (nullptr: none)
     double* prices;
     uint32_t* p2o;
     uint32_t* o2p;
@@ -269,6 +270,18 @@ __device__ __forceinline__ void ld_stream_d4(const double* p, double* r) {
                  : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
 }
 
+__device__ __forceinline__ uint4 ld_stream_u16x8(const uint16_t* p) {
+    uint4 r;
+    // (the L2::evict_first qualifier exists for the 256-bit forms only)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+// Exact u16 -> f64: 2^52 + x has x in its low mantissa bits, and the subtraction is exact.
+__device__ __forceinline__ double u16_to_f64(uint32_t x) {
+    return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
+}
+
 enum PriceMode : int {
     PRICE_ZERO = 0,   // all prices are exactly 0.0: no gather
     PRICE_LDG = 1,    // prices immutable during this kernel: read-only path
@@ -399,6 +412,81 @@ __device__ __forceinline__ void scan8(Choice& c, const uint32_t* __restrict__ co
         const double v = __hiloint2double(__double2hiint(vv[t]) ^ (int)flip, __double2loint(vv[t]));
         choice_update(c, (MODE == PRICE_ZERO) ? v : (v - pr[t]), v, g + t, cj[t]);
     }
+}
+
+// The same over the u16 mirror of the values (narrow upload, every value an integer in [0, 65535]): 6 instead of 12
+// bytes per arc.  (double)u16 equals the widened f64 value bit for bit, so the choice is identical.
+template <int MODE>
+__device__ __forceinline__ void scan8_narrow(Choice& c, const uint32_t* __restrict__ cols, const uint16_t* __restrict__ vals16,
+                                             const double* prices, uint32_t g, uint32_t flip) {
+    uint32_t cj[8];
+    double pr[8];
+    ld_stream_u8(cols + g, cj);
+    const uint4 w = ld_stream_u16x8(vals16 + g);
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int t = 0; t < 8; ++t) pr[t] = ld_price<MODE>(prices, cj[t]);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const double x = u16_to_f64((ww[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu);
+        const double v = __hiloint2double(__double2hiint(x) ^ (int)flip, __double2loint(x));
+        choice_update(c, (MODE == PRICE_ZERO) ? v : (v - pr[t]), v, g + t, cj[t]);
+    }
+}
+
+// First round (all prices exactly 0) over the u16 mirror, in integers: profit == +-value, so the choice rule is a
+// top-2 over order-preserving keys.  key = value (maximising) or 65535 - value (values negated on the fly: larger key
+// <=> larger -value); packed = key << 15 | (32767 - position in the row): the maximum is the best profit at the
+// lowest position (the reference's strict '>' in position order, ksparse.rs:206 / symmetric.rs:367), the second
+// largest packed word carries the second best profit in the multiset sense.  Rows of up to 32,768 arcs.
+struct KeyChoice {
+    int best, second;     // packed words, -1 = none yet
+    uint32_t col;         // column of `best`
+};
+__device__ __forceinline__ void key_choice_init(KeyChoice& c) { c.best = -1; c.second = -1; c.col = 0u; }
+
+__device__ __forceinline__ void scan8_keys(KeyChoice& c, const uint32_t* __restrict__ cols, const uint16_t* __restrict__ vals16,
+                                           uint32_t g, uint32_t local, uint32_t keyflip) {
+    uint32_t cj[8];
+    ld_stream_u8(cols + g, cj);
+    const uint4 w = ld_stream_u16x8(vals16 + g);
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    const int base = 32767 - (int)local;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const uint32_t x = (t & 1) ? (ww[t >> 1] >> 16) : (ww[t >> 1] & 0xFFFFu);
+        const int pk = (int)((x ^ keyflip) << 15) + (base - t);
+        c.col = (pk > c.best) ? cj[t] : c.col;
+        const int lo = min(c.best, pk);
+        c.best = max(c.best, pk);
+        c.second = max(c.second, lo);
+    }
+}
+
+template <int LPR>
+__device__ __forceinline__ void key_choice_group_reduce(KeyChoice& c) {
+#pragma unroll
+    for (int m = LPR / 2; m >= 1; m >>= 1) {
+        const int ob = __shfl_xor_sync(0xffffffffu, c.best, m);
+        const int os = __shfl_xor_sync(0xffffffffu, c.second, m);
+        const uint32_t oc = __shfl_xor_sync(0xffffffffu, c.col, m);
+        c.col = (ob > c.best) ? oc : c.col;
+        const int lo = min(c.best, ob);
+        c.best = max(c.best, ob);
+        c.second = max(max(c.second, os), lo);
+    }
+}
+
+// The f64 choice the packed words stand for (rows of at least two arcs: both words are set).
+__device__ __forceinline__ void key_choice_to_f64(Choice& out, const KeyChoice& c, uint32_t row_begin, uint32_t keyflip, uint32_t flip) {
+    const double xb = u16_to_f64(((uint32_t)c.best >> 15) ^ keyflip);
+    const double xs = u16_to_f64(((uint32_t)c.second >> 15) ^ keyflip);
+    out.value = __hiloint2double(__double2hiint(xb) ^ (int)flip, __double2loint(xb));
+    out.best = out.value;
+    out.second = __hiloint2double(__double2hiint(xs) ^ (int)flip, __double2loint(xs));
+    out.pos = row_begin + (32767u - ((uint32_t)c.best & 32767u));
+    out.col = c.col;
+    out.aux = SLA_DEV_NONE;
 }
 
 // ---- warp-per-bidder scan for the small rounds of the single-CTA engines ---------------------------------------

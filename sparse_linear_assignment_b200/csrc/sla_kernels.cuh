@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kWideThreads) bid_wide_kernel(const Params p) 
 
 // Regular-CSR variant (every row has exactly K arcs, K % 8 == 0: all of BASELINE.json's configs): no row-extent
 // loads (a = i * K), no masking, 8 arcs per lane per step through 256-bit loads.  LPR8 lanes share one row.
-template <int LPR8, int MODE>
+template <int LPR8, int MODE, bool NARROW>
 __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t qlen, const bool identity,
                                                  const uint32_t* __restrict__ queue, const uint32_t algo, const double eps,
                                                  const double threshold, const uint32_t pbits, const uint32_t sign_flip,
@@ -112,6 +112,53 @@ __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t
 #endif
     constexpr int U = (MODE == PRICE_ZERO) ? SLA_REG_UNROLL : SLA_REG_UNROLL_LDG;
     constexpr bool ADJ = SLA_REG_ADJ != 0;   // the U rows of a group are neighbours in the queue
+    if constexpr (NARROW && MODE == PRICE_ZERO) {
+        // u16 values and all prices zero: the choice in integer keys (scan8_keys), converted to the f64 choice at the end
+        // (the host takes this kernel for K <= 32,768 only: narrow_scan_ptr)
+        const uint32_t keyflip = sign_flip ? 0xFFFFu : 0u;
+#ifndef SLA_KEY_UNROLL
+#define SLA_KEY_UNROLL 2
+#endif
+        constexpr int UK = SLA_KEY_UNROLL;           // rows per group and pass (48 B per lane and row in flight)
+        for (uint32_t base = 0; base < qlen; base += ngroups * UK) {
+            if (base + warp_group0 >= qlen) break;   // warp-uniform: the whole warp is past the end
+            KeyChoice kc[UK];
+            uint32_t i[UK];
+            bool valid[UK];
+#pragma unroll
+            for (int u = 0; u < UK; ++u) {
+                const uint32_t q = base + (uint32_t)u * ngroups + group;
+                valid[u] = q < qlen;
+                key_choice_init(kc[u]);
+                i[u] = 0;
+                if (valid[u]) {
+                    i[u] = identity ? q : __ldg(queue + q);
+                    const uint32_t a = i[u] * K;
+                    for (uint32_t off = 8u * (uint32_t)lane; off < K; off += 8u * LPR8)
+                        scan8_keys(kc[u], p.cols, p.vals16, a + off, off, keyflip);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UK; ++u) {
+                if (u && base + (uint32_t)u * ngroups + warp_group0 >= qlen) break;   // warp-uniform
+                const uint32_t q = base + (uint32_t)u * ngroups + group;
+                key_choice_group_reduce<LPR8>(kc[u]);
+                if (valid[u] && lane == 0) {
+                    Choice c;
+                    key_choice_to_f64(c, kc[u], i[u] * K, keyflip, sign_flip);
+                    const Bid r = make_bid<MODE>(c, algo, eps, threshold, p.prices);
+                    if (r.dropped) {
+                        p.slot_obj[q] = SLA_DEV_NONE;
+                        my_dropped += 1;
+                    } else {
+                        p.slot_obj[q] = r.obj;
+                        p.slot_bid[q] = r.bid;
+                        if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i[u] + person_base, pbits));
+                    }
+                }
+            }
+        }
+    } else {
     for (uint32_t base = 0; base < qlen; base += ngroups * U) {
         if (base + (ADJ ? warp_group0 * U : warp_group0) >= qlen) break;   // warp-uniform: the whole warp is past the end
         Choice c[U];
@@ -126,8 +173,10 @@ __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t
             if (valid[u]) {
                 i[u] = identity ? q : __ldg(queue + q);
                 const uint32_t a = i[u] * K;
-                for (uint32_t off = 8u * (uint32_t)lane; off < K; off += 8u * LPR8)
-                    scan8<MODE>(c[u], p.cols, p.vals, p.prices, a + off, sign_flip);
+                for (uint32_t off = 8u * (uint32_t)lane; off < K; off += 8u * LPR8) {
+                    if (NARROW) scan8_narrow<MODE>(c[u], p.cols, p.vals16, p.prices, a + off, sign_flip);
+                    else scan8<MODE>(c[u], p.cols, p.vals, p.prices, a + off, sign_flip);
+                }
             }
         }
 #pragma unroll
@@ -153,6 +202,7 @@ __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t
                 }
             }
         }
+    }
     }
     if (my_dropped) atomicAdd(&p.st->dropped, my_dropped);
     // arcs of a regular round = bidders * K: accounted in control step A
@@ -184,11 +234,16 @@ __global__ void profile_fence_kernel() {}
 
 // MODE is a launch-time decision of the host: PRICE_ZERO only for the very first round of a solve (prices are
 // exactly 0 after init_solve, solver.rs:218-219, and the option zero_price_skip is on), PRICE_LDG otherwise.
-template <int LPR8, int MODE>
+// NARROW: the values are read from their u16 mirror (Params::vals16), which a narrow upload left in HBM.
+template <int LPR8, int MODE, bool NARROW = false>
 #ifndef SLA_REG_MINB_ZERO
 #define SLA_REG_MINB_ZERO 3
 #endif
-__global__ void __launch_bounds__(kWideThreads, (MODE == PRICE_ZERO) ? SLA_REG_MINB_ZERO : 4) bid_regular_kernel(const Params p) {
+// CTAs per SM of the integer-key first round (46 registers at 5, spills from 6 up): cfg3 scan 29.4 us at 3, 26.7 at 4
+#ifndef SLA_KEY_OCC
+#define SLA_KEY_OCC 5
+#endif
+__global__ void __launch_bounds__(kWideThreads, (MODE == PRICE_ZERO) ? (NARROW ? SLA_KEY_OCC : SLA_REG_MINB_ZERO) : 4) bid_regular_kernel(const Params p) {
     const HotState h = load_hot(p.st);
     const uint32_t cur = h.cur;
     const uint32_t qlen = h.qlen[cur & 1u];
@@ -197,7 +252,7 @@ __global__ void __launch_bounds__(kWideThreads, (MODE == PRICE_ZERO) ? SLA_REG_M
     const uint32_t algo = h.algo, pbits = h.pbits, sf = h.sign_flip, K = h.regular_k;
     const double eps = h.eps, thr = h.threshold;
     const uint32_t* queue = cur ? p.queue[1] : p.queue[0];
-    bid_regular_body<LPR8, MODE>(p, qlen, identity, queue, algo, eps, thr, pbits, sf, K, h.person_base);
+    bid_regular_body<LPR8, MODE, NARROW>(p, qlen, identity, queue, algo, eps, thr, pbits, sf, K, h.person_base);
 }
 
 // =============================================================================================================

@@ -408,6 +408,14 @@ class AuctionSolver:
         _lib.check(ctx, _lib.load().sla_last_upload(ctx, C.byref(b), C.byref(w)))
         return int(b.value), int(w.value)
 
+    def scan_value_bytes(self) -> int:
+        """Bytes per value the grid-wide uniform-degree scans read on the resident CSR (sla_scan_value_bytes): 2 after a
+        u16 upload, else 8."""
+        ctx = self._context()
+        w = C.c_uint32()
+        _lib.check(ctx, _lib.load().sla_scan_value_bytes(ctx, C.byref(w)))
+        return int(w.value)
+
     def set_option(self, key: str, value: int) -> None:
         ctx = self._context()
         _lib.check(ctx, _lib.load().sla_set_option(ctx, key.encode(), int(value)))

@@ -300,6 +300,47 @@ def test_narrow_upload_is_lossless(sla, oracle, flavour):
 
 
 @pytest.mark.parametrize("kind,cls_name", SOLVERS)
+@pytest.mark.parametrize("maximize", [False, True])
+def test_narrow_scan_reads_the_u16_mirror_and_changes_nothing(sla, oracle, kind, cls_name, maximize):
+    """After a u16 upload the grid-wide uniform-degree scans read the u16 copy of the values that stayed in HBM
+    (sla_scan_value_bytes == 2, option narrow_scan): 6 instead of 12 bytes per arc.  The doubles are the same after the
+    exact conversion, so prices / assignment / counters equal the f64 scan (narrow_scan = 0) and the CPU model bit for
+    bit -- with and without the on-the-fly sign flip, with the extreme values 0 and 65,535 present, across a second
+    solve on the resident CSR, and a later upload of other values drops the mirror."""
+    n, m, k = (70_000, 200_000, 16) if kind == "khosla" else (66_000, 66_000, 16)
+    rp, c, v = sla.generators.kregular_host(n, m, k, seed=21, planted=(kind == "forward"))
+    v = v.astype(np.float64)
+    v[7::1001] = 0.0
+    v[11::1003] = 65535.0
+    out = []
+    for narrow in (1, 0):
+        solver, z = getattr(sla, cls_name).new(n, m, n * k)
+        solver.set_option("narrow_scan", narrow)
+        solver.load_csr(n, m, rp, c, v.copy())
+        solver.solve(z, maximize, None)
+        assert solver.last_upload()[1] == 2
+        assert solver.scan_value_bytes() == (2 if narrow else 8)
+        assert solver.last_stats["wide_rounds"] >= 2                # both the zero-price and the gathering scan ran
+        first = (z.person_to_object.copy(), z.object_to_person.copy(), solver.prices().copy(), dict(solver.last_stats))
+        if narrow and kind == "khosla":
+            assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v.copy(), maximize=maximize)
+        solver.solve(z, maximize, None)                             # resident CSR again: same mirror, same results
+        assert np.array_equal(z.person_to_object, first[0]) and np.array_equal(solver.prices(), first[2])
+        out.append(first)
+        if narrow:
+            w = v + 0.25                                            # not u16: the next upload must drop the mirror
+            solver.load_csr(n, m, rp, c, w.copy())
+            solver.solve(z, maximize, None)
+            assert solver.last_upload()[1] == 4 and solver.scan_value_bytes() == 8
+            ref, zr = gpu_solve(sla, cls_name, n, m, rp, c, w.copy(), maximize=maximize, options={"narrow_upload": 0})
+            assert np.array_equal(z.person_to_object, zr.person_to_object) and np.array_equal(solver.prices(), ref.prices())
+    for x, y in zip(out[0][:3], out[1][:3]):
+        assert np.array_equal(x, y)
+    for key in ("num_unassigned", "nits", "nreductions", "rounds", "bids", "bid_arcs", "dropped", "values_negated", "eps"):
+        assert out[0][3][key] == out[1][3][key], key
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
 def test_u16_index_type(sla, oracle, kind, cls_name):
     rng = np.random.default_rng(3)
     n, m, k = 300, 300 if kind == "forward" else 400, 6
