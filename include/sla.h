@@ -166,6 +166,14 @@ int sla_generate_device_shard(sla_ctx *ctx, uint32_t global_rows, uint32_t num_c
                               uint32_t row_count);
 int sla_generate_host(uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed, uint32_t value_lo,
                       uint32_t value_hi, int planted, uint32_t *row_ptr, uint32_t *column_indices, double *values);
+/* Same generator, more knobs: value_dist 0 = uniform integers in [value_lo, value_hi), 1 = floor((hi - lo) * Beta(3,3) + lo)
+ * -- the values of the reference's asymmetric bench, floor(700 * Beta(3,3) + 300) (benches/benchmark.rs:60,73); rows
+ * [row_begin, row_begin + row_count) of the global instance with row_ptr local to that block (one rank's shard);
+ * `threads` host threads.  Both host generators are also exported by libsla_host.so, which is built with g++ and maps no
+ * CUDA library (CPU-only processes: the reference arm of bench.py, oracle tests). */
+int sla_generate_host_ex(uint32_t global_rows, uint32_t num_cols, uint32_t k, uint64_t seed, uint32_t value_lo,
+                         uint32_t value_hi, int planted, int value_dist, uint32_t row_begin, uint32_t row_count, int threads,
+                         uint32_t *row_ptr, uint32_t *column_indices, double *values);
 
 /* ---- solves.  eps / start_eps: NaN means None; max_iterations: 0 means None (100000, symmetric.rs:190).
  *      Output pointers are host memory (any may be NULL: the result then stays resident and can be fetched

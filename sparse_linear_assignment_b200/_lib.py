@@ -13,6 +13,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libsla_b200.so")
+HOST_LIB_PATH = os.path.join(_PKG, "libsla_host.so")   # host-only entry points (the instance generator), no CUDA
 CSRC = os.path.join(_PKG, "csrc")
 INCLUDE = os.path.join(_ROOT, "include")
 
@@ -22,7 +23,7 @@ ALGO_KHOSLA, ALGO_FORWARD = 0, 1
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 
@@ -73,7 +74,21 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
             "-o", LIB_PATH, os.path.join(CSRC, "sla_api.cu")]
         subprocess.run(cmd, check=True)
+    build_host_library(force)
     return LIB_PATH
+
+
+def build_host_library(force: bool = False) -> str:
+    """Compile csrc/sla_host.cpp into libsla_host.so with plain g++: the host-only entry points of include/sla.h."""
+    srcs = [os.path.join(CSRC, f) for f in ("sla_host.cpp", "sla_host_impl.h", "synth.h")] + [os.path.join(INCLUDE, "sla.h")]
+    stale = force or not os.path.exists(HOST_LIB_PATH)
+    if not stale:
+        t = os.path.getmtime(HOST_LIB_PATH)
+        stale = any(os.path.getmtime(s) > t for s in srcs)
+    if stale:
+        gxx = shutil.which("g++") or "g++"
+        subprocess.run([gxx, "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", HOST_LIB_PATH, srcs[0]], check=True)
+    return HOST_LIB_PATH
 
 
 _u32p = C.POINTER(C.c_uint32)
@@ -104,6 +119,8 @@ SIGNATURES = {
                                             C.c_int, C.c_uint32, C.c_uint32]),
     "sla_generate_host": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
                                     _vp, _vp, _vp]),
+    "sla_generate_host_ex": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
+                                       C.c_int, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp]),
     "sla_khosla_solve": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp, _vp, C.POINTER(SlaStats)]),
     "sla_forward_solve": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_uint32, _vp, _vp, _vp,
                                     C.POINTER(SlaStats)]),
@@ -147,6 +164,23 @@ def load() -> C.CDLL:
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+_host_lib = None
+
+
+def load_host() -> C.CDLL:
+    """Load libsla_host.so (g++-built, no CUDA): the synthetic instance generator for CPU-only processes."""
+    global _host_lib
+    if _host_lib is None:
+        lib = C.CDLL(build_host_library())
+        for name in ("sla_generate_host", "sla_generate_host_ex"):
+            res, args = SIGNATURES[name]
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _host_lib = lib
+    return _host_lib
 
 
 def check(ctx, rc: int) -> None:

@@ -15,8 +15,11 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost a few ns unless a profiler is attached
+
 #include "../../include/sla.h"
 #include "sla_kernels.cuh"
+#include "sla_host_impl.h"
 
 using namespace sla;
 
@@ -24,6 +27,15 @@ using namespace sla;
 namespace {
 
 thread_local std::string g_create_error;
+
+// NVTX ranges around the phases of the path -- the device-side counterpart of the reference's `trace!` hooks
+// (ksparse.rs:182,189-190, symmetric.rs:406-407): upload, solve, the graph launches inside it, download.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct GraphSlot {
     cudaGraphExec_t exec = nullptr;
@@ -733,6 +745,7 @@ int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz)
 int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double start_eps_in, uint32_t max_iterations,
                  uint32_t* h_p2o, uint32_t* h_o2p, double* h_prices, sla_stats* stats) {
     if (!ctx) return SLA_ERR_INVALID;
+    NvtxRange nvtx_solve(algo == SLA_ALGO_FORWARD ? "sla_forward_solve" : "sla_khosla_solve");
     WorkerJoinGuard join_guard{ctx};
     if (!ctx->has_csr) return fail(ctx, SLA_ERR_STATE, "solve called before a CSR was uploaded");
     CU(cudaSetDevice(ctx->device));
@@ -836,12 +849,16 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
         bool first = true;
         while (!done) {
             cudaGraphExec_t exec = exec_first;
+            const bool first_graph = first;
             if (!first) {
                 if (!exec_next && (rc = get_graph(ctx, forward, false, &exec_next))) return rc;
                 exec = exec_next;
             }
             first = false;
-            CU(cudaGraphLaunch(exec, ctx->stream));
+            {
+                NvtxRange nvtx_graph(first_graph ? "super-rounds graph (first)" : "super-rounds graph (continuation)");
+                CU(cudaGraphLaunch(exec, ctx->stream));
+            }
             graph_launches += 1;
             if (small_dl) {
                 // small results ride behind every graph launch into page-locked staging: when the poll below reports
@@ -948,6 +965,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
         if (h_o2p) memcpy(h_o2p, ctx->h_dl + dl_o2p, (size_t)M * 4);
         if (h_prices) memcpy(h_prices, ctx->h_dl + dl_prices, (size_t)M * 8);
     } else {
+        NvtxRange nvtx_dl("download solution");
         if (h_p2o) CU(cudaMemcpyAsync(h_p2o, ctx->d_p2o, (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (h_o2p) CU(cudaMemcpyAsync(h_o2p, ctx->d_o2p, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (h_prices) CU(cudaMemcpyAsync(h_prices, ctx->d_prices, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1115,6 +1133,7 @@ bool stage_cols(const uint32_t* cols, uint32_t* stage, uint64_t nnz, uint32_t nu
 
 int upload_small(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* row_ptr, const uint32_t* column_indices,
                  double* values, uint64_t nnz, bool negate_host) {
+    NvtxRange nvtx_up("upload CSR (small: host statistics + staged H2D)");
     const size_t b_rp = (((size_t)num_rows + 1) * 4 + 15) & ~(size_t)15, b_cols = ((size_t)nnz * 4 + 15) & ~(size_t)15;
     int rc = small_block(ctx, b_rp + b_cols + (size_t)nnz * 8);
     if (rc) return rc;
@@ -1202,6 +1221,7 @@ int check_shape(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz
 // upload / destroy call on this context returns.  The device always receives the ORIGINAL values.
 int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint32_t* row_ptr, const uint32_t* column_indices,
                  double* values, uint64_t nnz, bool negate, int threads) {
+    NvtxRange nvtx_up("upload CSR (large: narrow staging + H2D)");
     const size_t total = (size_t)nnz;
     const bool dbg = getenv("SLA_DEBUG_UPLOAD") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
@@ -1616,13 +1636,8 @@ int sla_upload_csr_device(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, co
 
 static int make_spec(sla_ctx* ctx, sla_synth::Spec* s, uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed,
                      uint32_t value_lo, uint32_t value_hi, int planted) {
-    if (k == 0 || k > num_cols || (planted && num_cols < 2 && k > 1))
-        return fail(ctx, SLA_ERR_INVALID, "k must be in [1, num_cols]");
-    if (!(value_hi > value_lo)) return fail(ctx, SLA_ERR_INVALID, "value_hi must be > value_lo");
-    if ((uint64_t)num_rows * k >= 0xFFFFFFFFull) return fail(ctx, SLA_ERR_INVALID, "num_rows * k must be < u32::MAX");
-    s->num_rows = num_rows; s->num_cols = num_cols; s->k = k; s->seed = seed;
-    s->value_lo = value_lo; s->value_hi = value_hi; s->planted = planted ? 1u : 0u;
-    sla_synth::finish_spec(*s);
+    if (sla_hostgen::make_spec(s, num_rows, num_cols, k, seed, value_lo, value_hi, planted, 0))
+        return fail(ctx, SLA_ERR_INVALID, "generator arguments: k in [1, num_cols], value_hi > value_lo, num_rows * k < u32::MAX");
     return SLA_OK;
 }
 
@@ -1657,21 +1672,6 @@ int sla_generate_device_shard(sla_ctx* ctx, uint32_t global_rows, uint32_t num_c
     return finish_csr(ctx, row_count, num_cols, nnz);
 }
 
-int sla_generate_host(uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed, uint32_t value_lo,
-                      uint32_t value_hi, int planted, uint32_t* row_ptr, uint32_t* column_indices, double* values) {
-    if (!row_ptr || !column_indices || !values) return SLA_ERR_INVALID;
-    sla_synth::Spec s;
-    int rc = make_spec(nullptr, &s, num_rows, num_cols, k, seed, value_lo, value_hi, planted);
-    if (rc) return rc;
-    for (uint32_t r = 0; r < num_rows; ++r) {
-        const size_t off = (size_t)r * k;
-        sla_synth::make_row(s, r, column_indices + off, values + off);
-        row_ptr[r] = (uint32_t)off;
-    }
-    row_ptr[num_rows] = num_rows * k;
-    return SLA_OK;
-}
-
 int sla_khosla_solve(sla_ctx* ctx, int maximize, double eps, uint32_t* person_to_object, uint32_t* object_to_person,
                      double* prices, sla_stats* stats) {
     return solve_common(ctx, SLA_ALGO_KHOSLA, maximize, eps, NAN, 0, person_to_object, object_to_person, prices, stats);
@@ -1686,6 +1686,7 @@ int sla_forward_solve(sla_ctx* ctx, int maximize, double eps, double start_eps, 
 int sla_download_solution(sla_ctx* ctx, uint32_t* person_to_object, uint32_t* object_to_person, double* prices) {
     if (!ctx) return SLA_ERR_INVALID;
     if (!ctx->has_solution) return fail(ctx, SLA_ERR_STATE, "no resident solution");
+    NvtxRange nvtx_dl("sla_download_solution");
     CU(cudaSetDevice(ctx->device));
     if (person_to_object)
         CU(cudaMemcpyAsync(person_to_object, ctx->d_p2o, (size_t)ctx->n_rows * 4, cudaMemcpyDeviceToHost, ctx->stream));

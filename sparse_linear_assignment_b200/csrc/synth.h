@@ -43,7 +43,26 @@ struct Spec {
     uint32_t value_lo, value_hi;
     uint32_t planted;        // 0 / 1
     uint32_t perm_a, perm_b; // planted column of row i = (perm_a * i + perm_b) mod num_rows
+    uint32_t value_dist;     // 0: uniform integers in [value_lo, value_hi); 1: floor((hi - lo) * Beta(3,3) + lo), the
+                             // reference's asymmetric bench values floor(700 * Beta(3,3) + 300) (benches/benchmark.rs:60,73)
 };
+
+// Uniform double in [0, 1) from the top 53 bits.
+SLA_HD double unit(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); }
+
+// Beta(3,3) variate: the median (3rd order statistic) of five independent uniforms is exactly Beta(3, 3).
+SLA_HD double beta33(uint64_t seed, uint64_t row, uint64_t slot) {
+    double u[5];
+    for (int t = 0; t < 5; ++t) u[t] = unit(draw(seed, 3 + (uint64_t)t, row, slot));
+    // partial selection: two passes of a bubble pass leave the two largest at the end; the max of the rest is the median
+    for (int pass = 0; pass < 2; ++pass)
+        for (int t = 0; t + 1 < 5 - pass; ++t)
+            if (u[t] > u[t + 1]) { const double x = u[t]; u[t] = u[t + 1]; u[t + 1] = x; }
+    double m = u[0];
+    if (u[1] > m) m = u[1];
+    if (u[2] > m) m = u[2];
+    return m;
+}
 
 SLA_HD uint32_t planted_col(const Spec& s, uint32_t row) {
     return (uint32_t)(((uint64_t)s.perm_a * row + s.perm_b) % s.num_rows);
@@ -75,8 +94,15 @@ SLA_HD void make_row(const Spec& s, uint32_t row, uint32_t* out_cols, double* ou
         out_cols[b] = x;
     }
     const uint32_t span = s.value_hi - s.value_lo;
-    for (uint32_t t = 0; t < k; ++t)
-        out_vals[t] = (double)(s.value_lo + below(draw(s.seed, 2, row, t), span));
+    for (uint32_t t = 0; t < k; ++t) {
+        if (s.value_dist == 1u) {
+            uint32_t x = (uint32_t)((double)span * beta33(s.seed, row, t));
+            if (x >= span) x = span - 1u;
+            out_vals[t] = (double)(s.value_lo + x);
+        } else {
+            out_vals[t] = (double)(s.value_lo + below(draw(s.seed, 2, row, t), span));
+        }
+    }
 }
 
 SLA_HD uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }

@@ -466,6 +466,17 @@ class AuctionSolver:
         th.start()
         return th, True
 
+    def _check_solve(self, ctx, rc):
+        """Raises on a failed solve.  A failure (timeout_s, CUDA error, safety round limit) can come after the device
+        has already applied the sign normalisation and the upload's workers have negated the host copy, so both sides
+        are consistent; only the marker that the *next* solve's normalisation was pre-applied must not survive, or
+        every later solve would expect a flip the device no longer reports."""
+        try:
+            _lib.check(ctx, rc)
+        except SlaError:
+            self._pre_negated = False
+            raise
+
     def _finish(self, solution: AuctionSolution, stats: SlaStats, p2o, o2p, negation=(None, None)):
         th, flip = negation
         if th is not None:
@@ -575,7 +586,7 @@ class KhoslaSolver(AuctionSolver):
                                           p2o.ctypes.data, o2p.ctypes.data, None, C.byref(st))
         if neg[0] is not None:
             neg[0].join()
-        _lib.check(ctx, rc)
+        self._check_solve(ctx, rc)
         self._prices_on_device = True
         self._finish(solution, st, p2o, o2p, neg)
 
@@ -613,7 +624,7 @@ class ForwardAuctionSolver(AuctionSolver):
                                            p2o.ctypes.data, o2p.ctypes.data, None, C.byref(st))
         if neg[0] is not None:
             neg[0].join()
-        _lib.check(ctx, rc)
+        self._check_solve(ctx, rc)
         self._prices_on_device = True
         self._finish(solution, st, p2o, o2p, neg)
         self.nreductions = int(st.nreductions)
