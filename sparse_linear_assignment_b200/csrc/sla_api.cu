@@ -48,8 +48,10 @@ struct GraphSlot {
     uint32_t tail_smem_bytes = 0;
     uint32_t tail_max = 0;
     bool khosla_phases = false;
+    bool zero_first = false;
     size_t l2_bytes = 0;
     const void* vals16 = nullptr;   // u16 value mirror the regular bid kernels were captured with (nullptr: f64 values)
+    uint32_t learned_wide = 0;      // > 0: first graph of a plain Khosla solve shaped as `learned_wide` wide rounds + one tail launch
 };
 
 }  // namespace
@@ -293,6 +295,11 @@ struct sla_ctx {
     size_t l2_persist_max = 0, l2_window_max = 0;
     int opt_stream_scan = 0;   // first-round scan through the TMA pipeline (bid_stream_kernel): opt-in, measured 4 % slower
     int opt_smem_prices = 1, opt_smem_owners = 1, opt_khosla_scaling = 1;
+    int opt_prune = 1;         // bound-pruned gather in the uniform-degree scans of rounds with >= 32 Ki bidders
+    int opt_learn_shape = 1;   // plain Khosla: the first graph of a solve has as many wide rounds as the previous solve of the
+                               // same resident CSR needed, followed by one tail launch (no no-op launches in between)
+    int opt_prezero_best = 0;  // development: zero the bid words in front of every solve (the RED targets then sit in the L2)
+    uint32_t learned_wide = 0; // wide rounds of the last plain Khosla solve of the resident CSR (0: unknown)
     // tail-engine plan of the current instance (plan_tail): what is mirrored in shared memory and how many bidders fit
     bool tail_smem_prices = false;   // object prices mirrored
     uint32_t tail_own_mode = 0;      // owners mirrored: 0 no, 1 u32, 2 u16
@@ -310,6 +317,9 @@ struct sla_ctx {
     int grid_wide = 0;
 
     std::vector<sla_round_profile> profile;
+    int opt_profile_graph = 1;             // "profile": bracket each wide scan inside one small graph launch (see solve_common)
+    cudaGraphExec_t profile_exec = nullptr;
+    bool profile_graph_failed = false;
     NegPool neg;                           // host workers negating the caller's `values` (sla_upload_csr_negating)
 
     sla_batch_state* batch = nullptr;
@@ -615,15 +625,53 @@ void apply_l2_policy(sla_ctx* c) {
     cudaGetLastError();
 }
 
-int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out) {
-    GraphSlot& g = ctx->graphs[(forward ? 2 : 0) + (zero_first ? 1 : 0)];
+// The persisting-L2 window over the bid words on every kernel node of a captured graph (the stream attribute alone
+// is not relied upon for captured work).
+void window_on_kernel_nodes(const sla_ctx* ctx, cudaGraph_t graph) {
+    cudaKernelNodeAttrValue av;
+    memset(&av, 0, sizeof av);
+    if (!l2_window(ctx, &av.accessPolicyWindow)) return;
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    std::vector<cudaGraphNode_t> nodes(nn);
+    if (nn) cudaGraphGetNodes(graph, nodes.data(), &nn);
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeKernel)
+            cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &av);
+    }
+    cudaGetLastError();
+}
+
+// Plain Khosla solves (no eps-schedule) of a CSR that stays resident are deterministic: the number of wide rounds the
+// previous solve needed before the tail engine took over is the number this one needs.  The first graph of such a solve
+// is then captured as exactly that many (bid, assign) pairs followed by ONE tail launch, instead of a tail launch behind
+// every pair that returns at once (2.5 us each: cfg3 has five of them).  Every kernel still decides from the device
+// state whether it has work, so a wrong guess (another eps, another sign) costs time, never correctness: continuation
+// graphs of the default shape finish the solve.
+uint32_t learned_shape(const sla_ctx* c, bool forward, bool first_graph) {
+    if (!first_graph || forward || khosla_phases(c) || !c->opt_learn_shape || is_tail_only(c, forward)) return 0u;
+    return (c->learned_wide >= 1u && c->learned_wide <= 64u) ? c->learned_wide : 0u;
+}
+
+int graph_kernel_count(const sla_ctx* c, bool forward, bool first_graph, bool late_init) {
+    const uint32_t lw = learned_shape(c, forward, first_graph);
+    int n = lw ? (int)(2u * lw + 1u)
+               : super_rounds_for(c, forward) * kernels_per_super_round(c, forward, is_tail_only(c, forward));
+    if (late_init && first_graph) n += 1;   // first_assign_objects_kernel sits in the first graph
+    return n;
+}
+
+int get_graph(sla_ctx* ctx, bool forward, bool zero_first, bool first_graph, cudaGraphExec_t* out) {
+    GraphSlot& g = ctx->graphs[(forward ? 2 : 0) + (first_graph ? 1 : 0)];
     const uint32_t reg_key = use_regular(ctx) ? ctx->regular_k : 0u;
     const bool tail_only = is_tail_only(ctx, forward);
     const int n_super = super_rounds_for(ctx, forward);
-    if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == n_super &&
+    const uint32_t lw = learned_shape(ctx, forward, first_graph);
+    if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == n_super && g.learned_wide == lw &&
         g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices && g.tail_only == tail_only &&
         g.tail_smem_bytes == ctx->tail_smem_bytes && g.tail_max == solve_tail_max(ctx, forward) && g.khosla_phases == khosla_phases(ctx) &&
-        g.l2_bytes == ctx->l2_bytes && g.vals16 == narrow_scan_ptr(ctx)) {
+        g.l2_bytes == ctx->l2_bytes && g.vals16 == narrow_scan_ptr(ctx) && g.zero_first == zero_first) {
         *out = g.exec;
         return SLA_OK;
     }
@@ -631,25 +679,20 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     const Params p = make_params(ctx);
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    for (int r = 0; r < n_super; ++r) launch_super_round(ctx, p, forward, zero_first && r == 0, tail_only);
+    if (lw) {
+        for (uint32_t r = 0; r < lw; ++r) {
+            const bool zf = zero_first && r == 0;
+            launch_one(ctx, p, 0, zf);
+            if (zf) first_assign_objects_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p);
+            launch_one(ctx, p, 1, zf);
+        }
+        launch_one(ctx, p, 2);
+    } else {
+        for (int r = 0; r < n_super; ++r) launch_super_round(ctx, p, forward, zero_first && r == 0, tail_only);
+    }
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (e != cudaSuccess) return fail(ctx, SLA_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    {
-        cudaKernelNodeAttrValue av;
-        memset(&av, 0, sizeof av);
-        if (l2_window(ctx, &av.accessPolicyWindow)) {
-            size_t nn = 0;
-            cudaGraphGetNodes(graph, nullptr, &nn);
-            std::vector<cudaGraphNode_t> nodes(nn);
-            if (nn) cudaGraphGetNodes(graph, nodes.data(), &nn);
-            for (cudaGraphNode_t nd : nodes) {
-                cudaGraphNodeType t;
-                if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeKernel)
-                    cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &av);
-            }
-            cudaGetLastError();
-        }
-    }
+    window_on_kernel_nodes(ctx, graph);
     e = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) {
@@ -667,6 +710,8 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, cudaGraphExec_t* out)
     g.khosla_phases = khosla_phases(ctx);
     g.l2_bytes = ctx->l2_bytes;
     g.vals16 = narrow_scan_ptr(ctx);
+    g.learned_wide = lw;
+    g.zero_first = zero_first;
     *out = g.exec;
     return SLA_OK;
 }
@@ -739,7 +784,7 @@ int poll_state(sla_ctx* ctx) {
     return SLA_OK;
 }
 
-int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz);
+int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz, bool build_mirror = false);
 
 // The solve driver shared by both algorithms.
 int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double start_eps_in, uint32_t max_iterations,
@@ -805,6 +850,8 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
         }
         s.start_opt = start_opt ? 1u : 0u;
     }
+    // every eps of the solve is >= 0 (later phases only multiply by 0.15): prices stay >= 0, the gathering scan may prune
+    s.prune_ok = (ctx->opt_prune && s.eps >= 0.0 && s.target_eps >= 0.0) ? 1u : 0u;
     *ctx->h_state = s;
 
     const Params p = make_params(ctx);
@@ -818,7 +865,8 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_state, ctx->h_state, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
     if (late_init) {
-        if (ctx->best_dirty) CU(cudaMemsetAsync(ctx->d_best, 0, (size_t)M * sizeof(unsigned long long), ctx->stream));
+        if (ctx->best_dirty || ctx->opt_prezero_best)
+            CU(cudaMemsetAsync(ctx->d_best, 0, (size_t)M * sizeof(unsigned long long), ctx->stream));
     } else {
         init_solve_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, N, M, ctx->best_dirty ? 1 : 0);
         launches += 1;
@@ -844,14 +892,14 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
     };
     if (use_graph) {
         cudaGraphExec_t exec_first = nullptr, exec_next = nullptr;
-        int rc = get_graph(ctx, forward, ctx->opt_skip_zero != 0, &exec_first);
+        int rc = get_graph(ctx, forward, ctx->opt_skip_zero != 0, true, &exec_first);
         if (rc) return rc;
         bool first = true;
         while (!done) {
             cudaGraphExec_t exec = exec_first;
             const bool first_graph = first;
             if (!first) {
-                if (!exec_next && (rc = get_graph(ctx, forward, false, &exec_next))) return rc;
+                if (!exec_next && (rc = get_graph(ctx, forward, false, false, &exec_next))) return rc;
                 exec = exec_next;
             }
             first = false;
@@ -869,8 +917,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
                 if (h_prices) CU(cudaMemcpyAsync(ctx->h_dl + dl_prices, ctx->d_prices, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream));
                 CU(cudaEventRecord(ctx->ev[2], ctx->stream));
             }
-            launches += (uint32_t)(super_rounds_for(ctx, forward) * kernels_per_super_round(ctx, forward, is_tail_only(ctx, forward)));
-            if (late_init && graph_launches == 1) launches += 1;   // first_assign_objects_kernel sits in the first graph
+            launches += (uint32_t)graph_kernel_count(ctx, forward, first_graph, late_init);
             if ((rc = poll_state(ctx))) return rc;
             done = ctx->h_state->done != 0;
             if (!done && timed_out()) return fail(ctx, SLA_ERR_STATE, "solve exceeded the wall-clock guard (timeout_s)");
@@ -882,16 +929,44 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
         bool first = true;
         while (!done) {
             const bool wide = !prev.done && prev.qlen[prev.cur] > prev.tail_max;
-            if (ctx->opt_profile) {
-                profile_fence_kernel<<<1, 32, 0, ctx->stream>>>();
-                CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-            }
-            launch_one(ctx, p, 0, first && ctx->opt_skip_zero != 0);
             // "profile_repeat" (development): the scan is idempotent (same slots, same maxima), so it can be launched
             // several times between the two events to separate its duration from the event overhead
-            if (ctx->opt_profile && wide && first)
-                for (int r = 1; r < ctx->opt_profile_repeat; ++r) launch_one(ctx, p, 0, first && ctx->opt_skip_zero != 0);
-            if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+            const int reps = (ctx->opt_profile && wide && first) ? ctx->opt_profile_repeat : 1;
+            bool bracketed = false;
+            if (ctx->opt_profile && ctx->opt_profile_graph && wide) {
+                // The bracket as ONE graph launch -- fence kernel, event-record node, the scan, event-record node -- so
+                // that the two time stamps are taken by the device's own node-to-node sequencing (what a scan inside the
+                // solve graph sees) and not across two host-side launch latencies.  Any failure falls back to the eager bracket.
+                cudaGraph_t pg = nullptr;
+                if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    profile_fence_kernel<<<1, 32, 0, ctx->stream>>>();
+                    cudaError_t e1 = cudaEventRecordWithFlags(ctx->ev[1], ctx->stream, cudaEventRecordExternal);
+                    for (int r = 0; r < reps; ++r) launch_one(ctx, p, 0, first && ctx->opt_skip_zero != 0);
+                    cudaError_t e2 = cudaEventRecordWithFlags(ctx->ev[2], ctx->stream, cudaEventRecordExternal);
+                    cudaError_t e3 = cudaStreamEndCapture(ctx->stream, &pg);
+                    if (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && pg) {
+                        window_on_kernel_nodes(ctx, pg);
+                        if (ctx->profile_exec) { cudaGraphExecDestroy(ctx->profile_exec); ctx->profile_exec = nullptr; }
+                        if (cudaGraphInstantiate(&ctx->profile_exec, pg, 0) == cudaSuccess &&
+                            cudaGraphLaunch(ctx->profile_exec, ctx->stream) == cudaSuccess)
+                            bracketed = true;
+                    }
+                    if (pg) cudaGraphDestroy(pg);
+                }
+                if (!bracketed) {
+                    cudaGetLastError();
+                    if (!ctx->profile_graph_failed) fprintf(stderr, "[sla] profile: graph bracket unavailable, using the eager bracket\n");
+                    ctx->profile_graph_failed = true;
+                }
+            }
+            if (!bracketed) {
+                if (ctx->opt_profile) {
+                    profile_fence_kernel<<<1, 32, 0, ctx->stream>>>();
+                    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+                }
+                for (int r = 0; r < reps; ++r) launch_one(ctx, p, 0, first && ctx->opt_skip_zero != 0);
+                if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+            }
             const bool late_now = first && late_init;
             if (late_now) {
                 first_assign_objects_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p);
@@ -902,7 +977,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
             if (ctx->opt_profile) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
             launches += 2;
             if (ctx->opt_profile) {
-                int rc = poll_state(ctx);   // state after the wide pair, before control step A
+                int rc = poll_state(ctx);   // state after the wide pair and its control step A
                 if (rc) return rc;
                 if (wide) {
                     sla_round_profile r;
@@ -928,9 +1003,9 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
                 if (ctx->h_state->tail_rounds > mid.tail_rounds) {
                     sla_round_profile r;
                     memset(&r, 0, sizeof r);
-                    r.round = (uint32_t)(mid.rounds + (wide ? 1 : 0));
+                    r.round = (uint32_t)mid.rounds;            // (control step A of the wide round has already run)
                     r.engine = 1;
-                    r.bidders = wide ? mid.qlen[mid.cur ^ 1u] : mid.qlen[mid.cur];
+                    r.bidders = mid.qlen[mid.cur];
                     r.rounds_covered = (uint32_t)(ctx->h_state->tail_rounds - mid.tail_rounds);
                     r.arcs = ctx->h_state->bid_arcs - mid.bid_arcs;
                     cudaEventElapsedTime(&r.bid_ms, ctx->ev[1], ctx->ev[2]);
@@ -958,6 +1033,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
     if (f.safety_rounds_left <= 1) return fail(ctx, SLA_ERR_STATE, "safety round limit reached");
     ctx->best_dirty = false;
     ctx->has_solution = true;
+    if (!forward && !khosla_phases(ctx)) ctx->learned_wide = (uint32_t)(f.wide_rounds < 65u ? f.wide_rounds : 0u);
 
     if (small_dl) {
         // already downloaded behind the last graph launch (events 1 and 2 recorded there, completed by the poll's sync)
@@ -1001,9 +1077,9 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
 }
 
 // After the three CSR arrays are resident: statistics + validation (solver.rs:232-243).
-int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz) {
+int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz, bool build_mirror) {
     DevCsrStats init;
-    init.min_key = ~0ull; init.max_key = 0ull; init.bad_cols = 0; init.bad_rows = 0; init.irregular_rows = 0;
+    init.min_key = ~0ull; init.max_key = 0ull; init.bad_cols = 0; init.bad_rows = 0; init.irregular_rows = 0; init.not_u16 = 0;
     *ctx->h_csr_stats = init;
     CU(cudaMemcpyAsync(ctx->d_csr_stats, ctx->h_csr_stats, sizeof(DevCsrStats), cudaMemcpyHostToDevice, ctx->stream));
     csr_stats_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(ctx->d_row_ptr, ctx->d_cols, ctx->d_vals, num_rows,
@@ -1035,8 +1111,22 @@ int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz)
         while (l < 32 && (uint32_t)(l * 8) < ctx->regular_k) l *= 2;
         ctx->lpr8 = l;
     }
+    // all values are u16 integers and no u16 copy came with the upload (CSR generated in HBM / handed over in device
+    // memory): build the mirror the uniform-degree scans read (6 instead of 12 bytes per arc)
+    if (build_mirror && ctx->regular_k && ctx->opt_narrow_scan && ctx->h_csr_stats->not_u16 == 0 && nnz >= ((uint64_t)1 << 20)) {
+        const size_t need = (size_t)nnz * 2u;
+        if (need > ctx->d_narrow_cap) {
+            if (ctx->d_narrow) { cudaFree(ctx->d_narrow); ctx->d_narrow = nullptr; ctx->d_narrow_cap = 0; }
+            if (cudaMalloc(&ctx->d_narrow, need) == cudaSuccess) ctx->d_narrow_cap = need; else cudaGetLastError();
+        }
+        if (need <= ctx->d_narrow_cap) {
+            narrow_mirror_kernel<<<ctx->num_sms * 8, kWideThreads, 0, ctx->stream>>>(ctx->d_vals, (uint16_t*)ctx->d_narrow, (size_t)nnz);
+            ctx->vals16_valid = true;
+        }
+    }
     ctx->has_csr = true;
     ctx->has_solution = false;
+    ctx->learned_wide = 0;
     plan_tail(ctx);
     apply_l2_policy(ctx);
     return SLA_OK;
@@ -1196,6 +1286,7 @@ int upload_small(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
     }
     ctx->has_csr = true;
     ctx->has_solution = false;
+    ctx->learned_wide = 0;
     plan_tail(ctx);
     apply_l2_policy(ctx);
     return SLA_OK;
@@ -1477,6 +1568,7 @@ void sla_ctx_destroy(sla_ctx* ctx) {
     sla_batch_free(ctx);
     sla_part_free(ctx);
     drop_graphs(ctx);
+    if (ctx->profile_exec) cudaGraphExecDestroy(ctx->profile_exec);
     cudaFree(ctx->d_row_ptr); cudaFree(ctx->d_cols); cudaFree(ctx->d_vals); cudaFree(ctx->d_prices);
     cudaFree(ctx->d_p2o); cudaFree(ctx->d_o2p); cudaFree(ctx->d_best); cudaFree(ctx->d_queue[0]);
     cudaFree(ctx->d_queue[1]); cudaFree(ctx->d_slot_obj); cudaFree(ctx->d_slot_bid); cudaFree(ctx->d_state);
@@ -1521,10 +1613,19 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
         plan_tail(ctx);
     } else if (k == "khosla_scaling") {
         ctx->opt_khosla_scaling = value ? 1 : 0;
+    } else if (k == "prune_gather") {
+        ctx->opt_prune = value ? 1 : 0;
+    } else if (k == "learn_shape") {
+        ctx->opt_learn_shape = value ? 1 : 0;
+        ctx->learned_wide = 0;
+    } else if (k == "prezero_best") {
+        ctx->opt_prezero_best = value ? 1 : 0;
     } else if (k == "regular") {
         ctx->opt_regular = value ? 1 : 0;
     } else if (k == "timeout_s") {
         ctx->opt_timeout_s = (double)value;
+    } else if (k == "profile_graph") {
+        ctx->opt_profile_graph = value ? 1 : 0;
     } else if (k == "profile_repeat") {
         if (value < 1 || value > 64) return fail(ctx, SLA_ERR_INVALID, "profile_repeat must be in [1, 64]");
         ctx->opt_profile_repeat = (int)value;
@@ -1631,7 +1732,7 @@ int sla_upload_csr_device(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, co
     CU(cudaMemcpyAsync(ctx->d_row_ptr, d_row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_cols, d_column_indices, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_vals, d_values, (size_t)nnz * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    return finish_csr(ctx, num_rows, num_cols, nnz);
+    return finish_csr(ctx, num_rows, num_cols, nnz, true);
 }
 
 static int make_spec(sla_ctx* ctx, sla_synth::Spec* s, uint32_t num_rows, uint32_t num_cols, uint32_t k, uint64_t seed,
@@ -1652,7 +1753,7 @@ int sla_generate_device(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint
     CU(cudaSetDevice(ctx->device));
     if ((rc = ensure_capacity(ctx, num_rows, num_cols, nnz))) return rc;
     generate_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(s, 0u, num_rows, ctx->d_row_ptr, ctx->d_cols, ctx->d_vals);
-    return finish_csr(ctx, num_rows, num_cols, nnz);
+    return finish_csr(ctx, num_rows, num_cols, nnz, true);
 }
 
 int sla_generate_device_shard(sla_ctx* ctx, uint32_t global_rows, uint32_t num_cols, uint32_t k, uint64_t seed,
@@ -1669,7 +1770,7 @@ int sla_generate_device_shard(sla_ctx* ctx, uint32_t global_rows, uint32_t num_c
     if ((rc = ensure_capacity(ctx, row_count, num_cols, nnz))) return rc;
     generate_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(s, row_begin, row_count, ctx->d_row_ptr, ctx->d_cols,
                                                                      ctx->d_vals);
-    return finish_csr(ctx, row_count, num_cols, nnz);
+    return finish_csr(ctx, row_count, num_cols, nnz, true);
 }
 
 int sla_khosla_solve(sla_ctx* ctx, int maximize, double eps, uint32_t* person_to_object, uint32_t* object_to_person,

@@ -60,7 +60,10 @@ struct DevState {
     uint32_t max_iterations;
     uint32_t tail_round_cap; // rounds one tail launch may run before handing control back to the host
     uint32_t kscale;         // Khosla rounds currently run under the eps-schedule (square instances)
-    uint32_t cold_pad[3];
+    uint32_t assign_ticket;  // blocks of assign_wide_kernel that have finished (the last one runs control step A)
+    uint32_t prune_ok;       // prices are known to be >= 0 for the whole solve (eps >= 0): profit <= value, so the
+                             // gathering scan may skip arcs whose value is below a proven bound on the second-best profit
+    uint32_t wide_ctl_done;  // control step A of this super-round already ran (in assign_wide_kernel's last block)
     unsigned long long rounds, bids, bid_arcs, wide_rounds, tail_rounds;
     unsigned long long safety_rounds_left;
     unsigned long long dbg[24];  // cycle counters of the tail engine when built with -DSLA_TAIL_TIMING
@@ -94,7 +97,15 @@ struct DevCsrStats {
     unsigned long long bad_cols;           // arcs whose column index is >= num_cols
     unsigned long long bad_rows;           // rows whose extents are not monotone / exceed nnz
     unsigned long long irregular_rows;     // rows whose degree differs from row 0's
+    unsigned long long not_u16;            // values that are not integers in [0, 65535] with a clear sign bit
 };
+
+// true when (double)(uint16_t)x reproduces x bit for bit
+__device__ __forceinline__ bool is_u16_value(double x) {
+    if (!(x >= 0.0 && x <= 65535.0)) return false;            // also rejects NaN
+    const uint32_t q = (uint32_t)x;
+    return __double_as_longlong((double)q) == __double_as_longlong(x);   // rejects fractions and -0.0
+}
 
 // Every buffer a kernel needs, passed by value.  Pointers only: sizes, sign and all per-solve scalars live in
 // the device-resident DevState, so a captured graph stays valid across uploads and solves until a buffer is

@@ -88,11 +88,16 @@ __global__ void __launch_bounds__(kWideThreads) bid_wide_kernel(const Params p) 
 
 // Regular-CSR variant (every row has exactly K arcs, K % 8 == 0: all of BASELINE.json's configs): no row-extent
 // loads (a = i * K), no masking, 8 arcs per lane per step through 256-bit loads.  LPR8 lanes share one row.
+#ifndef SLA_PRUNE_MIN_QUEUE
+#define SLA_PRUNE_MIN_QUEUE 32768
+#endif
+constexpr uint32_t kPruneMinQueue = SLA_PRUNE_MIN_QUEUE;   // bidders from which the gathering scan prunes by value bound
+
 template <int LPR8, int MODE, bool NARROW>
 __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t qlen, const bool identity,
                                                  const uint32_t* __restrict__ queue, const uint32_t algo, const double eps,
                                                  const double threshold, const uint32_t pbits, const uint32_t sign_flip,
-                                                 const uint32_t K, const uint32_t person_base) {
+                                                 const uint32_t K, const uint32_t person_base, const bool prune) {
     constexpr int GROUPS_PER_BLOCK = kWideThreads / LPR8;
     const int lane = threadIdx.x % LPR8;
     const uint32_t group = blockIdx.x * GROUPS_PER_BLOCK + threadIdx.x / LPR8;
@@ -155,6 +160,120 @@ __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t
                         p.slot_bid[q] = r.bid;
                         if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i[u] + person_base, pbits));
                     }
+                }
+            }
+        }
+    } else if (MODE == PRICE_LDG && prune && K <= 8u * LPR8) {
+        // ---- bound-pruned gather ------------------------------------------------------------------------------------
+        // Prices never go below zero (they start at 0 and every winning bid is >= old price + eps, eps >= 0: DevState::
+        // prune_ok), so profit = value - price <= value.  Each lane first gathers the prices of its two most valuable
+        // arcs only; the second largest of the 2 x LPR8 profits found that way, L, is a lower bound on the row's true
+        // second-best profit.  An arc with value < L has profit < L <= second <= best: it can change neither the best
+        // arc, nor the second-best profit, nor a tie (ties need equality) -- its price is not fetched.  Every other arc
+        // is gathered and goes through the unchanged choice rule in position order, so the choice is the reference's
+        // bit for bit (ksparse.rs:199-214, symmetric.rs:361-376).  What changes is the number of scattered 8-byte
+        // gathers per row: 2 per lane plus the few arcs that can still matter, instead of all K -- the gathers (one L1
+        // wavefront each), not the CSR stream, bound the unpruned scan.
+        const uint32_t keyflip = sign_flip ? 0xFFFFu : 0u;
+        for (uint32_t base = 0; base < qlen; base += ngroups) {
+            if (base + warp_group0 >= qlen) break;   // warp-uniform: the whole warp is past the end
+            const uint32_t q = base + group;
+            const bool valid = q < qlen;
+            const uint32_t off = 8u * (uint32_t)lane;
+            const bool has = valid && off < K;
+            uint32_t i = 0, cj[8];
+            double vv[8];
+            int key[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { cj[t] = 0u; vv[t] = neg_inf(); key[t] = (int)0x80000000; }
+            uint32_t g = 0;
+            if (valid) i = identity ? q : __ldg(queue + q);
+            if (has) {
+                g = i * K + off;
+                ld_stream_u8(p.cols + g, cj);
+                if (NARROW) {
+                    const uint4 w = ld_stream_u16x8(p.vals16 + g);
+                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const uint32_t x = (t & 1) ? (ww[t >> 1] >> 16) : (ww[t >> 1] & 0xFFFFu);
+                        const double d = u16_to_f64(x);
+                        vv[t] = __hiloint2double(__double2hiint(d) ^ (int)sign_flip, __double2loint(d));
+                        key[t] = (int)(x ^ keyflip);                 // exact order of the effective values
+                    }
+                } else {
+                    double raw[8];
+                    ld_stream_d4(p.vals + g, raw);
+                    ld_stream_d4(p.vals + g + 4, raw + 4);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int hi = __double2hiint(raw[t]) ^ (int)sign_flip;
+                        vv[t] = __hiloint2double(hi, __double2loint(raw[t]));
+                        key[t] = hi ^ ((hi >> 31) & 0x7FFFFFFF);     // order of the high words: any two probes give a valid bound
+                    }
+                }
+            }
+            // the lane's two probes: (approximately) its two most valuable arcs
+            int b1 = (int)0x80000000, b2 = (int)0x80000000;
+            uint32_t i1 = 0u, i2 = 1u, c1 = cj[0], c2 = cj[1];
+            double v1 = vv[0], v2 = vv[1];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const bool gt = key[t] > b1 || t == 0, gs = key[t] > b2 || t <= 1;
+                i2 = gt ? i1 : (gs ? (uint32_t)t : i2);
+                c2 = gt ? c1 : (gs ? cj[t] : c2);
+                v2 = gt ? v1 : (gs ? vv[t] : v2);
+                b2 = gt ? b1 : (gs ? key[t] : b2);
+                i1 = gt ? (uint32_t)t : i1;
+                c1 = gt ? cj[t] : c1;
+                v1 = gt ? vv[t] : v1;
+                b1 = gt ? key[t] : b1;
+            }
+            double p1 = 0.0, p2 = 0.0, hiP = neg_inf(), loP = neg_inf();
+            if (has) {
+                p1 = __ldg(p.prices + c1);
+                p2 = __ldg(p.prices + c2);
+                const double a = v1 - p1, b = v2 - p2;
+                hiP = a > b ? a : b;
+                loP = a > b ? b : a;
+            }
+#pragma unroll
+            for (int m = LPR8 / 2; m >= 1; m >>= 1) {
+                const double oh = __shfl_xor_sync(0xffffffffu, hiP, m);
+                const double ol = __shfl_xor_sync(0xffffffffu, loP, m);
+                const double mn = hiP > oh ? oh : hiP;          // the smaller of the two maxima
+                double l2 = loP > ol ? loP : ol;
+                l2 = mn > l2 ? mn : l2;
+                hiP = hiP > oh ? hiP : oh;
+                loP = l2;
+            }
+            const double bound = loP;
+            double pr[8];
+            bool use[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const bool probe = ((uint32_t)t == i1) || ((uint32_t)t == i2);
+                use[t] = has && (probe || vv[t] >= bound);
+                pr[t] = 0.0;
+                if (has && !probe && vv[t] >= bound) pr[t] = __ldg(p.prices + cj[t]);
+            }
+            Choice c;
+            choice_init(c);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const double pt = ((uint32_t)t == i1) ? p1 : (((uint32_t)t == i2) ? p2 : pr[t]);
+                choice_update(c, use[t] ? (vv[t] - pt) : neg_inf(), vv[t], g + t, cj[t]);
+            }
+            choice_group_reduce<LPR8>(c);
+            if (valid && lane == 0) {
+                const Bid r = make_bid<MODE>(c, algo, eps, threshold, p.prices);
+                if (r.dropped) {
+                    p.slot_obj[q] = SLA_DEV_NONE;
+                    my_dropped += 1;
+                } else {
+                    p.slot_obj[q] = r.obj;
+                    p.slot_bid[q] = r.bid;
+                    if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i + person_base, pbits));
                 }
             }
         }
@@ -252,7 +371,10 @@ __global__ void __launch_bounds__(kWideThreads, (MODE == PRICE_ZERO) ? (NARROW ?
     const uint32_t algo = h.algo, pbits = h.pbits, sf = h.sign_flip, K = h.regular_k;
     const double eps = h.eps, thr = h.threshold;
     const uint32_t* queue = cur ? p.queue[1] : p.queue[0];
-    bid_regular_body<LPR8, MODE, NARROW>(p, qlen, identity, queue, algo, eps, thr, pbits, sf, K, h.person_base);
+    // bound-pruned gather (bid_regular_body): two dependent gather phases instead of one, so only where the scan is
+    // throughput-bound, not for the short latency-bound rounds
+    const bool prune = (MODE == PRICE_LDG) && qlen >= kPruneMinQueue && p.st->prune_ok != 0u;
+    bid_regular_body<LPR8, MODE, NARROW>(p, qlen, identity, queue, algo, eps, thr, pbits, sf, K, h.person_base, prune);
 }
 
 // =============================================================================================================
@@ -399,6 +521,71 @@ __global__ void __launch_bounds__(kStreamThreads + 32, 2) bid_stream_kernel(cons
 }
 
 // =============================================================================================================
+// Control helpers (executed by exactly one thread)
+// =============================================================================================================
+// Queue ran empty.  Forward is finished without an eps-CS check when start_from_optimal_eps holds
+// (symmetric.rs:279-288); otherwise the ecs kernel decides.  Khosla is finished (ksparse.rs:186 loop exit) unless
+// its rounds run under the eps-schedule (square instances): then a phase in which nobody was dropped is followed by
+// the next, smaller eps (the assignment is wiped, the prices are kept, the last phase runs at exactly the caller's
+// eps), and a phase that dropped anybody -- the instance is not known to have a perfect matching, and only the plain
+// rounds define what the reference's price threshold does then -- makes the solve start over without a schedule.
+// ST is DevState (the tail engine's shared-memory copy of the block) or volatile DevState (the block in global memory,
+// read and written past the L1 by the last block of a grid-wide kernel).
+template <class ST>
+__device__ __forceinline__ void finish_if_possible(ST* st) {
+    if (st->algo == ALGO_KHOSLA) {
+        if (!st->kscale) { st->done = 1; return; }
+        if (st->dropped != 0) {
+            st->kscale = 0;
+            st->eps = st->target_eps;
+            st->dropped = 0;
+            st->action = ACTION_RESET_ALL;
+        } else if (st->eps > st->target_eps) {
+            const double e = st->eps * 0.15, te = st->target_eps;
+            st->eps = (e < te) ? te : e;
+            st->nreductions = st->nreductions + 1;
+            st->action = ACTION_RESET;
+        } else {
+            st->done = 1;
+            return;
+        }
+        st->qlen[st->cur] = st->n_rows;
+        st->identity = 1;
+    } else if (st->start_opt) {
+        st->optimal = 1;
+        st->done = 1;
+    }
+}
+
+// Control step A: account for the wide round of this super-round (if one ran) and flip the queues.
+// Returns the current queue length afterwards.
+template <class ST>
+__device__ __forceinline__ uint32_t control_after_wide(ST* st) {
+    uint32_t cur = st->cur;
+    uint32_t qlen = st->qlen[cur];
+    st->action = ACTION_NONE;
+    if (!st->done && qlen > st->tail_max) {
+        st->rounds = st->rounds + 1;
+        st->wide_rounds = st->wide_rounds + 1;
+        st->bids = st->bids + qlen;
+        if (st->regular_k) st->bid_arcs = st->bid_arcs + (unsigned long long)qlen * st->regular_k;
+        st->qlen[cur] = 0;
+        cur ^= 1u;
+        st->cur = cur;
+        qlen = st->qlen[cur];
+        st->identity = 0;
+        st->zero_prices = 0;
+        if (st->algo == ALGO_FORWARD) {
+            st->nits = st->nits + 1;
+            if (qlen > 0 && st->nits >= st->max_iterations) st->done = 1;   // symmetric.rs:326-328
+        }
+        if (st->safety_rounds_left <= 1) st->done = 1; else st->safety_rounds_left = st->safety_rounds_left - 1;
+        if (!st->done && qlen == 0) finish_if_possible(st);
+    }
+    return qlen;
+}
+
+// =============================================================================================================
 // Grid-wide assignment + queue compaction (reference src/symmetric.rs:386-463, src/ksparse.rs:229-244).
 // One thread per old queue slot; each slot yields 0 or 1 entries of the next queue (loser -> itself,
 // winner that evicts -> the evicted owner, winner of a free object or dropped person -> nothing).
@@ -502,67 +689,22 @@ __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params 
         for (uint32_t e = threadIdx.x; e < cnt; e += kWideThreads) next_queue[gbase + e] = s_emit[e];
         __syncthreads();
     }
-}
 
-// =============================================================================================================
-// Control helpers (executed by exactly one thread)
-// =============================================================================================================
-// Queue ran empty.  Forward is finished without an eps-CS check when start_from_optimal_eps holds
-// (symmetric.rs:279-288); otherwise the ecs kernel decides.  Khosla is finished (ksparse.rs:186 loop exit) unless
-// its rounds run under the eps-schedule (square instances): then a phase in which nobody was dropped is followed by
-// the next, smaller eps (the assignment is wiped, the prices are kept, the last phase runs at exactly the caller's
-// eps), and a phase that dropped anybody -- the instance is not known to have a perfect matching, and only the plain
-// rounds define what the reference's price threshold does then -- makes the solve start over without a schedule.
-__device__ __forceinline__ void finish_if_possible(DevState* st) {
-    if (st->algo == ALGO_KHOSLA) {
-        if (!st->kscale) { st->done = 1; return; }
-        if (st->dropped != 0) {
-            st->kscale = 0;
-            st->eps = st->target_eps;
-            st->dropped = 0;
-            st->action = ACTION_RESET_ALL;
-        } else if (st->eps > st->target_eps) {
-            double e = st->eps * 0.15;
-            st->eps = (e < st->target_eps) ? st->target_eps : e;
-            st->nreductions += 1;
-            st->action = ACTION_RESET;
-        } else {
-            st->done = 1;
-            return;
+    // Control step A (round accounting, queue flip, termination tests) by the last block to finish: every block has
+    // published its emissions (fence) before it takes its ticket, so the last one sees the complete next queue length.
+    // The block is read and written past the L1 (volatile): other blocks changed it with atomics in the L2.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t ticket = atomicAdd(&st->assign_ticket, 1u);
+        if (ticket == gridDim.x - 1u) {
+            __threadfence();
+            volatile DevState* vst = st;
+            vst->assign_ticket = 0u;
+            control_after_wide(vst);
+            vst->wide_ctl_done = 1u;
         }
-        st->qlen[st->cur] = st->n_rows;
-        st->identity = 1;
-    } else if (st->start_opt) {
-        st->optimal = 1;
-        st->done = 1;
     }
-}
-
-// Control step A: account for the wide round of this super-round (if one ran) and flip the queues.
-// Returns the current queue length afterwards.
-__device__ __forceinline__ uint32_t control_after_wide(DevState* st) {
-    uint32_t cur = st->cur;
-    uint32_t qlen = st->qlen[cur];
-    st->action = ACTION_NONE;
-    if (!st->done && qlen > st->tail_max) {
-        st->rounds += 1;
-        st->wide_rounds += 1;
-        st->bids += qlen;
-        if (st->regular_k) st->bid_arcs += (unsigned long long)qlen * st->regular_k;
-        st->qlen[cur] = 0;
-        cur ^= 1u;
-        st->cur = cur;
-        qlen = st->qlen[cur];
-        st->identity = 0;
-        st->zero_prices = 0;
-        if (st->algo == ALGO_FORWARD) {
-            st->nits += 1;
-            if (qlen > 0 && st->nits >= st->max_iterations) st->done = 1;   // symmetric.rs:326-328
-        }
-        if (st->safety_rounds_left <= 1) st->done = 1; else st->safety_rounds_left -= 1;
-        if (!st->done && qlen == 0) finish_if_possible(st);
-    }
-    return qlen;
 }
 
 // =============================================================================================================
@@ -572,7 +714,7 @@ __device__ __forceinline__ uint32_t control_after_wide(DevState* st) {
 //   * <= 32 bidders: entirely in shared memory by one warp (no global atomics, no L2 round trips);
 //   * more bidders : an open-addressing hash table in shared memory keyed by the object (atomicCAS on the key,
 //                    atomicMax on the packed word) -- still no global atomics and no L2 round trips.
-// Also hosts control step A (it is the first single-CTA kernel after the wide pair).
+// (Control step A of a wide round runs in the last block of assign_wide_kernel.)
 // =============================================================================================================
 // SPRICES: the object prices are mirrored in dynamic shared memory for the lifetime of the launch (write-through to
 // global), which removes k scattered L1 misses per bidder -- the single SM's miss throughput, not latency, is
@@ -602,7 +744,11 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     __syncthreads();
 
     if (tid == 0) {
-        const uint32_t qlen0 = control_after_wide(st);
+        // control step A of a wide round runs in assign_wide_kernel's last block; a phase action it may have set (Khosla
+        // eps-schedule: the queue ran empty) belongs to this super-round's phase kernel and must survive, any older one
+        // has been consumed
+        if (st->wide_ctl_done) st->wide_ctl_done = 0u; else st->action = ACTION_NONE;
+        const uint32_t qlen0 = st->qlen[st->cur];
         const uint32_t run = (!st->done && qlen0 > 0 && qlen0 <= st->tail_max) ? 1u : 0u;
         s_ctl[0] = run;
         s_ctl[1] = qlen0;
@@ -1147,7 +1293,7 @@ __global__ void __launch_bounds__(kWideThreads) csr_stats_kernel(const uint32_t*
                                                                  DevCsrStats* out) {
     const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long kmin = ~0ull, kmax = 0ull, bad_c = 0, bad_r = 0, irr = 0;
+    unsigned long long kmin = ~0ull, kmax = 0ull, bad_c = 0, bad_r = 0, irr = 0, n16 = 0;
     const uint32_t k0 = row_ptr[1] - row_ptr[0];
     // 4 arcs per thread and step: one 128-bit load of column indices, two of values (the arrays are 256 B-aligned)
     const unsigned long long quads = nnz / 4ull;
@@ -1163,12 +1309,15 @@ __global__ void __launch_bounds__(kWideThreads) csr_stats_kernel(const uint32_t*
         kmin = lo < kmin ? lo : kmin;
         kmax = hi > kmax ? hi : kmax;
         bad_c += (c4.x >= n_cols ? 1u : 0u) + (c4.y >= n_cols ? 1u : 0u) + (c4.z >= n_cols ? 1u : 0u) + (c4.w >= n_cols ? 1u : 0u);
+        n16 += (is_u16_value(v01.x) ? 0u : 1u) + (is_u16_value(v01.y) ? 0u : 1u) + (is_u16_value(v23.x) ? 0u : 1u) +
+               (is_u16_value(v23.y) ? 0u : 1u);
     }
     for (unsigned long long g = quads * 4ull + tid; g < nnz; g += stride) {
         const unsigned long long k = f64_order_key(vals[g]);
         kmin = k < kmin ? k : kmin;
         kmax = k > kmax ? k : kmax;
         bad_c += (cols[g] >= n_cols) ? 1u : 0u;
+        n16 += is_u16_value(vals[g]) ? 0u : 1u;
     }
     for (unsigned long long i = tid; i < n_rows; i += stride) {
         const uint32_t a = row_ptr[i], b = row_ptr[i + 1];
@@ -1184,6 +1333,7 @@ __global__ void __launch_bounds__(kWideThreads) csr_stats_kernel(const uint32_t*
         bad_c += __shfl_xor_sync(0xffffffffu, bad_c, m);
         bad_r += __shfl_xor_sync(0xffffffffu, bad_r, m);
         irr += __shfl_xor_sync(0xffffffffu, irr, m);
+        n16 += __shfl_xor_sync(0xffffffffu, n16, m);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMin(&out->min_key, kmin);
@@ -1191,6 +1341,28 @@ __global__ void __launch_bounds__(kWideThreads) csr_stats_kernel(const uint32_t*
         if (bad_c) atomicAdd(&out->bad_cols, bad_c);
         if (bad_r) atomicAdd(&out->bad_rows, bad_r);
         if (irr) atomicAdd(&out->irregular_rows, irr);
+        if (n16) atomicAdd(&out->not_u16, n16);
+    }
+}
+
+// u16 mirror of values that are all integers in [0, 65535] (csr_stats_kernel: not_u16 == 0) for a CSR that did not
+// cross PCIe narrow (generated in HBM, handed over in device memory): the uniform-degree scans then read 6 instead of
+// 12 bytes per arc, exactly as behind a u16 upload.  8 values per thread and pass.
+__global__ void __launch_bounds__(kWideThreads) narrow_mirror_kernel(const double* __restrict__ src, uint16_t* __restrict__ dst,
+                                                                     const size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 8u;
+    for (size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8u; g < n; g += stride) {
+        if (g + 8u <= n) {
+            uint32_t w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double2 d = *reinterpret_cast<const double2*>(src + g + 2 * u);
+                w[u] = (uint32_t)d.x | ((uint32_t)d.y << 16);
+            }
+            *reinterpret_cast<uint4*>(dst + g) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (size_t u = g; u < n; ++u) dst[u] = (uint16_t)(uint32_t)src[u];
+        }
     }
 }
 
