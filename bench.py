@@ -346,13 +346,13 @@ def main_cfg4(args):
             cpu = {"value": o_arcs / o_t, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{sample} of the {CFG4['instances']} instances, one oracle solver per host thread "
                              f"({o_t * 1e3:.0f} ms wall)"}
-        cfg["parallelism"] = f"{world} GPU(s), {count} instances each, one CTA per instance, no collective"
-        cfg["e2e_sample"] = f"{e2e_count} instances per rank per step"
+        e2e_sample = f"{e2e_count} instances per rank per step"
         print(json.dumps({
             "metric": METRIC, "value": arcs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": {"value": e2e_arcs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(rp.nbytes + c.nbytes + v.nbytes),
+            "parallelism": f"{world} GPU(s), {count} instances each, one CTA per instance, no collective",
+            "e2e": {"value": e2e_arcs / e2e_s, "unit": UNIT, "sample": e2e_sample, "h2d_bytes_per_step": int(rp.nbytes + c.nbytes + v.nbytes),
                     "d2h_bytes_per_step": int(e2e_count * (4 * n + 12 * m)), "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": args.steps * world,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
@@ -469,7 +469,14 @@ def main_ours(args):
         # ---- roofline of the dominant kernel (round-1 bid scan), CUDA events inside the library -------------------------
         peak, peak_src = measured_peak_gbs()
         roof = {}
-        for skip, key in ((1, "roofline"), (0, "roofline_general_gather")):
+        # the variant that runs in the timed region, the general gathering variant, and the same two with the values read
+        # as f64 (SURVEY 8(d)'s 12 bytes per arc: what real-valued weights get) -- all event-bracketed, live, in this run
+        for skip, key, narrow in ((1, "roofline", 1), (0, "roofline_general_gather", 1), (1, "roofline_f64_values", 0),
+                                  (0, "roofline_f64_general_gather", 0)):
+            resident.set_option("narrow_scan", narrow)
+            if not narrow and resident.scan_value_bytes() == 8 and "roofline" in roof and roof["roofline"]["value_bytes_in_hbm"] == 8:
+                roof[key] = roof["roofline" if skip else "roofline_general_gather"]      # values were f64 to begin with
+                continue
             resident.set_option("profile", 1)
             resident.set_option("zero_price_skip", skip)
             ts, rec = [], None
@@ -483,7 +490,7 @@ def main_ours(args):
             # latency of a host-launched kernel, event -- costs several microseconds that the graph-launched solve does
             # not pay; reported beside the single-launch figure, which stays the headline
             b2b = None
-            if skip and rec:
+            if rec:
                 resident.set_option("profile_repeat", 8)
                 tb = []
                 for _ in range(5):
@@ -493,13 +500,26 @@ def main_ours(args):
                         tb.append(prof[0]["bid_ms"] / 8.0)
                 resident.set_option("profile_repeat", 1)
                 b2b = sorted(tb)[len(tb) // 2] if tb else None
+            # the eager bracket of round 1 (event, host-launched kernel, event), for comparison with the graph-launched one
+            eager = None
+            if rec and key in ("roofline", "roofline_f64_values"):
+                resident.set_option("profile_graph", 0)
+                te = []
+                for _ in range(5):
+                    resident.solve_resident(False, eps)
+                    prof = [p for p in resident.round_profile() if p["engine"] == 0]
+                    if prof:
+                        te.append(prof[0]["bid_ms"])
+                resident.set_option("profile_graph", 1)
+                eager = sorted(te)[len(te) // 2] if te else None
             resident.set_option("profile", 0)
             resident.set_option("zero_price_skip", 1)
+            vb = resident.scan_value_bytes()
+            resident.set_option("narrow_scan", 1)
             if rec:
                 t_ms = sorted(ts)[len(ts) // 2]
                 # bytes per arc the scan must read: 4 (column index) + the width the values are resident with -- 8 (f64,
                 # 12*A + 8*B) or 2 when a u16 upload left its lossless copy in HBM and the scan reads that
-                vb = resident.scan_value_bytes()
                 survey = 12 * rec["arcs"] + 8 * rec["bidders"]
                 alg = (4 + vb) * rec["arcs"] + 8 * rec["bidders"]
                 ach = alg / (t_ms * 1e-3) / 1e9
@@ -511,6 +531,10 @@ def main_ours(args):
                              "bidders": rec["bidders"], "arcs": rec["arcs"], "algorithmic_bytes": alg,
                              "launch_us": t_ms * 1e3, "peak_source": peak_src, "value_bytes_in_hbm": vb,
                              "bytes_at_f64_values": survey, "equivalent_f64_gbs": survey / (t_ms * 1e-3) / 1e9}
+                roof[key]["bracket"] = ("one graph launch: fence kernel, event-record node, the scan, event-record node "
+                                        "(CUDA events on the context's stream)")
+                if eager:
+                    roof[key]["launch_us_eager_bracket"] = eager * 1e3
                 if b2b:
                     roof[key]["launch_us_back_to_back"] = b2b * 1e3
                     roof[key]["frac_back_to_back"] = alg / (b2b * 1e-3) / 1e9 / peak
@@ -525,17 +549,19 @@ def main_ours(args):
                              f"({min(times) * 1e3:.1f} ms, {o_arcs} bid-arcs; the reference is single-threaded)",
                    "ms": min(times) * 1e3, "objective": o_obj, "objective_matches_gpu": bool(o_obj == objective)}
         cfg = describe(args.workload)
-        cfg["parallelism"] = "1 GPU" if world == 1 else f"{world} independent instances, one per GPU (no collective)"
         line = {
             "metric": METRIC, "value": arcs / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_value / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "parallelism": "1 GPU" if world == 1 else f"{world} independent instances, one per GPU (no collective)",
             "clocks": clocks,
             "e2e": {"value": e2e_arcs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "h2d_value_bytes": value_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
             "roofline": roof.get("roofline"),
             "roofline_general_gather": roof.get("roofline_general_gather"),
+            "roofline_f64_values": roof.get("roofline_f64_values"),
+            "roofline_f64_general_gather": roof.get("roofline_f64_general_gather"),
             "roofline_whole_solve": {"achieved": whole, "unit": "GB/s", "frac": whole / peak,
                                      "note": "sum over rounds of 12*A + 8*B (values counted as f64) over the whole solve time, tail rounds included"},
             "cpu_baseline": cpu,

@@ -236,6 +236,37 @@ int sla_part_sparse_buffers(sla_ctx *ctx, int world, void **d_send, void **d_rec
 int sla_part_collect(sla_ctx *ctx, uint32_t *local_winners);
 int sla_part_apply_sparse(sla_ctx *ctx, int world, uint32_t max_count, uint32_t *local_queue_len, uint32_t *local_dropped);
 
+/* ---- mesh: one KhoslaSolver instance over the GPUs of one NVLink / NVSwitch domain (BASELINE.json config 5; replaces
+ *      the body of KhoslaSolver::solve, ksparse.rs:153-251, for an instance whose rows live on several GPUs).
+ *      Persons are row-partitioned (this context holds rows [row_begins[rank], row_begins[rank + 1]), uploaded /
+ *      generated as a shard with the GLOBAL number of columns); objects are owner-partitioned in ranges of 2^shift ids
+ *      over the same ranks.  All exchange happens inside the round kernels through peer mappings of the ranks' "mesh
+ *      blocks": bids are pushed into the owner's HBM, prices are gathered from it, replies and evictions are pushed
+ *      back, and the ranks meet in flag barriers written over NVLink -- no collective and no host synchronisation per
+ *      round (csrc/sla_mesh.cuh).  Results equal the one-GPU solve bit for bit.
+ *          sla_mesh_create   layout + this rank's block (device memory, one cudaMalloc)
+ *          sla_ipc_export / sla_ipc_import / sla_ipc_release   the block as a 64-byte handle for the other processes
+ *          sla_mesh_connect  every rank's block as addressable from this device (own block, IPC map, or in-process peer)
+ *          sla_mesh_begin -> sla_mesh_solve -> sla_mesh_finish   one solve; global_* as for sla_part_begin
+ *          sla_mesh_phase / sla_mesh_poll   one kernel of a round at a time, for ranks driven in lockstep by one thread
+ *      world <= 8.  A barrier that waits longer than SLA_MESH_TIMEOUT_S (default 20 s) gives up: the solve fails with
+ *      SLA_ERR_STATE instead of hanging. ---- */
+int sla_mesh_create(sla_ctx *ctx, int rank, int world, const uint32_t *row_begins /* world + 1 */, uint32_t global_cols,
+                    void **block, size_t *block_bytes);
+int sla_ipc_export(void *dev_ptr, unsigned char *handle64);
+int sla_ipc_import(int device, const unsigned char *handle64, void **dev_ptr);
+int sla_ipc_release(int device, void *dev_ptr);
+int sla_mesh_connect(sla_ctx *ctx, void *const *peer_blocks /* world */, const int *peer_devices /* world or NULL */);
+int sla_mesh_begin(sla_ctx *ctx, int maximize, double eps, double global_w_min, double global_w_max,
+                   double global_first_value);
+int sla_mesh_solve(sla_ctx *ctx);
+int sla_mesh_phase(sla_ctx *ctx, int which /* 0 bid, 1 max, 2 resolve, 3 finish */);
+int sla_mesh_poll(sla_ctx *ctx, int *done, uint32_t *round, uint32_t *local_queue_len);
+/* person_to_object: this rank's rows (global object ids); object_to_person / prices: the objects this rank owns
+ * (sla_mesh_owned: first_object .. first_object + num_owned).  stats: this rank's share (the caller adds them up). */
+int sla_mesh_finish(sla_ctx *ctx, uint32_t *person_to_object, uint32_t *object_to_person, double *prices, sla_stats *stats);
+int sla_mesh_owned(sla_ctx *ctx, uint32_t *shard_objects, uint32_t *num_owned, uint32_t *first_object, uint32_t *first_row);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,6 +145,17 @@ SIGNATURES = {
     "sla_part_sparse_buffers": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_uint64)]),
     "sla_part_collect": (C.c_int, [_vp, _u32p]),
     "sla_part_apply_sparse": (C.c_int, [_vp, C.c_int, C.c_uint32, _u32p, _u32p]),
+    "sla_mesh_create": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_uint32, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
+    "sla_ipc_export": (C.c_int, [_vp, _vp]),
+    "sla_ipc_import": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "sla_ipc_release": (C.c_int, [C.c_int, _vp]),
+    "sla_mesh_connect": (C.c_int, [_vp, _vp, _vp]),
+    "sla_mesh_begin": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "sla_mesh_solve": (C.c_int, [_vp]),
+    "sla_mesh_phase": (C.c_int, [_vp, C.c_int]),
+    "sla_mesh_poll": (C.c_int, [_vp, C.POINTER(C.c_int), _u32p, _u32p]),
+    "sla_mesh_finish": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(SlaStats)]),
+    "sla_mesh_owned": (C.c_int, [_vp, _u32p, _u32p, _u32p, _u32p]),
 }
 
 _lib = None

@@ -1,5 +1,6 @@
 // sla_api.cu -- host side of libsla_b200.so: context, CSR mirror, solve drivers (CUDA-graph super-rounds or a
 // host-driven loop), post-processing, and the extern "C" boundary declared in include/sla.h.
+#include <algorithm>
 #include <cmath>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -58,6 +59,7 @@ struct GraphSlot {
 
 struct sla_batch_state;
 struct sla_part_state;
+struct sla_mesh_state;
 
 // Persistent host workers of one context for the in-place negation of the caller's `values` (solver.rs:214-216):
 // chunk w of the array is negated by worker w as soon as the H2D copy of that chunk has completed (one event per chunk),
@@ -324,6 +326,7 @@ struct sla_ctx {
 
     sla_batch_state* batch = nullptr;
     sla_part_state* part = nullptr;
+    sla_mesh_state* mesh = nullptr;
 };
 
 namespace {
@@ -1558,6 +1561,7 @@ int sla_ctx_create(int device, size_t row_capacity, size_t col_capacity, size_t 
 
 void sla_batch_free(sla_ctx* ctx);
 void sla_part_free(sla_ctx* ctx);
+void sla_mesh_free(sla_ctx* ctx);
 
 void sla_ctx_destroy(sla_ctx* ctx) {
     if (!ctx) return;
@@ -1567,6 +1571,7 @@ void sla_ctx_destroy(sla_ctx* ctx) {
     release_l2_policy(ctx);
     sla_batch_free(ctx);
     sla_part_free(ctx);
+    sla_mesh_free(ctx);
     drop_graphs(ctx);
     if (ctx->profile_exec) cudaGraphExecDestroy(ctx->profile_exec);
     cudaFree(ctx->d_row_ptr); cudaFree(ctx->d_cols); cudaFree(ctx->d_vals); cudaFree(ctx->d_prices);
@@ -1906,3 +1911,4 @@ int sla_get_round_profile(sla_ctx* ctx, sla_round_profile* out, size_t capacity,
 
 #include "sla_batch.cuh"
 #include "sla_part.cuh"
+#include "sla_mesh.cuh"

@@ -64,6 +64,9 @@ struct DevState {
     uint32_t prune_ok;       // prices are known to be >= 0 for the whole solve (eps >= 0): profit <= value, so the
                              // gathering scan may skip arcs whose value is below a proven bound on the second-best profit
     uint32_t wide_ctl_done;  // control step A of this super-round already ran (in assign_wide_kernel's last block)
+    // mesh engine (sla_mesh.cuh): round number of the current solve (from 1), barrier epoch at the start of the round
+    // (keeps counting across solves), 1 = a barrier gave up / 2 = safety limit
+    uint32_t mesh_round, mesh_epoch, mesh_error, mesh_pad;
     unsigned long long rounds, bids, bid_arcs, wide_rounds, tail_rounds;
     unsigned long long safety_rounds_left;
     unsigned long long dbg[24];  // cycle counters of the tail engine when built with -DSLA_TAIL_TIMING
@@ -298,7 +301,24 @@ enum PriceMode : int {
     PRICE_LDG = 1,    // prices immutable during this kernel: read-only path
     PRICE_CG = 2,     // L2-coherent loads
     PRICE_CA = 3,     // prices mutated by this very CTA (tail / batch engines): coherent L1-cached loads
-    PRICE_SMEM = 4    // `prices` points at a shared-memory copy kept by a single-CTA engine
+    PRICE_SMEM = 4,   // `prices` points at a shared-memory copy kept by a single-CTA engine
+    PRICE_MESH = 5    // `prices` points at a MeshView: the price lives in the owner rank's HBM (peer-mapped over NVLink)
+};
+
+// Mesh engine (sla_mesh.cuh): object state is owner-partitioned over up to kMeshMaxRanks GPUs, one 32-byte cell (one
+// sector) per object, so that a bid resolution touches one sector and a remote price gather fetches one.
+constexpr int kMeshMaxRanks = 8;
+struct alignas(32) ObjCell {
+    unsigned long long best;   // packed bid word of the current round, 0 = no bid
+    double price;
+    uint32_t owner;            // global person id or SLA_DEV_NONE
+    uint32_t pad0;
+    unsigned long long pad1;
+};
+static_assert(sizeof(ObjCell) == 32, "one object cell is one 32-byte sector");
+struct MeshView {
+    const ObjCell* cells[kMeshMaxRanks];   // rank g's cells (peer-mapped), object j lives at cells[j >> shift][j & mask]
+    uint32_t shift, mask;
 };
 
 template <int MODE>
@@ -307,6 +327,12 @@ __device__ __forceinline__ double ld_price(const double* prices, uint32_t j) {
     if (MODE == PRICE_LDG) return __ldg(prices + j);   // L1-allocating on purpose: no_allocate gathers measured 1.6x slower
     if (MODE == PRICE_CA) return ld_ca_f64(prices + j);
     if (MODE == PRICE_SMEM) return prices[j];
+    if (MODE == PRICE_MESH) {
+        // frozen for the duration of the bid kernel, so the read-only path (L1) may cache it; peer addresses bypass the
+        // local L2 and are served by the owner's
+        const MeshView* mv = reinterpret_cast<const MeshView*>(prices);
+        return __ldg(&(mv->cells[j >> mv->shift] + (j & mv->mask))->price);
+    }
     return __ldcg(prices + j);
 }
 

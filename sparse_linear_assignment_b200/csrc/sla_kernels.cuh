@@ -6,6 +6,7 @@
 // Every kernel decides from the device-resident DevState whether it has work, so the same sequence can be
 // replayed without host involvement until DevState::done is set.
 #pragma once
+#include <cstddef>
 #include "sla_common.cuh"
 #include "synth.h"
 
@@ -692,18 +693,31 @@ __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params 
 
     // Control step A (round accounting, queue flip, termination tests) by the last block to finish: every block has
     // published its emissions (fence) before it takes its ticket, so the last one sees the complete next queue length.
-    // The block is read and written past the L1 (volatile): other blocks changed it with atomics in the L2.
+    // The control block is fetched past the L1 with independent 128-bit loads (other blocks changed it with atomics in
+    // the L2), worked on in shared memory and stored back -- one L2 round trip instead of a chain of dependent ones.
+    __shared__ uint32_t s_last;
+    __shared__ DevState s_state;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const uint32_t ticket = atomicAdd(&st->assign_ticket, 1u);
-        if (ticket == gridDim.x - 1u) {
-            __threadfence();
-            volatile DevState* vst = st;
-            vst->assign_ticket = 0u;
-            control_after_wide(vst);
-            vst->wide_ctl_done = 1u;
+        s_last = (atomicAdd(&st->assign_ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        constexpr int kCtlWords = (int)(offsetof(DevState, dbg) / 16);
+        static_assert(offsetof(DevState, dbg) % 16 == 0, "the control fields are copied as 128-bit words");
+        __threadfence();
+        if (threadIdx.x < kCtlWords)
+            reinterpret_cast<uint4*>(&s_state)[threadIdx.x] = __ldcg(reinterpret_cast<const uint4*>(st) + threadIdx.x);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_state.assign_ticket = 0u;
+            control_after_wide(&s_state);
+            s_state.wide_ctl_done = 1u;
         }
+        __syncthreads();
+        if (threadIdx.x < kCtlWords)
+            reinterpret_cast<uint4*>(st)[threadIdx.x] = reinterpret_cast<const uint4*>(&s_state)[threadIdx.x];
     }
 }
 

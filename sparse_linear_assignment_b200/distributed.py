@@ -25,7 +25,8 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import SlaStats
 
-__all__ = ["PartitionedKhoslaSolver", "CudaShardEngine", "shard_rows"]
+__all__ = ["PartitionedKhoslaSolver", "CudaShardEngine", "shard_rows", "MeshKhoslaSolver", "MeshShard", "mesh_lockstep_solve",
+           "object_shard"]
 
 
 def shard_rows(global_rows: int, world: int, rank: int):
@@ -235,3 +236,244 @@ class _NullCtx:
 
     def __exit__(self, *a):
         return False
+
+
+# =====================================================================================================================
+# Mesh engine: owner-partitioned objects, bids pushed into the owner's HBM over NVLink peer mappings (csrc/sla_mesh.cuh)
+# =====================================================================================================================
+def object_shard(num_cols: int, world: int) -> int:
+    """Objects per rank of the mesh engine: the power of two at or above ceil(num_cols / world)."""
+    per = (num_cols + world - 1) // world
+    s = 1
+    while s < per:
+        s <<= 1
+    return s
+
+
+class MeshShard:
+    """This rank's shard in the mesh engine: thin wrapper over sla_mesh_* (include/sla.h).  `solver` is a KhoslaSolver
+    whose CSR holds the local rows (uploaded or generated with the GLOBAL number of columns)."""
+
+    def __init__(self, solver, rank: int, world: int, row_begins):
+        self.solver, self.rank, self.world = solver, int(rank), int(world)
+        self.lib = _lib.load()
+        self.ctx = solver._sync_device()
+        self.row_begins = np.ascontiguousarray(row_begins, dtype=np.uint32)
+        assert self.row_begins.size == world + 1
+        block, nbytes = C.c_void_p(), C.c_size_t()
+        _lib.check(self.ctx, self.lib.sla_mesh_create(self.ctx, self.rank, self.world, self.row_begins.ctypes.data,
+                                                      solver.num_cols(), C.byref(block), C.byref(nbytes)))
+        self.block, self.block_bytes = block.value, nbytes.value
+        self._imported = []
+
+    def export_handle(self) -> bytes:
+        h = (C.c_ubyte * 64)()
+        rc = self.lib.sla_ipc_export(self.block, h)
+        if rc != _lib.SLA_OK:
+            raise _lib.SlaError(rc, "cudaIpcGetMemHandle failed for the mesh block")
+        return bytes(h)
+
+    def connect_handles(self, handles):
+        """handles[g]: rank g's 64-byte IPC handle (the entry of this rank is ignored)."""
+        ptrs = (C.c_void_p * self.world)()
+        for g in range(self.world):
+            if g == self.rank:
+                ptrs[g] = self.block
+                continue
+            buf = (C.c_ubyte * 64).from_buffer_copy(handles[g])
+            out = C.c_void_p()
+            rc = self.lib.sla_ipc_import(self.solver.device, buf, C.byref(out))
+            if rc != _lib.SLA_OK:
+                msg = self.lib.sla_last_error(None)
+                raise _lib.SlaError(rc, f"cannot map rank {g}'s mesh block: " + (msg.decode() if msg else ""))
+            self._imported.append(out.value)
+            ptrs[g] = out.value
+        _lib.check(self.ctx, self.lib.sla_mesh_connect(self.ctx, ptrs, None))
+
+    def connect_pointers(self, blocks, devices=None):
+        """Same process: the other shards' block pointers (and their devices, when they differ)."""
+        ptrs = (C.c_void_p * self.world)(*blocks)
+        devs = (C.c_int * self.world)(*devices) if devices is not None else None
+        _lib.check(self.ctx, self.lib.sla_mesh_connect(self.ctx, ptrs, devs))
+
+    def local_value_range(self):
+        lo, hi, first = C.c_double(), C.c_double(), C.c_double()
+        _lib.check(self.ctx, self.lib.sla_part_local_value_range(self.ctx, C.byref(lo), C.byref(hi), C.byref(first)))
+        return lo.value, hi.value, first.value
+
+    def begin(self, maximize, eps, gmin, gmax, gfirst):
+        _lib.check(self.ctx, self.lib.sla_mesh_begin(self.ctx, int(bool(maximize)), float("nan") if eps is None else float(eps),
+                                                     gmin, gmax, gfirst))
+
+    def solve(self):
+        _lib.check(self.ctx, self.lib.sla_mesh_solve(self.ctx))
+
+    def phase(self, which: int):
+        _lib.check(self.ctx, self.lib.sla_mesh_phase(self.ctx, which))
+
+    def poll(self):
+        d, r, q = C.c_int(), C.c_uint32(), C.c_uint32()
+        _lib.check(self.ctx, self.lib.sla_mesh_poll(self.ctx, C.byref(d), C.byref(r), C.byref(q)))
+        return bool(d.value), r.value, q.value
+
+    def owned(self):
+        s, n, f, r = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _lib.check(self.ctx, self.lib.sla_mesh_owned(self.ctx, C.byref(s), C.byref(n), C.byref(f), C.byref(r)))
+        return dict(shard_objects=s.value, num_owned=n.value, first_object=f.value, first_row=r.value)
+
+    def finish(self, download: bool = True):
+        """Returns (person_to_object of the local rows, object_to_person and prices of the owned objects, stats)."""
+        own = self.owned()
+        n = self.solver.num_rows()
+        p2o = o2p = prices = None
+        if download:
+            from .solver import host_array
+            p2o = host_array(n, np.uint32)
+            o2p = host_array(max(own["num_owned"], 1), np.uint32)[: own["num_owned"]]
+            prices = host_array(max(own["num_owned"], 1), np.float64)[: own["num_owned"]]
+        st = SlaStats()
+        _lib.check(self.ctx, self.lib.sla_mesh_finish(self.ctx, p2o.ctypes.data if download else None,
+                                                      o2p.ctypes.data if download and own["num_owned"] else None,
+                                                      prices.ctypes.data if download and own["num_owned"] else None,
+                                                      C.byref(st)))
+        return p2o, o2p, prices, st.as_dict()
+
+    def close(self):
+        for ptr in self._imported:
+            self.lib.sla_ipc_release(self.solver.device, ptr)
+        self._imported = []
+
+
+def _global_range(shards_or_ranges):
+    lo = min(r[0] for r in shards_or_ranges)
+    hi = max(r[1] for r in shards_or_ranges)
+    return lo, hi
+
+
+def mesh_lockstep_solve(shards, maximize=False, eps=None, max_rounds=1 << 20):
+    """Drives all ranks of a mesh solve from ONE host thread, one kernel at a time (every rank's phase k before any rank's
+    phase k + 1) -- the way to run G ranks on fewer than G GPUs, where kernels that wait for each other's flags must never
+    be resident together (tests; same kernels, same peer pointers, same results as the concurrent path).
+    Returns the assembled global solution."""
+    world = len(shards)
+    ranges = [s.local_value_range() for s in shards]
+    gmin, gmax = _global_range(ranges)
+    gfirst = ranges[0][2]
+    for s in shards:
+        s.begin(maximize, eps, gmin, gmax, gfirst)
+    rounds = 0
+    while rounds < max_rounds:
+        for which in range(4):
+            for s in shards:
+                s.phase(which)
+        states = [s.poll() for s in shards]
+        assert len({st[0] for st in states}) == 1, "ranks disagree about the end of the solve"
+        if states[0][0]:
+            break
+        rounds += 1
+    return mesh_assemble([s.finish() for s in shards], [s.owned() for s in shards], shards[0].solver.num_cols())
+
+
+def mesh_assemble(parts, owned, num_cols):
+    """Global vectors from the ranks' slices: parts[g] = (p2o_local, o2p_owned, prices_owned, stats)."""
+    p2o = np.concatenate([p[0] for p in parts])
+    o2p = np.full(num_cols, 0xFFFFFFFF, dtype=np.uint32)
+    prices = np.zeros(num_cols, dtype=np.float64)
+    for (_, o, pr, _), own in zip(parts, owned):
+        a, n = own["first_object"], own["num_owned"]
+        o2p[a:a + n] = o
+        prices[a:a + n] = pr
+    stats = dict(parts[0][3])
+    for key in ("num_unassigned", "bids", "bid_arcs", "dropped", "nits"):
+        stats[key] = int(sum(p[3][key] for p in parts))
+    return dict(p2o=p2o, o2p=o2p, prices=prices, stats=stats)
+
+
+class MeshKhoslaSolver:
+    """One KhoslaSolver instance over the ranks of a process group, one process per GPU (KhoslaSolver::solve,
+    ksparse.rs:153-251, for an instance whose rows are spread over the GPUs of one NVLink domain).  torch.distributed is
+    used for the plumbing only: shard sizes, the exchange of the 64-byte IPC handles, the global value range and the final
+    totals.  The rounds themselves never touch the host or a collective (csrc/sla_mesh.cuh)."""
+
+    def __init__(self, solver, group: Optional[dist.ProcessGroup] = None, shard_factory=None):
+        self.solver = solver
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        backend = dist.get_backend(group) if dist.is_initialized() else "none"
+        self.dev = torch.device("cuda", solver.device) if backend == "nccl" else torch.device("cpu")
+        self.shard = None
+        self.row_begins = None
+        self.shard_factory = shard_factory or MeshShard     # the CPU tests put a numpy model of the protocol here
+
+    def _gather_i64(self, value: int):
+        t = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+        t[self.rank] = int(value)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return [int(x) for x in t.tolist()]
+
+    def setup(self):
+        """Shard layout, this rank's mesh block, peer mappings of every other rank's block."""
+        counts = self._gather_i64(self.solver.num_rows())
+        self.row_begins = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+        self.shard = self.shard_factory(self.solver, self.rank, self.world, self.row_begins)
+        mine = torch.frombuffer(bytearray(self.shard.export_handle()), dtype=torch.uint8).to(self.dev)
+        allh = torch.zeros(self.world * 64, dtype=torch.uint8, device=self.dev)
+        allh[self.rank * 64:(self.rank + 1) * 64] = mine
+        if self.world > 1:
+            dist.all_reduce(allh, op=dist.ReduceOp.SUM, group=self.group)      # disjoint slices: a sum is a gather
+        raw = bytes(allh.cpu().numpy().tobytes())
+        self.shard.connect_handles([raw[g * 64:(g + 1) * 64] for g in range(self.world)])
+        if self.world > 1:
+            dist.barrier(group=self.group)      # every rank has mapped every block before anybody starts a solve
+        return self
+
+    def solve(self, maximize: bool = False, eps: Optional[float] = None, download: bool = True, gather: bool = False) -> dict:
+        if self.shard is None:
+            self.setup()
+        sh = self.shard
+        lo, hi, first = sh.local_value_range()
+        rng = torch.tensor([-lo, hi, first if self.rank == 0 else 0.0], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            mx = rng[:2].clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+            f = rng[2:].clone()
+            dist.all_reduce(f, op=dist.ReduceOp.SUM, group=self.group)
+            rng = torch.cat([mx, f])
+        gmin, gmax, gfirst = -float(rng[0].item()), float(rng[1].item()), float(rng[2].item())
+        sh.begin(maximize, eps, gmin, gmax, gfirst)
+        sh.solve()                                   # graphs of rounds; the ranks meet only in the kernels' flag barriers
+        p2o, o2p, prices, st = sh.finish(download)
+        tot = torch.tensor([st["num_unassigned"], st["bids"], st["bid_arcs"]], dtype=torch.int64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+        st = dict(st)
+        st["global_num_unassigned"], st["global_bids"], st["global_bid_arcs"] = [int(x) for x in tot.tolist()]
+        own = sh.owned()
+        out = dict(p2o=p2o, o2p=o2p, prices=prices, stats=st, owned=own, row_begin=int(self.row_begins[self.rank]),
+                   global_rows=int(self.row_begins[-1]))
+        if gather and download:
+            out.update(self._gather_solution(p2o, o2p, prices, own))
+        return out
+
+    def _gather_solution(self, p2o, o2p, prices, own):
+        """All ranks' slices on every rank (tests and small instances; large ones keep their slices)."""
+        n, m = int(self.row_begins[-1]), self.solver.num_cols()
+        gp = torch.zeros(n, dtype=torch.int64, device=self.dev)
+        a = int(self.row_begins[self.rank])
+        gp[a:a + p2o.size] = torch.from_numpy(p2o.astype(np.int64)).to(self.dev) + 1      # 0 = not mine
+        go = torch.zeros(m, dtype=torch.int64, device=self.dev)
+        gpr = torch.zeros(m, dtype=torch.float64, device=self.dev)
+        f, k = own["first_object"], own["num_owned"]
+        go[f:f + k] = torch.from_numpy(o2p.astype(np.int64)).to(self.dev) + 1
+        gpr[f:f + k] = torch.from_numpy(np.ascontiguousarray(prices)).to(self.dev)
+        if self.world > 1:
+            for t in (gp, go, gpr):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return dict(global_p2o=(gp - 1).cpu().numpy().astype(np.uint32), global_o2p=(go - 1).cpu().numpy().astype(np.uint32),
+                    global_prices=gpr.cpu().numpy())
+
+    def close(self):
+        if self.shard is not None:
+            self.shard.close()

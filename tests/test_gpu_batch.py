@@ -70,6 +70,45 @@ def test_cfg4_shaped_batch_generated_on_device(sla, oracle, kind):
     assert res["total"]["num_unassigned"] == 0
 
 
+def test_cfg4_full_batch_8192_instances(sla, oracle):
+    """BASELINE.json config 4 at its full count: 8,192 independent 512 x 512 k=32 instances (Forward, eps-scaled)
+    generated in HBM and solved by one launch.  Every instance against the CPU model bit for bit (assignment, prices,
+    counters); 256 of them against the reference oracle (num_unassigned, bit-exact objective: integer costs,
+    eps = 1/(n+1) < 1/n)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from sparse_linear_assignment_b200 import generators as G
+    n = m = 512
+    k, count = 32, 8192
+    eps = 1.0 / (n + 1)
+    b = sla.BatchSolver("forward")
+    b.generate_device(count, 0, n, m, k, seed=0, planted=True)
+    res = b.solve(eps=eps)
+    assert res["total"]["num_unassigned"] == 0
+    oracle.lib()
+
+    def check(i):
+        rp, c, v = G.kregular_host(n, m, k, seed=i, planted=True, threads=1)
+        rs, cs = b.instance_slices(i)
+        model = oracle.jacobi_model("forward", n, m, rp, c, v, eps=eps)
+        ok = (np.array_equal(res["p2o"][rs], model["p2o"]) and np.array_equal(res["o2p"][cs], model["o2p"]) and
+              np.array_equal(res["prices"][cs], model["prices"]))
+        st = res["stats"][i]
+        ok = ok and all(st[q] == model["stats"][q] for q in ("num_unassigned", "nits", "nreductions", "optimal_soln_found",
+                                                             "rounds", "bids", "bid_arcs"))
+        if ok and i % 32 == 0:
+            o = oracle.OracleSolver("forward", n, m, n * k)
+            o.load_csr(n, m, rp, c, v)
+            o.solve(eps=eps)
+            ok = o.num_unassigned == 0 and objective_of(rp, c, v, res["p2o"][rs]) == o.get_objective()
+        return ok
+
+    # jacobi_model keeps its option in a global: set it once, the worker threads then only read it
+    oracle.jacobi_model("forward", 1, 1, np.array([0, 1], dtype=np.uint32), np.zeros(1, dtype=np.uint32), np.ones(1))
+    with ThreadPoolExecutor(max_workers=16) as ex:
+        bad = [i for i, ok in enumerate(ex.map(check, range(count))) if not ok]
+    assert not bad, bad[:10]
+
+
 def test_batch_errors(sla):
     b = sla.BatchSolver("khosla")
     with pytest.raises(sla.SlaError):

@@ -41,6 +41,29 @@ def assert_equals_model(O, kind, solver, z, n, m, rp, c, v, maximize=False, eps=
     return r
 
 
+def assert_reference_parity(O, kind, solver, z, n, m, rp, c, v, maximize=False, eps=None, integer=False):
+    """The north star's bar against the REFERENCE (the pinned oracle, not the model of the device rounds): same
+    num_unassigned; with everybody assigned the objective is bit-exact for integer weights when the final eps is
+    below 1/n (both solutions are optimal) and within n * eps_final otherwise (both are within n * eps of the optimum:
+    ksparse.rs / symmetric.rs end in eps-complementary slackness).  Returns the oracle."""
+    if kind == "forward" and int(np.diff(np.asarray(rp, dtype=np.int64)).min()) < 2:
+        return None      # single-arc rows make Forward bid +inf and then NaN (symmetric.rs:378, 394): no comparable end state
+    o = O.OracleSolver(kind, n, m, len(c))
+    o.load_csr(n, m, rp, c, v)
+    o.solve(maximize=maximize, eps=eps)
+    assert z.num_unassigned == o.num_unassigned, (kind, n, m, z.num_unassigned, o.num_unassigned)
+    if z.num_unassigned == 0:
+        got, ref = solver.get_objective(z), o.get_objective()
+        e = max(z.eps, o.eps)
+        if kind == "forward" and not (solver.optimal_soln_found and o.optimal_soln_found):
+            return o     # cut short by max_iterations: a complete assignment, but no eps-CS certificate on one side
+        if integer and e < 1.0 / n:
+            assert got == ref, (kind, n, m, got, ref)
+        else:
+            assert abs(got - ref) <= n * e + 1e-9 * max(1.0, abs(ref)), (kind, n, m, got, ref, e)
+    return o
+
+
 # ---- the reference's own test-suite, instantiated for both solvers (src/solver.rs:246-445) ------------------------
 @pytest.mark.parametrize("kind,cls_name", SOLVERS)
 def test_random_solve_small(sla, oracle, kind, cls_name):
@@ -673,6 +696,7 @@ def test_randomized_sweep_matches_model(sla, oracle):
         solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v, maximize=maximize, eps=eps)
         assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v, maximize=maximize, eps=eps)
         check_matching(n, m, rp, c, z.person_to_object, z.object_to_person, z.num_unassigned)
+        assert_reference_parity(oracle, kind, solver, z, n, m, rp, c, v, maximize=maximize, eps=eps, integer=bool(trial % 4))
 
 
 def test_randomized_square_sweep_matches_model(sla, oracle):
@@ -699,3 +723,159 @@ def test_randomized_square_sweep_matches_model(sla, oracle):
         solver, z = gpu_solve(sla, cls_name, n, n, rp, c, v, maximize=maximize, eps=eps)
         assert_equals_model(oracle, kind, solver, z, n, n, rp, c, v, maximize=maximize, eps=eps)
         check_matching(n, n, rp, c, z.person_to_object, z.object_to_person, z.num_unassigned)
+        assert_reference_parity(oracle, kind, solver, z, n, n, rp, c, v, maximize=maximize, eps=eps,
+                                integer=bool(np.all(v == np.floor(v))))
+
+
+# ---- Khosla on square instances around the feasibility boundary: num_unassigned is the reference's ---------------------
+def test_square_khosla_feasibility_boundary_equals_reference(sla, oracle):
+    """KhoslaSolver drops a person for good once the price of its best object exceeds the threshold
+    (ksparse.rs:181, 218-220); on a square instance that is what decides `num_unassigned`.  The device runs such
+    instances under an eps-schedule and falls back to plain rounds when a phase drops anybody.  Property,
+    on sparse random square graphs of mean degree 2 .. 4 -- right at the threshold where a perfect matching stops
+    existing -- with the schedule ON: the device's num_unassigned equals the reference's, for 200 unplanted instances
+    (n = 10 .. 200; three quarters of them without a perfect matching) and 40 planted ones (n = 200 .. 2,000; a perfect
+    matching exists, so nobody may be dropped), integer and real weights; the matching is valid; with everybody assigned
+    the objective meets the north star's bar."""
+    solver, z = sla.KhoslaSolver.new(2048, 2048, 2048 * 12)
+    infeasible = feasible = 0
+    for seed in range(240):
+        rng = np.random.default_rng(seed)
+        planted = seed >= 200
+        n = int(rng.integers(200, 2001)) if planted else int(rng.integers(10, 201))
+        integer = seed % 2 == 0
+        rp, c, v = _symmetric_instance(n, float(rng.uniform(2.0, 4.0)), 5000 + seed, planted, 0.0, 50.0 if integer else 10.0)
+        if integer:
+            v = np.floor(v)
+        solver.load_csr(n, n, rp, c, v.copy())
+        solver.solve(z, False, None)
+        o = assert_reference_parity(oracle, "khosla", solver, z, n, n, rp, c, v, integer=integer)
+        check_matching(n, n, rp, c, z.person_to_object, z.object_to_person, o.num_unassigned)
+        if planted:
+            assert z.num_unassigned == 0
+        infeasible += int(o.num_unassigned > 0)
+        feasible += int(o.num_unassigned == 0)
+    assert infeasible >= 100 and feasible >= 50
+
+
+@pytest.mark.parametrize("kind,cls_name", SOLVERS)
+def test_square_real_weight_fixtures_against_reference(sla, oracle, kind, cls_name):
+    """Square instances with real-valued weights (the reference's own fixture family, solver.rs:261-292, and its
+    symmetric bench shape, benches/benchmark.rs:16-47) against the reference oracle: Khosla runs them under the
+    eps-schedule, so equality with the reference's prices is not promised -- eps-CS at the caller's eps is, and with it
+    the objective within n * eps."""
+    for n, k, seed in ((60, 6, 1), (300, 10, 2), (1200, 12, 3)):
+        rp, c, v = oracle.fixture_ksparse(n, n, k, 10.0, val_seed=seed, filter_seed=seed + 100)
+        rp2, c2, v2 = _symmetric_instance(n, k, 40 + seed, True, 500.0, 1000.0)
+        for (a, b, w) in ((rp, c, v), (rp2, c2, v2)):
+            solver, z = gpu_solve(sla, cls_name, n, n, a, b, w.copy())
+            o = assert_reference_parity(oracle, kind, solver, z, n, n, a, b, w)
+            check_matching(n, n, a, b, z.person_to_object, z.object_to_person, z.num_unassigned)
+            if z.num_unassigned == 0:
+                # eps-CS as solver.rs:154-189 tests it; Khosla's update rule (ksparse.rs:222-227) guarantees it in
+                # exact arithmetic only, so its check gets a few ulps of the weight range on top of the toleration
+                tol = solver.get_toleration(float(np.max(np.abs(w))))
+                e = 1.0 / n if kind == "forward" else z.eps + 64 * tol
+                assert solver.device_ecs_satisfied(e, tol)
+            del o
+
+
+def test_failed_solve_does_not_poison_the_next_one(sla, oracle):
+    """A solve that fails after the upload has pre-applied the sign normalisation (here: the wall-clock guard) must leave
+    host and device agreeing about the sign, so that the next solve on the unchanged CSR just works."""
+    rng = np.random.default_rng(4)
+    n, k = 3000, 16
+    rp, c, v = random_sparse_instance(rng, n, n, k, integer=True, lo=1, hi=1000)
+    solver, z = sla.ForwardAuctionSolver.new(n, n, n * k)
+    solver.load_csr(n, n, rp, c, v.copy())
+    solver.set_option("super_rounds", 1)
+    solver.set_option("timeout_s", 0)
+    with pytest.raises(sla.SlaError) as e:
+        solver.solve(z, False, 1.0 / (n + 1))                # needs far more than one graph launch
+    assert "timeout" in e.value.message or "guard" in e.value.message
+    assert np.array_equal(solver.values(), -v)               # the normalisation happened (solver.rs:214-216) ...
+    solver.set_option("timeout_s", 900)
+    solver.set_option("super_rounds", 6)
+    solver.solve(z, False, 1.0 / (n + 1))                    # ... and the next solve agrees with it
+    assert np.array_equal(solver.values(), -v)
+    o = oracle.OracleSolver("forward", n, n, n * k)
+    o.load_csr(n, n, rp, c, v)
+    o.solve(eps=1.0 / (n + 1))
+    assert z.num_unassigned == 0 and solver.get_objective(z) == o.get_objective()
+
+
+def test_bound_pruned_gather_changes_nothing(sla, oracle):
+    """Rounds with >= 32 Ki bidders gather prices only for arcs that can still matter (value >= a proven bound on the
+    second-best profit); option prune_gather = 0 gathers everything.  Identical bits either way, equal to the model: u16
+    and f64 values, both signs, a first round that gathers (zero_price_skip = 0), K = 8 .. 64."""
+    for n, m, k, seed in ((70_000, 200_000, 16, 1), (40_000, 90_000, 8, 2), (36_000, 120_000, 40, 3), (34_000, 34_000, 64, 4)):
+        rp, c, v = sla.generators.kregular_host(n, m, k, seed=seed, planted=(n == m))
+        for vals in (v, v + 0.25):                           # u16 mirror / f64 values (f32 on the wire)
+            for maximize in (False, True):
+                out = []
+                for prune in (1, 0):
+                    solver, z = gpu_solve(sla, "KhoslaSolver", n, m, rp, c, vals.copy(), maximize=maximize,
+                                          options=dict(prune_gather=prune, zero_price_skip=0, khosla_scaling=0))
+                    assert solver.last_stats["wide_rounds"] >= 2
+                    out.append((z.person_to_object.copy(), z.object_to_person.copy(), solver.prices().copy(),
+                                {q: solver.last_stats[q] for q in ("rounds", "bids", "bid_arcs", "num_unassigned", "dropped")}))
+                for x, y in zip(out[0][:3], out[1][:3]):
+                    assert np.array_equal(x, y)
+                assert out[0][3] == out[1][3]
+        solver, z = gpu_solve(sla, "KhoslaSolver", n, m, rp, c, v.copy(), options=dict(zero_price_skip=0, khosla_scaling=0))
+        assert_equals_model(oracle, "khosla", solver, z, n, m, rp, c, v.copy(), khosla_scaling=False)
+
+
+def test_resident_repeat_solves_learn_the_graph_shape(sla, oracle):
+    """Repeated plain-Khosla solves of a resident CSR capture their first graph as (wide rounds of the previous solve) x
+    (bid, assign) + one tail launch; results and counters stay identical, launches go down, and a solve whose round count
+    differs (another eps) is finished by continuation graphs."""
+    n, m, k = 300_000, 1_200_000, 16
+    solver, z = sla.KhoslaSolver.new(n, m, n * k)
+    sla.generators.kregular_device(solver, n, m, k, seed=3)
+    a = solver.solve_resident(False, None)
+    first = (a["rounds"], a["bids"], a["bid_arcs"], a["num_unassigned"])
+    obj = solver.device_objective()
+    b = solver.solve_resident(False, None)
+    c2 = solver.solve_resident(False, None)
+    for st in (b, c2):
+        assert (st["rounds"], st["bids"], st["bid_arcs"], st["num_unassigned"]) == first
+        assert st["kernel_launches"] < a["kernel_launches"] and st["graph_launches"] == 1
+    assert solver.device_objective() == obj
+    d = solver.solve_resident(False, 5.0)                    # coarser eps: fewer rounds than the learned shape expects
+    e = solver.solve_resident(False, None)                   # and back
+    assert (e["rounds"], e["bids"], e["bid_arcs"], e["num_unassigned"]) == first and d["num_unassigned"] == 0
+    assert solver.device_objective() == obj
+    solver.set_option("learn_shape", 0)
+    f = solver.solve_resident(False, None)
+    assert (f["rounds"], f["bids"], f["bid_arcs"]) == first[:3] and f["kernel_launches"] == a["kernel_launches"]
+
+
+def test_cfg5_khosla_16Mx64M_k16(sla, oracle):
+    """BASELINE.json config 5 at full size on one GPU, from host memory, against the reference oracle: same
+    num_unassigned, bit-exact objective (integer costs, eps = 1/M < 1/N), valid matching (device-side validator)."""
+    from sparse_linear_assignment_b200 import generators as G
+    n, m, k, _ = G.CONFIGS["cfg5"]
+    solver, z = sla.KhoslaSolver.new(n, m, n * k)
+    solver.init(n, m)
+    solver._i_starts_stops.resize(n + 1, 0)                   # generate straight into the solver's (page-locked) storage
+    solver._j_counts.resize(n, k)
+    solver._column_indices.resize(n * k, 0)
+    solver._values.resize(n * k, 0.0)
+    G.kregular_host(n, m, k, seed=1, out=(solver._i_starts_stops.view, solver._column_indices.view, solver._values.view))
+    o = oracle.OracleSolver("khosla", n, m, n * k)
+    o.load_csr(n, m, solver.i_starts_stops(), solver.column_indices(), solver.values())
+    solver.solve(z, False, None)
+    o.solve()
+    assert z.num_unassigned == o.num_unassigned == 0
+    assert solver.device_validate_matching() == (0, True)
+    assert solver.device_objective() == o.get_objective()      # exact: integer costs
+    assert np.array_equal(solver.values(), o.values)          # both negated in place
+    p2o = z.person_to_object
+    assert np.array_equal(z.object_to_person[p2o], np.arange(n, dtype=np.uint32))
+    # the same instance generated in HBM: identical work counters
+    dev, zd = sla.KhoslaSolver.new(n, m, n * k)
+    G.kregular_device(dev, n, m, k, seed=1)
+    st = dev.solve_resident(False, None)
+    assert st["bid_arcs"] == solver.last_stats["bid_arcs"] and st["num_unassigned"] == 0
+    assert dev.device_objective() == o.get_objective()

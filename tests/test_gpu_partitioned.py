@@ -124,3 +124,94 @@ def test_lockstep_shards_sparse_exchange_equal_model(sla, oracle, world, maximiz
         assert np.array_equal(o[1], ref["o2p"]) and np.array_equal(o[2], ref["prices"])
     assert rounds == ref["stats"]["rounds"]
     assert sum(o[3]["bid_arcs"] for o in outs) == ref["stats"]["bid_arcs"]
+
+
+# ---- mesh engine: owner-partitioned objects, bids pushed into the owner's memory through peer pointers -----------------
+def make_mesh_shards(sla, n, m, rp, c, v, world, options=None):
+    from sparse_linear_assignment_b200.distributed import MeshShard, shard_rows
+    begins = [shard_rows(n, world, r)[0] for r in range(world)] + [n]
+    shards = []
+    for r in range(world):
+        b, cnt = begins[r], begins[r + 1] - begins[r]
+        a0, a1 = int(rp[b]), int(rp[b + cnt])
+        solver, _ = sla.KhoslaSolver.new(cnt, m, max(a1 - a0, 1))
+        for k_, v_ in (options or {}).items():
+            solver.set_option(k_, v_)
+        solver.load_csr(cnt, m, (rp[b:b + cnt + 1].astype(np.int64) - a0).astype(np.uint32), c[a0:a1], v[a0:a1].copy())
+        shards.append(MeshShard(solver, r, world, begins))
+    for s in shards:
+        s.connect_pointers([t.block for t in shards])
+    return shards
+
+
+def assert_mesh_equals_model(res, ref):
+    assert np.array_equal(res["p2o"], ref["p2o"]), "person_to_object differs from the model"
+    assert np.array_equal(res["o2p"], ref["o2p"]), "object_to_person differs from the model"
+    assert np.array_equal(res["prices"], ref["prices"]), "prices differ from the model (bit-exact f64)"
+    for key in ("num_unassigned", "bids", "bid_arcs", "dropped", "rounds"):
+        assert res["stats"][key] == ref["stats"][key], (key, res["stats"][key], ref["stats"][key])
+
+
+@pytest.mark.parametrize("world,n,m,k,maximize,ragged", [
+    (2, 4001, 6000, 16, False, False),       # uniform degree: the LDG.256 scan, two lanes per row
+    (3, 3000, 7000, 8, True, False),         # one lane per row, objects split 4096 / 2904 / 0 ... a rank that owns few
+    (4, 5003, 5003, 24, False, False),       # square, three of four lanes busy
+    (8, 2500, 9000, 40, False, False),       # eight ranks, K > 32
+    (3, 3001, 5000, 7, False, True),         # ragged CSR: the masked 128-bit scan
+    (2, 2, 5, 3, False, True),               # one person per rank
+])
+def test_mesh_lockstep_equals_model(sla, oracle, world, n, m, k, maximize, ragged):
+    """All ranks of the mesh engine on ONE GPU, stepped in lockstep (sla_mesh_phase): every rank's block is reached
+    through the same peer-pointer tables as across GPUs.  Bit-identical to the sequential model: assignment, prices,
+    rounds and work counters; solved twice to cover the reuse of the blocks and the running barrier epoch."""
+    from sparse_linear_assignment_b200.distributed import mesh_lockstep_solve
+    rng = np.random.default_rng(100 * world + k)
+    if ragged:
+        counts = rng.integers(1, k + 1, size=n)
+        rp = np.zeros(n + 1, dtype=np.uint32)
+        rp[1:] = np.cumsum(counts)
+        c = np.concatenate([np.sort(rng.choice(m, size=int(t), replace=False)) for t in counts]).astype(np.uint32)
+        v = rng.integers(1, 500, size=int(rp[-1])).astype(np.float64)
+    else:
+        rp, c, v = random_sparse_instance(rng, n, m, k, integer=True, lo=1, hi=500)
+    eps = 1.0 / (m + 1)
+    shards = make_mesh_shards(sla, n, m, rp, c, v, world)
+    ref = oracle.jacobi_model("khosla", n, m, rp, c, v, maximize=maximize, eps=eps, khosla_scaling=False)
+    for _ in range(2):
+        res = mesh_lockstep_solve(shards, maximize=maximize, eps=eps)
+        assert_mesh_equals_model(res, ref)
+
+
+def test_mesh_lockstep_large_rounds_u16_and_f64(sla, oracle):
+    """Rounds large enough for several staging chunks per block and the u16 value mirror (70,000 persons per rank), then
+    the same instance with real-valued weights (f64 scan); against the one-GPU engine bit for bit."""
+    from sparse_linear_assignment_b200.distributed import mesh_lockstep_solve
+    n, m, k, world = 140_000, 400_000, 16, 2
+    rp, c, v = sla.generators.kregular_host(n, m, k, seed=11)
+    for vals in (v, v + 0.125):
+        single, z = sla.KhoslaSolver.new(n, m, n * k)
+        single.load_csr(n, m, rp, c, vals.copy())
+        single.solve(z, False, None)
+        shards = make_mesh_shards(sla, n, m, rp, c, vals, world)
+        if vals is v:
+            assert all(s.solver.scan_value_bytes() == 2 for s in shards)
+        res = mesh_lockstep_solve(shards, maximize=False, eps=None)
+        assert np.array_equal(res["p2o"], z.person_to_object) and np.array_equal(res["o2p"], z.object_to_person)
+        assert np.array_equal(res["prices"], single.prices())
+        for key in ("bids", "bid_arcs", "rounds", "num_unassigned"):
+            assert res["stats"][key] == single.last_stats[key], key
+
+
+def test_mesh_threshold_drops_match_model(sla, oracle):
+    """An instance without a perfect matching: persons dropped at the price threshold (ksparse.rs:218-220) are counted
+    per rank and add up to the model's num_unassigned."""
+    from sparse_linear_assignment_b200.distributed import mesh_lockstep_solve
+    rng = np.random.default_rng(5)
+    n, m, k = 60, 70, 3
+    rp = np.arange(0, n * k + 1, k, dtype=np.uint32)
+    c = np.sort(rng.integers(0, 20, size=(n, k)), axis=1).astype(np.uint32).reshape(-1)      # 60 persons want 20 objects
+    v = rng.integers(1, 50, size=n * k).astype(np.float64)
+    ref = oracle.jacobi_model("khosla", n, m, rp, c, v, khosla_scaling=False)
+    assert ref["stats"]["num_unassigned"] >= 40
+    res = mesh_lockstep_solve(make_mesh_shards(sla, n, m, rp, c, v, 3))
+    assert_mesh_equals_model(res, ref)
