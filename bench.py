@@ -15,9 +15,14 @@ bid-arc is one (column, value) pair examined for one bidding person in one round
             algorithmic bytes 12*A + 8*B over the launch duration, against the measured HBM copy bandwidth.
   cpu_baseline   the CPU oracle (C restatement of the reference, goldens verified) on one host core.
 
-With N > 1 (torchrun, one rank per GPU) every rank solves its own independent instance (seed = 1 + rank): the
-path shards over independent instances with no data-path collective, so scaling is "weak".
-`--impl reference` times the reference's CPU algorithm (the oracle port; the Rust crate cannot be built here).
+With N > 1 (torchrun, one rank per GPU) the default workload is the one the north star partitions: cfg5, ONE KhoslaSolver
+instance of 16M x 64M, k=16, row-partitioned over the N GPUs with the mesh engine (objects owner-partitioned, bids pushed
+into the owner's HBM over NVLink inside the bid kernel; csrc/sla_mesh.cuh) -- "scaling": "strong".  The same line carries
+the one-GPU solve of the same instance measured on rank 0 in the same run (`one_gpu`), a slice-by-slice comparison of the two
+solutions, and the cfg4 batch (8,192 independent instances) split over the ranks.  `--workload cfg3 --gpus N` still runs N
+independent replicas ("replicas").
+`--impl reference` times the reference's CPU algorithm (the oracle port; the Rust crate cannot be built here) on the same
+workload: cfg3 in full at N = 1; for cfg5 a bounded sample (the first 2,000,000 persons against all 64M objects).
 """
 import argparse
 import json
@@ -49,7 +54,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4"])
+    ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS) + ["cfg4"],
+                    help="auto: cfg3 on one GPU, cfg5 partitioned over the GPUs (mesh engine) on several")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -189,10 +195,51 @@ def run_oracle(workload, csr, reps):
     return times, arcs, obj
 
 
-def main_reference(args):
+REF_SAMPLE_ROWS = 2_000_000      # cfg5 on the CPU: persons [0, 2M) of the instance against all 64M objects per step
+
+
+def main_reference_sample(args):
+    """The reference's CPU solver on a bounded sample of cfg5 (the full instance takes ~8 s per solve and 9 GB of host
+    arrays): the first REF_SAMPLE_ROWS persons of the same generated instance, all 64M objects -- so prices and owners
+    are as cache-hostile as in the full problem and bid-arcs/s is comparable."""
+    import numpy as np
+    from oracle import oracle as O
+    from sparse_linear_assignment_b200 import generators as G
+    kind, n, m, k, planted, eps = WORKLOADS["cfg5"]
+    rows = REF_SAMPLE_ROWS
+    rp, c, v = G.kregular_host(n, m, k, seed=args.seed, planted=planted, row_begin=0, row_count=rows)
+    total_arcs, total_t, obj = 0, 0.0, None
+    t0 = time.perf_counter()
+    for step in range(max(args.warmup, 0) + args.steps):
+        s = O.OracleSolver(kind, rows, m, rows * k)
+        s.load_csr(rows, m, rp, c, v)
+        t = time.perf_counter()
+        s.solve(maximize=False, eps=1.0 / m)          # the eps of the full instance (1 / num_cols, ksparse.rs:167)
+        dt = time.perf_counter() - t
+        if step >= max(args.warmup, 0):
+            total_arcs += s.bid_arcs
+            total_t += dt
+        obj = s.get_objective()
+        del s
+    value = total_arcs / total_t
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": describe("cfg5"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"persons [0, {rows}) of the cfg5 instance against all {m} objects per step, solve() only "
+                                   f"(the reference is single-threaded; C restatement of src/ksparse.rs, goldens verified)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "objective_of_sample": obj, "wall_s": time.perf_counter() - t0}))
+    return 0
+
+
+def main_reference(args, partitioned=False):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if partitioned or args.workload == "cfg5":
+        return main_reference_sample(args)
     csr, _keep = host_instance(args.workload, args.seed, pinned=False)
     for _ in range(max(args.warmup, 0)):
         run_oracle(args.workload, csr, 1)
@@ -365,6 +412,213 @@ def main_cfg4(args):
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
+    return 0
+
+
+def slice_checksums(np, p2o, o2p, prices, first_row, first_object):
+    """Order-sensitive 64-bit checksums of a rank's slices of a solution (wrap-around arithmetic)."""
+    def cs(a, off):
+        a = np.ascontiguousarray(a)
+        w = np.arange(off + 1, off + 1 + a.size, dtype=np.uint64)
+        return int(np.bitwise_xor.reduce(a.view(np.uint64 if a.dtype.itemsize == 8 else a.dtype).astype(np.uint64) * w +
+                                         (w << np.uint64(7)))) if a.size else 0
+    return [cs(p2o, first_row), cs(o2p, first_object), cs(prices, first_object)]
+
+
+def main_mesh(args):
+    """cfg5 -- ONE KhoslaSolver instance, 16M persons x 64M objects, k=16 -- row-partitioned over the ranks' GPUs with the
+    mesh engine; rank 0 also solves the whole instance alone (the honest comparison point: it fits one B200)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import sparse_linear_assignment_b200 as S
+    from sparse_linear_assignment_b200 import _lib, generators as G
+    from sparse_linear_assignment_b200.distributed import MeshKhoslaSolver, shard_rows
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    S.build_library()
+    device = torch.device("cuda", local_rank)
+    kind, n, m, k, planted, eps = WORKLOADS["cfg5"]
+    begin, count = shard_rows(n, world, rank)
+
+    def barrier():
+        dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(device)
+
+    def allmax(x):
+        t = torch.tensor(x, dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def allsum(x):
+        t = torch.tensor(x, dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.tolist()
+
+    # ---- value: shards generated in HBM, results left in HBM ---------------------------------------------------------------
+    solver, _ = S.KhoslaSolver.new(count, m, count * k, device=local_rank)
+    ctx = solver._context()
+    _lib.check(ctx, _lib.load().sla_generate_device_shard(ctx, n, m, k, args.seed, G.VALUE_LO, G.VALUE_HI, 0, begin, count))
+    solver._num_rows, solver._num_cols, solver._dirty, solver._device_only = count, m, False, True
+    mesh = MeshKhoslaSolver(solver).setup()
+    stream = torch.cuda.ExternalStream(solver._context_stream(), device=device)
+    for _ in range(max(args.warmup, 3)):
+        mesh.solve(False, eps, download=False, totals=False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    ms_dev, launches, r1 = 0.0, 0, []
+    for _ in range(args.steps):
+        res = mesh.solve(False, eps, download=False, totals=False)
+        ms_dev += res["stats"]["ms_solve"]
+        launches += res["stats"]["kernel_launches"]
+        r1.append(mesh.shard.round1_ms())
+    ev1.record(stream)
+    barrier()
+    ms_value = ev0.elapsed_time(ev1)
+    clocks = sampler.summary()
+    st = mesh.solve(False, eps, download=False, totals=True)["stats"]
+    objective = mesh.objective()
+    vb = solver.scan_value_bytes()
+    ms_value, ms_dev = allmax([ms_value, ms_dev])
+    launches = allsum([float(launches)])[0]
+    r1_max = allmax([sorted(r1)[len(r1) // 2]])[0]
+
+    # ---- the same instance on ONE GPU (rank 0), and a slice-by-slice comparison of the two solutions --------------------
+    res = mesh.solve(False, eps, download=True, totals=False)
+    own = res["owned"]
+    mine = slice_checksums(np, res["p2o"], res["o2p"], res["prices"], begin, own["first_object"])
+    spans = torch.tensor([begin, count, own["first_object"], own["num_owned"]] + [x >> 1 for x in mine] + [x & 1 for x in mine],
+                         dtype=torch.int64, device=device)
+    allspans = [torch.zeros_like(spans) for _ in range(world)]
+    dist.all_gather(allspans, spans)
+    one = None
+    if rank == 0:
+        single, z = S.KhoslaSolver.new(n, m, n * k, device=local_rank)
+        G.kregular_device(single, n, m, k, seed=args.seed)
+        for _ in range(3):
+            single.solve_resident(False, eps)
+        t1 = sorted(single.solve_resident(False, eps)["ms_solve"] for _ in range(max(min(args.steps, 10), 3)))
+        s1 = single.last_stats
+        single.download_solution(z)
+        pr = single.prices()
+        same = s1["bid_arcs"] == st["global_bid_arcs"] and s1["rounds"] == st["rounds"] and s1["num_unassigned"] == st["global_num_unassigned"]
+        for sp in allspans:
+            b_, c_, fo, no = [int(x) for x in sp[:4].tolist()]
+            theirs = [(int(h) << 1) | int(l) for h, l in zip(sp[4:7].tolist(), sp[7:10].tolist())]
+            ref = slice_checksums(np, z.person_to_object[b_:b_ + c_], z.object_to_person[fo:fo + no], pr[fo:fo + no], b_, fo)
+            same = same and theirs == ref
+        one = {"ms_per_step": t1[len(t1) // 2], "bid_arcs_per_s": s1["bid_arcs"] / (t1[len(t1) // 2] * 1e-3),
+               "objective": single.device_objective(), "rounds": s1["rounds"], "scan_value_bytes": single.scan_value_bytes(),
+               "identical_to_partitioned": bool(same and single.device_objective() == objective),
+               "compared": "bid_arcs, rounds, num_unassigned, objective, and checksums of every rank's person_to_object / "
+                           "object_to_person / prices slices against the same slices of the one-GPU solution"}
+        del single, z, pr
+    barrier()
+
+    # ---- e2e: every rank's shard in (page-locked) host memory -> upload + solve + download of its slices, per step ----------
+    hs, hz = S.KhoslaSolver.new(count, m, count * k, device=local_rank)
+    hs.init(count, m)
+    hs._i_starts_stops.resize(count + 1, 0)
+    hs._j_counts.resize(count, k)
+    hs._column_indices.resize(count * k, 0)
+    hs._values.resize(count * k, 0.0)
+    G.kregular_host(n, m, k, seed=args.seed, row_begin=begin, row_count=count,
+                    out=(hs._i_starts_stops.view, hs._column_indices.view, hs._values.view))
+    hmesh = MeshKhoslaSolver(hs).setup()
+    hv = hs.values()
+    e2e_steps = max(min(args.steps, 5), 2)
+    e2e_s, e2e_arcs = 0.0, 0
+    for step in range(2 + e2e_steps):
+        if hv[0] < 0:
+            np.negative(hv, out=hv)                      # untimed: hand the solver the caller's original costs again
+        hs._dirty = True                                 # a fresh problem every step
+        barrier()
+        t0 = time.perf_counter()
+        r = hmesh.solve(False, eps, download=True, totals=False)
+        torch.cuda.synchronize(device)
+        dt = time.perf_counter() - t0
+        if step >= 2:
+            e2e_s += dt
+            e2e_arcs += r["stats"]["bid_arcs"]
+    h2d, value_bytes = hs.last_upload()
+    d2h = 4 * count + 12 * r["owned"]["num_owned"]
+    e2e_s = allmax([e2e_s])[0]
+    e2e_arcs, h2d_all, d2h_all = allsum([float(e2e_arcs), float(h2d), float(d2h)])
+
+    # ---- the cfg4 batch split over the same ranks (secondary block) ----------------------------------------------------------
+    per = CFG4["instances"] // world
+    bs = S.BatchSolver("forward", device=local_rank)
+    bs.generate_device(per, rank * per, CFG4["rows"], CFG4["cols"], CFG4["k"], seed=0, planted=True)
+    for _ in range(3):
+        bs.solve(download=False, per_instance=False)
+    barrier()
+    c4_ms = c4_arcs = 0.0
+    c4_steps = max(min(args.steps, 5), 2)
+    for _ in range(c4_steps):
+        tot = bs.solve(download=False, per_instance=False)["total"]
+        c4_ms += tot["ms_solve"]
+        c4_arcs += tot["bid_arcs"]
+    c4_ms = allmax([c4_ms])[0]
+    c4_arcs, c4_un = allsum([c4_arcs, float(tot["num_unassigned"])])
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        arcs = st["global_bid_arcs"]
+        a1, b1 = count * k, count                       # round 1 on one rank: every local person bids
+        alg = (4 + vb) * a1 + 8 * b1
+        ach = alg / (r1_max * 1e-3) / 1e9 if r1_max > 0 else None
+        cfg = describe("cfg5")
+        line = {
+            "metric": METRIC, "value": arcs * args.steps / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "parallelism": f"one instance over {world} GPUs: persons row-partitioned ({count} per rank), objects owner-partitioned "
+                           f"({own['shard_objects']} per rank); bids pushed into the owner's HBM over NVLink peer mappings inside "
+                           f"the bid kernel, flag barriers between the kernels, no collective and no host sync per round",
+            "clocks": clocks,
+            "device_ms_per_step": ms_dev / args.steps,
+            "e2e": {"value": e2e_arcs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "h2d_value_bytes": value_bytes,
+                    "d2h_bytes_per_step": int(d2h_all), "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                    "what": "MeshKhoslaSolver.solve with every rank's shard in page-locked host memory: upload (u16 values on "
+                            "the wire, in-place sign normalisation of the host copy), solve, download of the rank's "
+                            "person_to_object rows and of the object_to_person / prices slices it owns"},
+            "gpu_launches": int(launches),
+            "roofline": None if ach is None else {
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": "mesh_bid_kernel<PRICE_ZERO" + (",u16>" if vb == 2 else ">"),
+                "launch": f"round 1 on one rank ({b1} local persons bid): CSR scan + push of the bids to the owners; event-record "
+                          f"nodes around the kernel inside the solve graph, median over the timed solves, max over ranks",
+                "bidders": b1, "arcs": a1, "algorithmic_bytes": alg, "launch_us": r1_max * 1e3, "peak_source": peak_src,
+                "value_bytes_in_hbm": vb,
+                "nvlink_bytes_pushed": int(16 * b1 * (world - 1) / world),
+                "note": "the kernel also stores 16 B per bid into the owners' inboxes, (world-1)/world of them over NVLink"},
+            "nvlink": {"bid_entries_bytes_per_solve": int(16 * st["global_bids"] * (world - 1) / world),
+                       "reply_bytes_per_solve": int(st["global_bids"] / 8 * (world - 1) / world),
+                       "price_gather_sector_bytes_upper_bound": int(32 * (arcs - n * k) * (world - 1) / world),
+                       "rounds": st["rounds"],
+                       "note": "bytes that cross NVLink for the whole job; gathers: 32 B sector per arc scanned after round 1 "
+                               "(upper bound: the bound-pruned scan fetches fewer)"},
+            "one_gpu": one,
+            "vs_one_gpu": None if not one else one["ms_per_step"] / (ms_value / args.steps),
+            "cfg4_batch": {"value": c4_arcs / (c4_ms * 1e-3), "unit": UNIT, "ms_per_step": c4_ms / c4_steps, "steps": c4_steps,
+                           "instances": CFG4["instances"], "instances_per_rank": per, "num_unassigned": int(c4_un),
+                           "scaling": "strong", "note": "8,192 independent 512x512 k=32 Forward instances split over the ranks, "
+                                                        "one CTA per instance, no collective; device time, max over ranks"},
+            "cpu_baseline": None,
+            "solve": {k_: st[k_] for k_ in ("rounds", "graph_launches", "kernel_launches")} |
+                     {"bids": st["global_bids"], "bid_arcs": st["global_bid_arcs"], "num_unassigned": st["global_num_unassigned"]},
+            "objective": objective,
+        }
+        print(json.dumps(line))
+    barrier()
+    dist.destroy_process_group()
     return 0
 
 
@@ -552,8 +806,9 @@ def main_ours(args):
         line = {
             "metric": METRIC, "value": arcs / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_value / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "parallelism": "1 GPU" if world == 1 else f"{world} independent instances, one per GPU (no collective)",
+            "scaling": "weak" if world == 1 else "replicas", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "parallelism": "1 GPU" if world == 1 else f"{world} independent instances, one per GPU (no collective): replicas, "
+                                                      f"not scaling of one instance",
             "clocks": clocks,
             "e2e": {"value": e2e_arcs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "h2d_value_bytes": value_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
@@ -578,6 +833,16 @@ def main_ours(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    mesh = (a.workload == "auto" and max(world_env, a.gpus) > 1) or (a.workload == "cfg5" and world_env > 1)
+    if a.workload == "auto":
+        a.workload = "cfg5" if mesh else "cfg3"
+    if a.gpus > 1 and "WORLD_SIZE" not in os.environ and a.impl == "ours":
+        # started by hand without torchrun: re-launch as one rank per GPU (the driver launches torchrun itself)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:])
     if a.workload == "cfg4":
         sys.exit(main_cfg4(a))
-    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
+    if a.impl == "reference":
+        sys.exit(main_reference(a, partitioned=mesh))
+    sys.exit(main_mesh(a) if mesh else main_ours(a))

@@ -266,6 +266,10 @@ int sla_mesh_poll(sla_ctx *ctx, int *done, uint32_t *round, uint32_t *local_queu
  * (sla_mesh_owned: first_object .. first_object + num_owned).  stats: this rank's share (the caller adds them up). */
 int sla_mesh_finish(sla_ctx *ctx, uint32_t *person_to_object, uint32_t *object_to_person, double *prices, sla_stats *stats);
 int sla_mesh_owned(sla_ctx *ctx, uint32_t *shard_objects, uint32_t *num_owned, uint32_t *first_object, uint32_t *first_row);
+/* Duration of the first round's bid kernel of the last solve (event-record nodes inside the first graph), and this rank's
+ * share of get_objective (solver.rs:110-142; exact for integer weights) -- the caller adds the shares up. */
+int sla_mesh_round1_ms(sla_ctx *ctx, float *bid_ms);
+int sla_mesh_objective(sla_ctx *ctx, double *objective);
 
 #ifdef __cplusplus
 }

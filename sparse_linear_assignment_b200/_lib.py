@@ -156,6 +156,8 @@ SIGNATURES = {
     "sla_mesh_poll": (C.c_int, [_vp, C.POINTER(C.c_int), _u32p, _u32p]),
     "sla_mesh_finish": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(SlaStats)]),
     "sla_mesh_owned": (C.c_int, [_vp, _u32p, _u32p, _u32p, _u32p]),
+    "sla_mesh_round1_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "sla_mesh_objective": (C.c_int, [_vp, _f64p]),
 }
 
 _lib = None

@@ -601,7 +601,7 @@ struct sla_mesh_state {
     uint64_t exec_generation = 0;
     const void* exec_vals16 = nullptr;
     bool exec_first = false;
-    double eps = 0.0;
+    double eps = 0.0, gfirst = 0.0;
     int flip = 0;
     uint32_t launches = 0, graph_launches = 0;
     double timeout_s = 20.0;
@@ -864,6 +864,7 @@ int sla_mesh_begin(sla_ctx* ctx, int maximize, double eps, double global_w_min, 
     ms->active = true;
     ms->eps = s.eps;
     ms->flip = flip ? 1 : 0;
+    ms->gfirst = global_first_value;
     ms->launches = 1;
     ms->graph_launches = 0;
     ctx->has_solution = false;
@@ -929,7 +930,13 @@ int sla_mesh_solve(sla_ctx* ctx) {
             cudaGraph_t graph = nullptr;
             CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             for (int r = 0; r < rounds; ++r)
-                for (int k = 0; k < 4; ++k) mesh_launch_phase(ctx, p, k, first && r == 0);
+                for (int k = 0; k < 4; ++k) {
+                    // the first round's scan + push is bracketed by two event-record nodes (sla_mesh_round1_ms)
+                    const bool bracket = first && r == 0 && k == 0;
+                    if (bracket) cudaEventRecordWithFlags(ctx->ev[3], ctx->stream, cudaEventRecordExternal);
+                    mesh_launch_phase(ctx, p, k, first && r == 0);
+                    if (bracket) cudaEventRecordWithFlags(ctx->ev[4], ctx->stream, cudaEventRecordExternal);
+                }
             cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
             if (e != cudaSuccess) return fail(ctx, SLA_ERR_CUDA, std::string("cudaStreamEndCapture(mesh): ") + cudaGetErrorString(e));
             e = cudaGraphInstantiate(&ms->exec, graph, 0);
@@ -999,6 +1006,38 @@ int sla_mesh_finish(sla_ctx* ctx, uint32_t* person_to_object, uint32_t* object_t
     ms->active = false;
     ctx->has_solution = false;      // the plain arrays hold this rank's slices only: the single-GPU post-processing calls do not apply
     ctx->best_dirty = true;
+    return SLA_OK;
+}
+
+// Duration of the first round's bid kernel (scan of all local rows + push of the bids) of the last solve, from the two
+// event-record nodes around it in the first graph; this rank's objective share (sum of the chosen arcs' values of the
+// local rows, exact for integer weights; get_objective, solver.rs:110-142) -- the caller adds the shares up.
+int sla_mesh_round1_ms(sla_ctx* ctx, float* bid_ms) {
+    if (!ctx || !bid_ms) return SLA_ERR_INVALID;
+    int rc = mesh_check(ctx, true, false);
+    if (rc) return rc;
+    *bid_ms = 0.f;
+    if (cudaEventElapsedTime(bid_ms, ctx->ev[3], ctx->ev[4]) != cudaSuccess) { cudaGetLastError(); *bid_ms = 0.f; }
+    return SLA_OK;
+}
+
+int sla_mesh_objective(sla_ctx* ctx, double* objective) {
+    if (!ctx || !objective) return SLA_ERR_INVALID;
+    int rc = mesh_check(ctx, true, false);
+    if (rc) return rc;
+    if (ctx->mesh->active) return fail(ctx, SLA_ERR_STATE, "mesh: sla_mesh_objective needs a finished solve");
+    CU(cudaSetDevice(ctx->device));
+    const Params p = make_params(ctx);
+    const uint32_t flip = ctx->dev_sign < 0 ? 0x80000000u : 0u;
+    objective_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p, ctx->n_rows, flip, ctx->d_partial);
+    CU(cudaMemcpyAsync(ctx->h_partial, ctx->d_partial, (size_t)ctx->grid_wide * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    double sum = 0.0;
+    for (int b = 0; b < ctx->grid_wide; ++b) sum += ctx->h_partial[b];
+    // reference src/solver.rs:111-137: the sign is taken from the (current, possibly negated) first value of the instance
+    const double first_eff = ctx->mesh->flip ? -ctx->mesh->gfirst : ctx->mesh->gfirst;
+    *objective = (first_eff >= 0.0) ? sum : -sum;
     return SLA_OK;
 }
 

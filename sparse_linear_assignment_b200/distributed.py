@@ -338,6 +338,16 @@ class MeshShard:
                                                       C.byref(st)))
         return p2o, o2p, prices, st.as_dict()
 
+    def round1_ms(self) -> float:
+        out = C.c_float()
+        _lib.check(self.ctx, self.lib.sla_mesh_round1_ms(self.ctx, C.byref(out)))
+        return float(out.value)
+
+    def objective(self) -> float:
+        out = C.c_double()
+        _lib.check(self.ctx, self.lib.sla_mesh_objective(self.ctx, C.byref(out)))
+        return float(out.value)
+
     def close(self):
         for ptr in self._imported:
             self.lib.sla_ipc_release(self.solver.device, ptr)
@@ -429,11 +439,9 @@ class MeshKhoslaSolver:
             dist.barrier(group=self.group)      # every rank has mapped every block before anybody starts a solve
         return self
 
-    def solve(self, maximize: bool = False, eps: Optional[float] = None, download: bool = True, gather: bool = False) -> dict:
-        if self.shard is None:
-            self.setup()
-        sh = self.shard
-        lo, hi, first = sh.local_value_range()
+    def _global_range(self):
+        """Global (min, max, first value) of the instance: one small all-reduce, cached while the shards stay resident."""
+        lo, hi, first = self.shard.local_value_range()
         rng = torch.tensor([-lo, hi, first if self.rank == 0 else 0.0], dtype=torch.float64, device=self.dev)
         if self.world > 1:
             mx = rng[:2].clone()
@@ -441,21 +449,47 @@ class MeshKhoslaSolver:
             f = rng[2:].clone()
             dist.all_reduce(f, op=dist.ReduceOp.SUM, group=self.group)
             rng = torch.cat([mx, f])
-        gmin, gmax, gfirst = -float(rng[0].item()), float(rng[1].item()), float(rng[2].item())
+        return -float(rng[0].item()), float(rng[1].item()), float(rng[2].item())
+
+    def solve(self, maximize: bool = False, eps: Optional[float] = None, download: bool = True, gather: bool = False,
+              totals: bool = True) -> dict:
+        if self.shard is None:
+            self.setup()
+        sh = self.shard
+        # a KhoslaSolver with host storage: mirror a changed CSR into HBM, with the in-place sign normalisation of the
+        # host copy of `values` that init_solve performs (solver.rs:209-216); every rank decides by its own first value
+        # (inputs with mixed signs are not supported by the reference either)
+        sync = getattr(self.solver, "_sync_device", None)
+        resynced = False
+        if sync is not None and getattr(self.solver, "_dirty", False) and not getattr(self.solver, "_device_only", False):
+            sync(maximize)
+            self.solver._pre_negated = False
+            resynced = True
+        if resynced or getattr(self, "_range", None) is None:
+            self._range = self._global_range()
+        gmin, gmax, gfirst = self._range
         sh.begin(maximize, eps, gmin, gmax, gfirst)
         sh.solve()                                   # graphs of rounds; the ranks meet only in the kernels' flag barriers
         p2o, o2p, prices, st = sh.finish(download)
-        tot = torch.tensor([st["num_unassigned"], st["bids"], st["bid_arcs"]], dtype=torch.int64, device=self.dev)
-        if self.world > 1:
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
         st = dict(st)
-        st["global_num_unassigned"], st["global_bids"], st["global_bid_arcs"] = [int(x) for x in tot.tolist()]
+        if totals:
+            tot = torch.tensor([st["num_unassigned"], st["bids"], st["bid_arcs"]], dtype=torch.int64, device=self.dev)
+            if self.world > 1:
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+            st["global_num_unassigned"], st["global_bids"], st["global_bid_arcs"] = [int(x) for x in tot.tolist()]
         own = sh.owned()
         out = dict(p2o=p2o, o2p=o2p, prices=prices, stats=st, owned=own, row_begin=int(self.row_begins[self.rank]),
                    global_rows=int(self.row_begins[-1]))
         if gather and download:
             out.update(self._gather_solution(p2o, o2p, prices, own))
         return out
+
+    def objective(self) -> float:
+        """get_objective (solver.rs:110-142) of the last solve: the ranks' shares added up (exact for integer weights)."""
+        t = torch.tensor([self.shard.objective()], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
 
     def _gather_solution(self, p2o, o2p, prices, own):
         """All ranks' slices on every rank (tests and small instances; large ones keep their slices)."""
