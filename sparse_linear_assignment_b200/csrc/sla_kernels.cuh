@@ -87,13 +87,105 @@ __global__ void __launch_bounds__(kWideThreads) bid_wide_kernel(const Params p) 
     else      bid_wide_body<LPR, PRICE_LDG>(p, qlen, identity, cur ? p.queue[1] : p.queue[0], algo, eps, thr, pbits, sf, h.person_base);
 }
 
-// Regular-CSR variant (every row has exactly K arcs, K % 8 == 0: all of BASELINE.json's configs): no row-extent
-// loads (a = i * K), no masking, 8 arcs per lane per step through 256-bit loads.  LPR8 lanes share one row.
+// One row of a uniform-degree CSR (K <= 8 * LPR8: one 8-arc chunk per lane) through the bound-pruned gather: see
+// bid_regular_body.  All LPR8 lanes of the group call it (also for an invalid slot); the finished choice is in every lane.
+template <int LPR8, int MODE, bool NARROW>
+__device__ __forceinline__ void scan_row_pruned(Choice& c, const Params& p, const double* prices, const uint32_t i,
+                                                const bool valid, const uint32_t K, const uint32_t sign_flip, const int lane) {
+    const uint32_t keyflip = sign_flip ? 0xFFFFu : 0u;
+    const uint32_t off = 8u * (uint32_t)lane;
+    const bool has = valid && off < K;
+    uint32_t cj[8];
+    double vv[8];
+    int key[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { cj[t] = 0u; vv[t] = neg_inf(); key[t] = (int)0x80000000; }
+    uint32_t g = 0;
+    if (has) {
+        g = i * K + off;
+        ld_stream_u8(p.cols + g, cj);
+        if (NARROW) {
+            const uint4 w = ld_stream_u16x8(p.vals16 + g);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t x = (t & 1) ? (ww[t >> 1] >> 16) : (ww[t >> 1] & 0xFFFFu);
+                const double d = u16_to_f64(x);
+                vv[t] = __hiloint2double(__double2hiint(d) ^ (int)sign_flip, __double2loint(d));
+                key[t] = (int)(x ^ keyflip);                 // exact order of the effective values
+            }
+        } else {
+            double raw[8];
+            ld_stream_d4(p.vals + g, raw);
+            ld_stream_d4(p.vals + g + 4, raw + 4);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int hi = __double2hiint(raw[t]) ^ (int)sign_flip;
+                vv[t] = __hiloint2double(hi, __double2loint(raw[t]));
+                key[t] = hi ^ ((hi >> 31) & 0x7FFFFFFF);     // order of the high words: any two probes give a valid bound
+            }
+        }
+    }
+    // the lane's two probes: (approximately) its two most valuable arcs
+    int b1 = (int)0x80000000, b2 = (int)0x80000000;
+    uint32_t i1 = 0u, i2 = 1u, c1 = cj[0], c2 = cj[1];
+    double v1 = vv[0], v2 = vv[1];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const bool gt = key[t] > b1 || t == 0, gs = key[t] > b2 || t <= 1;
+        i2 = gt ? i1 : (gs ? (uint32_t)t : i2);
+        c2 = gt ? c1 : (gs ? cj[t] : c2);
+        v2 = gt ? v1 : (gs ? vv[t] : v2);
+        b2 = gt ? b1 : (gs ? key[t] : b2);
+        i1 = gt ? (uint32_t)t : i1;
+        c1 = gt ? cj[t] : c1;
+        v1 = gt ? vv[t] : v1;
+        b1 = gt ? key[t] : b1;
+    }
+    double p1 = 0.0, p2 = 0.0, hiP = neg_inf(), loP = neg_inf();
+    if (has) {
+        p1 = ld_price<MODE>(prices, c1);
+        p2 = ld_price<MODE>(prices, c2);
+        const double a = v1 - p1, b = v2 - p2;
+        hiP = a > b ? a : b;
+        loP = a > b ? b : a;
+    }
+#pragma unroll
+    for (int m = LPR8 / 2; m >= 1; m >>= 1) {
+        const double oh = __shfl_xor_sync(0xffffffffu, hiP, m);
+        const double ol = __shfl_xor_sync(0xffffffffu, loP, m);
+        const double mn = hiP > oh ? oh : hiP;          // the smaller of the two maxima
+        double l2 = loP > ol ? loP : ol;
+        l2 = mn > l2 ? mn : l2;
+        hiP = hiP > oh ? hiP : oh;
+        loP = l2;
+    }
+    const double bound = loP;
+    double pr[8];
+    bool use[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const bool probe = ((uint32_t)t == i1) || ((uint32_t)t == i2);
+        use[t] = has && (probe || vv[t] >= bound);
+        pr[t] = 0.0;
+        if (has && !probe && vv[t] >= bound) pr[t] = ld_price<MODE>(prices, cj[t]);
+    }
+    choice_init(c);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const double pt = ((uint32_t)t == i1) ? p1 : (((uint32_t)t == i2) ? p2 : pr[t]);
+        choice_update(c, use[t] ? (vv[t] - pt) : neg_inf(), vv[t], g + t, cj[t]);
+    }
+    choice_group_reduce<LPR8>(c);
+}
+
 #ifndef SLA_PRUNE_MIN_QUEUE
 #define SLA_PRUNE_MIN_QUEUE 32768
 #endif
 constexpr uint32_t kPruneMinQueue = SLA_PRUNE_MIN_QUEUE;   // bidders from which the gathering scan prunes by value bound
 
+// Regular-CSR variant (every row has exactly K arcs, K % 8 == 0: all of BASELINE.json's configs): no row-extent
+// loads (a = i * K), no masking, 8 arcs per lane per step through 256-bit loads.  LPR8 lanes share one row.
 template <int LPR8, int MODE, bool NARROW>
 __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t qlen, const bool identity,
                                                  const uint32_t* __restrict__ queue, const uint32_t algo, const double eps,
@@ -175,97 +267,14 @@ __device__ __forceinline__ void bid_regular_body(const Params& p, const uint32_t
         // bit for bit (ksparse.rs:199-214, symmetric.rs:361-376).  What changes is the number of scattered 8-byte
         // gathers per row: 2 per lane plus the few arcs that can still matter, instead of all K -- the gathers (one L1
         // wavefront each), not the CSR stream, bound the unpruned scan.
-        const uint32_t keyflip = sign_flip ? 0xFFFFu : 0u;
         for (uint32_t base = 0; base < qlen; base += ngroups) {
             if (base + warp_group0 >= qlen) break;   // warp-uniform: the whole warp is past the end
             const uint32_t q = base + group;
             const bool valid = q < qlen;
-            const uint32_t off = 8u * (uint32_t)lane;
-            const bool has = valid && off < K;
-            uint32_t i = 0, cj[8];
-            double vv[8];
-            int key[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) { cj[t] = 0u; vv[t] = neg_inf(); key[t] = (int)0x80000000; }
-            uint32_t g = 0;
+            uint32_t i = 0;
             if (valid) i = identity ? q : __ldg(queue + q);
-            if (has) {
-                g = i * K + off;
-                ld_stream_u8(p.cols + g, cj);
-                if (NARROW) {
-                    const uint4 w = ld_stream_u16x8(p.vals16 + g);
-                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const uint32_t x = (t & 1) ? (ww[t >> 1] >> 16) : (ww[t >> 1] & 0xFFFFu);
-                        const double d = u16_to_f64(x);
-                        vv[t] = __hiloint2double(__double2hiint(d) ^ (int)sign_flip, __double2loint(d));
-                        key[t] = (int)(x ^ keyflip);                 // exact order of the effective values
-                    }
-                } else {
-                    double raw[8];
-                    ld_stream_d4(p.vals + g, raw);
-                    ld_stream_d4(p.vals + g + 4, raw + 4);
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const int hi = __double2hiint(raw[t]) ^ (int)sign_flip;
-                        vv[t] = __hiloint2double(hi, __double2loint(raw[t]));
-                        key[t] = hi ^ ((hi >> 31) & 0x7FFFFFFF);     // order of the high words: any two probes give a valid bound
-                    }
-                }
-            }
-            // the lane's two probes: (approximately) its two most valuable arcs
-            int b1 = (int)0x80000000, b2 = (int)0x80000000;
-            uint32_t i1 = 0u, i2 = 1u, c1 = cj[0], c2 = cj[1];
-            double v1 = vv[0], v2 = vv[1];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const bool gt = key[t] > b1 || t == 0, gs = key[t] > b2 || t <= 1;
-                i2 = gt ? i1 : (gs ? (uint32_t)t : i2);
-                c2 = gt ? c1 : (gs ? cj[t] : c2);
-                v2 = gt ? v1 : (gs ? vv[t] : v2);
-                b2 = gt ? b1 : (gs ? key[t] : b2);
-                i1 = gt ? (uint32_t)t : i1;
-                c1 = gt ? cj[t] : c1;
-                v1 = gt ? vv[t] : v1;
-                b1 = gt ? key[t] : b1;
-            }
-            double p1 = 0.0, p2 = 0.0, hiP = neg_inf(), loP = neg_inf();
-            if (has) {
-                p1 = __ldg(p.prices + c1);
-                p2 = __ldg(p.prices + c2);
-                const double a = v1 - p1, b = v2 - p2;
-                hiP = a > b ? a : b;
-                loP = a > b ? b : a;
-            }
-#pragma unroll
-            for (int m = LPR8 / 2; m >= 1; m >>= 1) {
-                const double oh = __shfl_xor_sync(0xffffffffu, hiP, m);
-                const double ol = __shfl_xor_sync(0xffffffffu, loP, m);
-                const double mn = hiP > oh ? oh : hiP;          // the smaller of the two maxima
-                double l2 = loP > ol ? loP : ol;
-                l2 = mn > l2 ? mn : l2;
-                hiP = hiP > oh ? hiP : oh;
-                loP = l2;
-            }
-            const double bound = loP;
-            double pr[8];
-            bool use[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const bool probe = ((uint32_t)t == i1) || ((uint32_t)t == i2);
-                use[t] = has && (probe || vv[t] >= bound);
-                pr[t] = 0.0;
-                if (has && !probe && vv[t] >= bound) pr[t] = __ldg(p.prices + cj[t]);
-            }
             Choice c;
-            choice_init(c);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const double pt = ((uint32_t)t == i1) ? p1 : (((uint32_t)t == i2) ? p2 : pr[t]);
-                choice_update(c, use[t] ? (vv[t] - pt) : neg_inf(), vv[t], g + t, cj[t]);
-            }
-            choice_group_reduce<LPR8>(c);
+            scan_row_pruned<LPR8, MODE, NARROW>(c, p, p.prices, i, valid, K, sign_flip, lane);
             if (valid && lane == 0) {
                 const Bid r = make_bid<MODE>(c, algo, eps, threshold, p.prices);
                 if (r.dropped) {

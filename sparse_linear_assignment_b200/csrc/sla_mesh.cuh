@@ -28,6 +28,7 @@
 namespace sla {
 
 constexpr uint32_t kMeshChunkRows = 512;     // bidders one block stages in shared memory before it pushes them
+constexpr uint32_t kMeshPruneMinQueue = 4096; // local bidders from which the gathering scan prunes by value bound
 
 struct alignas(16) BidEntry {
     uint32_t obj_local;      // object id relative to the owner's first object
@@ -274,6 +275,9 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params 
     const uint32_t group = threadIdx.x / LPR8;
     const uint32_t keyflip = sign_flip ? 0xFFFFu : 0u;
 
+    // bound-pruned gather (scan_row_pruned): here the gathers it saves cross NVLink -- from 4 Ki bidders on this rank
+    const bool prune = !ZERO && K <= 8u * LPR8 && qlen >= kMeshPruneMinQueue && p.st->prune_ok != 0u;
+
     mesh_stage_reset(s);
     if (threadIdx.x == 0) { s.dropped = 0u; s.arcs = 0ull; }
     __syncthreads();
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params 
                 if (valid[u]) {
                     i[u] = identity ? q[u] : __ldg(queue + q[u]);
                     const uint32_t a = i[u] * K;
+                    if (!prune)
                     for (uint32_t off = 8u * (uint32_t)lane; off < K; off += 8u * LPR8) {
                         if (ZERO && NARROW) scan8_keys(kc[u], p.cols, p.vals16, a + off, off, keyflip);
                         else if (NARROW) scan8_narrow<MODE>(c[u], p.cols, p.vals16, mesh_prices, a + off, sign_flip);
@@ -306,6 +311,8 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params 
                 if (ZERO && NARROW) {
                     key_choice_group_reduce<LPR8>(kc[u]);
                     if (valid[u] && lane == 0) key_choice_to_f64(c[u], kc[u], i[u] * K, keyflip, sign_flip);
+                } else if (!ZERO && prune) {
+                    scan_row_pruned<LPR8, MODE, NARROW>(c[u], p, mesh_prices, i[u], valid[u], K, sign_flip, lane);
                 } else {
                     choice_group_reduce<LPR8>(c[u]);
                 }
@@ -853,6 +860,7 @@ int sla_mesh_begin(sla_ctx* ctx, int maximize, double eps, double global_w_min, 
     s.eps = std::isnan(eps) ? 1.0 / m : eps;                        // ksparse.rs:162-169
     s.target_eps = s.eps;
     s.threshold = (m / 2.0) * (w_max - w_min + s.eps);               // ksparse.rs:181
+    s.prune_ok = (ctx->opt_prune && s.eps >= 0.0) ? 1u : 0u;
     s.mesh_round = 1;
     s.mesh_epoch = ms->epoch;
     *ctx->h_state = s;
@@ -970,6 +978,7 @@ int sla_mesh_finish(sla_ctx* ctx, uint32_t* person_to_object, uint32_t* object_t
     if (rc) return rc;
     sla_mesh_state* ms = ctx->mesh;
     CU(cudaSetDevice(ctx->device));
+    join_workers(ctx);      // the in-place negation of the host `values` an upload may have started (solver.rs:214-216)
     if ((rc = poll_state(ctx))) return rc;
     const DevState f = *ctx->h_state;
     if (!f.done) return fail(ctx, SLA_ERR_STATE, "mesh: sla_mesh_finish called before the solve has ended");

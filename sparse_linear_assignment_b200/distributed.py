@@ -327,10 +327,14 @@ class MeshShard:
         n = self.solver.num_rows()
         p2o = o2p = prices = None
         if download:
+            # page-locked result buffers are kept across solves (cudaMallocHost costs milliseconds): the returned arrays
+            # are overwritten by the next finish(download=True) of this shard
             from .solver import host_array
-            p2o = host_array(n, np.uint32)
-            o2p = host_array(max(own["num_owned"], 1), np.uint32)[: own["num_owned"]]
-            prices = host_array(max(own["num_owned"], 1), np.float64)[: own["num_owned"]]
+            if getattr(self, "_out_shape", None) != (n, own["num_owned"]):
+                self._out = (host_array(n, np.uint32), host_array(max(own["num_owned"], 1), np.uint32)[: own["num_owned"]],
+                             host_array(max(own["num_owned"], 1), np.float64)[: own["num_owned"]])
+                self._out_shape = (n, own["num_owned"])
+            p2o, o2p, prices = self._out
         st = SlaStats()
         _lib.check(self.ctx, self.lib.sla_mesh_finish(self.ctx, p2o.ctypes.data if download else None,
                                                       o2p.ctypes.data if download and own["num_owned"] else None,

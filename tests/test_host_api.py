@@ -26,6 +26,26 @@ def test_library_exports_every_declared_symbol(sla):
     assert b"sm_100a" in lib.sla_version()
 
 
+def test_host_only_library_and_rust_binding_cover_the_header(sla):
+    """libsla_host.so (g++, no CUDA) exports the host-only entry points and maps no CUDA runtime; rust/src/ffi.rs
+    declares every function of include/sla.h (the Rust side is not compiled here: no toolchain)."""
+    from sparse_linear_assignment_b200 import _lib
+    host = C.CDLL(_lib.build_host_library())
+    for name in ("sla_generate_host", "sla_generate_host_ex"):
+        assert hasattr(host, name)
+    import subprocess
+    needed = subprocess.run(["ldd", _lib.HOST_LIB_PATH], capture_output=True, text=True).stdout
+    assert "cuda" not in needed.lower()
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "sla.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(sla_[a-z0-9_]+)\s*\(", header))
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (sla_[a-z0-9_]+)\(", ffi))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    for rel in ("rust/src/device.rs", "rust/build.rs", "rust/apply.py", "rust/patches/ksparse.rs.ed",
+                "rust/patches/symmetric.rs.ed", "rust/patches/lib.rs.ed", "rust/patches/Cargo.toml.ed"):
+        assert os.path.exists(os.path.join(ROOT, rel)), rel
+
+
 def test_no_gpu_means_loud_failure(sla):
     """Without a device the product path must fail, never fall back to a CPU solve."""
     import torch
