@@ -269,6 +269,8 @@ int sla_mesh_owned(sla_ctx *ctx, uint32_t *shard_objects, uint32_t *num_owned, u
 /* Duration of the first round's bid kernel of the last solve (event-record nodes inside the first graph), and this rank's
  * share of get_objective (solver.rs:110-142; exact for integer weights) -- the caller adds the shares up. */
 int sla_mesh_round1_ms(sla_ctx *ctx, float *bid_ms);
+/* Development aid (environment SLA_MESH_TIMELINE=1 at sla_mesh_create): %globaltimer stamps of the last solve, 8 per round. */
+int sla_mesh_timeline(sla_ctx *ctx, unsigned long long *out, size_t capacity);
 int sla_mesh_objective(sla_ctx *ctx, double *objective);
 
 #ifdef __cplusplus

@@ -136,4 +136,5 @@ extern "C" {
                           first_row: *mut u32) -> c_int;
     pub fn sla_mesh_round1_ms(ctx: *mut sla_ctx, bid_ms: *mut f32) -> c_int;
     pub fn sla_mesh_objective(ctx: *mut sla_ctx, objective: *mut f64) -> c_int;
+    pub fn sla_mesh_timeline(ctx: *mut sla_ctx, out: *mut u64, capacity: usize) -> c_int;
 }

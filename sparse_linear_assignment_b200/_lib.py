@@ -158,6 +158,7 @@ SIGNATURES = {
     "sla_mesh_owned": (C.c_int, [_vp, _u32p, _u32p, _u32p, _u32p]),
     "sla_mesh_round1_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "sla_mesh_objective": (C.c_int, [_vp, _f64p]),
+    "sla_mesh_timeline": (C.c_int, [_vp, _vp, C.c_size_t]),
 }
 
 _lib = None

@@ -305,17 +305,17 @@ enum PriceMode : int {
     PRICE_MESH = 5    // `prices` points at a MeshView: the price lives in the owner rank's HBM (peer-mapped over NVLink)
 };
 
-// Mesh engine (sla_mesh.cuh): object state is owner-partitioned over up to kMeshMaxRanks GPUs, one 32-byte cell (one
-// sector) per object, so that a bid resolution touches one sector and a remote price gather fetches one.
+// Mesh engine (sla_mesh.cuh): object state is owner-partitioned over up to kMeshMaxRanks GPUs.  Price and owner of an
+// object share one 16-byte cell (a remote price gather and an owner update touch the same sector); the packed bid words
+// of the current round live in a separate, owner-local u64 array -- 8 B per object, so that the election of a round
+// (one atomicMax and one read per bid) works on a quarter of the footprint.
 constexpr int kMeshMaxRanks = 8;
-struct alignas(32) ObjCell {
-    unsigned long long best;   // packed bid word of the current round, 0 = no bid
+struct alignas(16) ObjCell {
     double price;
     uint32_t owner;            // global person id or SLA_DEV_NONE
-    uint32_t pad0;
-    unsigned long long pad1;
+    uint32_t pad;
 };
-static_assert(sizeof(ObjCell) == 32, "one object cell is one 32-byte sector");
+static_assert(sizeof(ObjCell) == 16, "one object cell is one 128-bit word");
 struct MeshView {
     const ObjCell* cells[kMeshMaxRanks];   // rank g's cells (peer-mapped), object j lives at cells[j >> shift][j & mask]
     uint32_t shift, mask;

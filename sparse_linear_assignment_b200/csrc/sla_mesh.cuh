@@ -1,25 +1,27 @@
 // sla_mesh.cuh -- one KhoslaSolver instance over G GPUs of one NVLink / NVSwitch domain (BASELINE.json config 5).
 //
 // Persons (CSR rows) are partitioned by row over the ranks, objects by contiguous ranges of S = 2^shift ids over the
-// SAME ranks: rank g owns the state {packed bid word, price, owner} of objects [g S, (g+1) S) in its own HBM.  Every
-// rank maps every other rank's "mesh block" (peer mapping: cudaIpc* between processes, plain pointers inside one
-// process), and all exchange happens INSIDE the round kernels, as loads and stores on those peer pointers:
+// SAME ranks: rank g owns {price, owner} (one 16-byte cell) and the packed bid word of objects [g S, (g+1) S) in its own
+// HBM.  Every rank maps every other rank's "mesh block" (peer mapping: cudaIpc* between processes, plain pointers inside
+// one process), and all exchange happens INSIDE the round kernels, as loads and stores on those peer pointers:
 //
 //   K1 bid      every queued local person scans its CSR row (the single-GPU choice rule, ksparse.rs:199-227); prices of
 //               objects another rank owns are gathered straight out of that rank's HBM; the bid {object, person, exact
 //               f64 bid} is staged in shared memory, sorted by owner, and PUSHED with coalesced stores into the owner's
 //               inbox over NVLink.  Last block: entry counts to the owners, flag barrier B1.
-//   K2 max      owner side, local: packed 64-bit word of every received bid -> atomicMax on the object's cell.
+//   K2 max      owner side, local: packed 64-bit word of every received bid -> atomicMax on the object's word.  Also the
+//               termination test: the sum of the ranks' queue lengths of this round == 0 ends the solve everywhere.
 //   K3 resolve  owner side: the entry whose word survived wins -- price := its exact bid, owner := its person, the
 //               previous owner is pushed into the evict inbox of the rank that holds that person; one reply bit per entry
 //               is stored back into the bidder's rank (32 entries = one word).  Last block: counts, barrier B2.
 //   K4 finish   bidder side: winners record their object, losers and the evicted persons received from the owners form
-//               the next queue.  Last block: round accounting, this rank's next queue length to every rank, barrier B3.
+//               the next queue.  Last block: round accounting, this rank's next queue length to every rank (it travels
+//               under the next B1).
 //
-// The next K1 adds up the G queue lengths: zero ends the solve on every rank in the same round.  A barrier is one
-// 32-bit epoch per (receiver, sender) pair: the last block of a kernel fences (system scope) and stores the epoch
-// into every peer's flag word; the first thing the next kernel does is wait for all G flags of its own rank.  Rounds
-// are captured into CUDA graphs; the host only polls `done` -- no collective, no host synchronisation per round.
+// A barrier is one 32-bit epoch per (receiver, sender) pair: every block fences its stores at system scope before it
+// takes its ticket; the last block of the producing kernel stores the epoch into every rank's flag word and then WAITS
+// for the other ranks' epochs itself, so the kernel boundary behind it is the barrier and nobody else polls.  Rounds are
+// captured into CUDA graphs; the host only polls `done` -- no collective, no host synchronisation per round.
 //
 // A Jacobi round does not depend on the order of its bids, winners are elected by the same packed words, and prices
 // are the winners' exact f64 bids: the result equals the one-GPU solve (and oracle/jacobi_model.c) bit for bit.
@@ -54,6 +56,7 @@ struct MeshParams {
     uint32_t* reply_out[kMeshMaxRanks];          // reply_out[a]: the region of rank a's reply words written by this rank
     uint32_t* evict_out[kMeshMaxRanks];          // evict_out[b]: the region of rank b's evict inbox reserved for this rank
     ObjCell* my_cells;
+    unsigned long long* my_best;                 // [2^shift] packed bid word of the current round per owned object (0 = none)
     BidEntry* my_bid_in;                         // [world][cap_bid]   entries received, by sender
     uint32_t* my_reply_in;                       // [world][cap_words] reply words received, by owner
     uint32_t* my_evict_in;                       // [world][cap_evict] evicted persons received, by owner
@@ -66,7 +69,15 @@ struct MeshParams {
     uint32_t my_objects;                         // objects this rank owns
     uint32_t row_begin[kMeshMaxRanks + 1];       // global person id of every rank's first row (+ total)
     unsigned long long timeout_ns;               // a barrier that waits longer gives up (DevState::mesh_error)
+    // Where a barrier is waited for.  0 (concurrent ranks, one per GPU): in the tail of the PRODUCING kernel -- its last
+    // block signals and then waits for the peers' signals, so the kernel boundary behind it is the barrier and nobody
+    // else polls (a thousand blocks polling one L2 line delay the very store they wait for).  1 (lockstep: ranks
+    // stepped one kernel at a time, possibly on one GPU): at the start of the CONSUMING kernel, where the flags are
+    // already there -- a producer that waited in its tail would wait for kernels that have not been launched yet.
+    uint32_t wait_at_start;
+    unsigned long long* timeline;                // [kMeshTimelineRounds][8] globaltimer stamps (development aid), or nullptr
 };
+constexpr uint32_t kMeshTimelineRounds = 64;
 
 // ---- barrier ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
@@ -90,15 +101,16 @@ __device__ __forceinline__ bool mesh_wait(const MeshParams& mp, DevState* st, co
     if (threadIdx.x == 0) s_fail = 0u;
     __syncthreads();
     if (threadIdx.x < mp.world) {
-        const uint32_t* f = &mp.box[mp.rank]->flags[threadIdx.x];
+        const volatile uint32_t* f = &mp.box[mp.rank]->flags[threadIdx.x];
         const unsigned long long t0 = global_timer_ns();
         uint32_t spins = 0;
-        while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) {
+        while ((int)(*f - epoch) < 0) {
             if ((++spins & 1023u) == 0u) {
                 if (global_timer_ns() - t0 > mp.timeout_ns || ((volatile DevState*)st)->mesh_error) { s_fail = 1u; break; }
             }
             __nanosleep(64);
         }
+        __threadfence_system();      // acquire: what the signalling ranks stored before their flags is visible from here on
     }
     __syncthreads();
     if (s_fail) {
@@ -114,21 +126,51 @@ __device__ __forceinline__ void mesh_signal(const MeshParams& mp, const uint32_t
     for (uint32_t g = 0; g < mp.world; ++g) st_release_sys_u32(&mp.box[g]->flags[mp.rank], epoch);
 }
 
+// Last block of a producing kernel (all its threads): signal `epoch` to every rank and -- unless the consumers wait for
+// themselves (wait_at_start) -- wait until every rank has signalled it to this one.  Thread g talks to rank g.
+__device__ __forceinline__ void mesh_barrier_tail(const MeshParams& mp, DevState* st, const uint32_t epoch) {
+    __threadfence_system();
+    if (threadIdx.x < mp.world) {
+        *reinterpret_cast<volatile uint32_t*>(&mp.box[threadIdx.x]->flags[mp.rank]) = epoch;
+        if (!mp.wait_at_start) {
+            const volatile uint32_t* f = &mp.box[mp.rank]->flags[threadIdx.x];
+            const unsigned long long t0 = global_timer_ns();
+            uint32_t spins = 0;
+            while ((int)(*f - epoch) < 0) {
+                if ((++spins & 255u) == 0u && global_timer_ns() - t0 > mp.timeout_ns) {
+                    ((volatile DevState*)st)->mesh_error = 1u;
+                    ((volatile DevState*)st)->done = 1u;
+                    break;
+                }
+            }
+            __threadfence_system();  // acquire
+        }
+    }
+}
+
+__device__ __forceinline__ void mesh_stamp(const MeshParams& mp, DevState* st, const uint32_t slot) {
+    if (mp.timeline) {
+        const uint32_t r = ((volatile DevState*)st)->mesh_round;
+        if (r < kMeshTimelineRounds) mp.timeline[r * 8u + slot] = global_timer_ns();
+    }
+}
+
 // Last-block detection (classic threadfence reduction): true in exactly one thread of the grid, after every block's
 // stores are visible to it.
 __device__ __forceinline__ bool mesh_last_block(uint32_t* ticket) {
+    __shared__ uint32_t s_is_last;
     __syncthreads();
-    bool last = false;
     if (threadIdx.x == 0) {
         __threadfence_system();
         const uint32_t t = atomicAdd(ticket, 1u);
-        if (t == gridDim.x - 1u) {
+        s_is_last = (t == gridDim.x - 1u) ? 1u : 0u;
+        if (s_is_last) {
             __threadfence();
             *ticket = 0u;
-            last = true;
         }
     }
-    return last;
+    __syncthreads();
+    return s_is_last != 0u;      // block-uniform: every thread of the last block gets true
 }
 
 __device__ __forceinline__ uint32_t mesh_person_rank(const MeshParams& mp, const uint32_t person) {
@@ -216,24 +258,11 @@ __device__ __forceinline__ void mesh_stage_flush(MeshStage& s, const MeshParams&
     __syncthreads();
 }
 
-// Start of K1: barrier B3 of the previous round, termination test.  Returns false when this kernel has nothing to do.
+// Start of K1.  Nothing to wait for: the queue is this rank's own (K4 of the previous round), and the prices it gathers
+// were written by the owners before the barrier B2 this rank has already passed.
 __device__ __forceinline__ bool mesh_round_begin(const Params& p, const MeshParams& mp, const HotState& h) {
-    DevState* st = p.st;
     if (h.done) return false;
-    const uint32_t round = ((volatile DevState*)st)->mesh_round, epoch = ((volatile DevState*)st)->mesh_epoch;
-    if (round > 1u) {
-        if (!mesh_wait(mp, st, epoch)) return false;
-        unsigned long long total = 0;
-        for (uint32_t g = 0; g < mp.world; ++g)
-            total += *reinterpret_cast<const volatile unsigned long long*>(&mp.box[mp.rank]->next_total[g]);
-        if (total == 0ull) {
-            // every rank sees the same G numbers: the solve ends here on all of them.  Marking `done` is left to ONE
-            // thread of the grid, and only after every block has read the state (ticket), so that no block of this very
-            // launch can take the `h.done` exit above while others wait in the barrier.
-            if (mesh_last_block(&mp.tickets[0])) ((volatile DevState*)st)->done = 1u;
-            return false;
-        }
-    }
+    if (((volatile DevState*)p.st)->mesh_error) return false;
     return true;
 }
 
@@ -246,12 +275,15 @@ __device__ __forceinline__ void mesh_bid_end(const Params& p, const MeshParams& 
     }
     if (mesh_last_block(&mp.tickets[0])) {
         const uint32_t epoch = ((volatile DevState*)st)->mesh_epoch;
-        for (uint32_t g = 0; g < mp.world; ++g) {
+        if (threadIdx.x < mp.world) {
+            const uint32_t g = threadIdx.x;
             const uint32_t c = *reinterpret_cast<volatile uint32_t*>(&mp.out_cnt[g]);
             *reinterpret_cast<volatile uint32_t*>(&mp.box[g]->bid_count[mp.rank]) = c;
             *reinterpret_cast<volatile uint32_t*>(&mp.out_cnt[g]) = 0u;
         }
-        mesh_signal(mp, epoch + 1u);
+        if (threadIdx.x == 0) mesh_stamp(mp, st, 1);
+        mesh_barrier_tail(mp, st, epoch + 1u);
+        if (threadIdx.x == 0) mesh_stamp(mp, st, 2);
     }
 }
 
@@ -262,6 +294,7 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params 
     __shared__ MeshStage s;
     const HotState h = load_hot(p.st);
     if (!mesh_round_begin(p, mp, h)) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) mesh_stamp(mp, p.st, 0);
     const uint32_t cur = h.cur, qlen = h.qlen[cur & 1u];
     const bool identity = h.identity != 0;
     const uint32_t* __restrict__ queue = cur ? p.queue[1] : p.queue[0];
@@ -382,17 +415,35 @@ __global__ void __launch_bounds__(kWideThreads) mesh_max_kernel(const Params p, 
     DevState* st = p.st;
     const HotState h = load_hot(st);
     if (h.done) return;
-    const uint32_t epoch = ((volatile DevState*)st)->mesh_epoch;
-    if (!mesh_wait(mp, st, epoch + 1u)) return;
+    const uint32_t epoch = ((volatile DevState*)st)->mesh_epoch, round = ((volatile DevState*)st)->mesh_round;
+    if (mp.wait_at_start && !mesh_wait(mp, st, epoch + 1u)) return;
+    if (((volatile DevState*)st)->mesh_error) return;
+    if (round > 1u) {
+        // the ranks' queue lengths of THIS round (published by their K4 of the previous one, ordered by B1): all zero means
+        // nobody bid -- the solve ends here on every rank, in the same round.  `done` is set by one thread, after every block
+        // has read the state (ticket), so that no block of this very launch can take the `h.done` exit while others go on.
+        unsigned long long total = 0;
+        for (uint32_t g = 0; g < mp.world; ++g)
+            total += *reinterpret_cast<const volatile unsigned long long*>(&mp.box[mp.rank]->next_total[g]);
+        if (total == 0ull) {
+            if (mesh_last_block(&mp.tickets[1]) && threadIdx.x == 0) {
+                // this round's B1 has been signalled by every rank: the next solve must start behind it
+                ((volatile DevState*)st)->mesh_epoch = epoch + 2u;
+                ((volatile DevState*)st)->done = 1u;
+            }
+            return;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) mesh_stamp(mp, st, 3);
     const uint32_t pbits = h.pbits;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     for (uint32_t a = 0; a < mp.world; ++a) {
         const uint32_t cnt = ld_cv_u32(&mp.box[mp.rank]->bid_count[a]);
         const BidEntry* in = mp.my_bid_in + (size_t)a * mp.cap_bid;
         for (uint32_t e = tid; e < cnt; e += stride) {
-            const uint4 raw = __ldcv(reinterpret_cast<const uint4*>(in + e));      // stored by another GPU: past the L1
+            const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(in + e));      // stored by another GPU: past the L1
             const double bid = __hiloint2double((int)raw.w, (int)raw.z);
-            atomicMax(&mp.my_cells[raw.x].best, pack_bid(bid, raw.y, pbits));
+            atomicMax(mp.my_best + raw.x, pack_bid(bid, raw.y, pbits));
         }
     }
 }
@@ -407,6 +458,7 @@ __global__ void __launch_bounds__(kWideThreads) mesh_resolve_kernel(const Params
     if (h.done) return;
     if (((volatile DevState*)st)->mesh_error) return;
     const uint32_t pbits = h.pbits;
+    const bool nobody_owns = h.zero_prices != 0;       // round 1 (K4 clears the flag at its end)
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t a = 0; a < mp.world; ++a) {
@@ -418,15 +470,15 @@ __global__ void __launch_bounds__(kWideThreads) mesh_resolve_kernel(const Params
             bool won = false;
             uint32_t prev = SLA_DEV_NONE;
             if (e < cnt) {
-                const uint4 raw = __ldcv(reinterpret_cast<const uint4*>(in + e));
+                const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(in + e));
                 const double bid = __hiloint2double((int)raw.w, (int)raw.z);
-                ObjCell* cell = mp.my_cells + raw.x;
-                won = __ldcg(&cell->best) == pack_bid(bid, raw.y, pbits);
+                won = __ldcg(mp.my_best + raw.x) == pack_bid(bid, raw.y, pbits);
                 if (won) {
-                    prev = __ldcg(&cell->owner);
-                    cell->price = bid;
-                    cell->owner = raw.y;
-                    cell->best = 0ull;          // losers that look later see 0 or this word: neither equals theirs
+                    ObjCell* cell = mp.my_cells + raw.x;
+                    if (!nobody_owns) prev = __ldcg(&cell->owner);     // first round: every object is still free
+                    // one 128-bit store: {price = the winner's exact bid, owner = its person}
+                    *reinterpret_cast<uint4*>(cell) = make_uint4(raw.z, raw.w, raw.y, 0u);
+                    mp.my_best[raw.x] = 0ull;   // losers that look later see 0 or this word: neither equals theirs
                 }
             }
             const uint32_t wonmask = __ballot_sync(0xffffffffu, won);
@@ -449,12 +501,15 @@ __global__ void __launch_bounds__(kWideThreads) mesh_resolve_kernel(const Params
     }
     if (mesh_last_block(&mp.tickets[2])) {
         const uint32_t epoch = ((volatile DevState*)st)->mesh_epoch;
-        for (uint32_t b = 0; b < mp.world; ++b) {
+        if (threadIdx.x < mp.world) {
+            const uint32_t b = threadIdx.x;
             const uint32_t c = *reinterpret_cast<volatile uint32_t*>(&mp.ev_cnt[b]);
             *reinterpret_cast<volatile uint32_t*>(&mp.box[b]->evict_count[mp.rank]) = c;
             *reinterpret_cast<volatile uint32_t*>(&mp.ev_cnt[b]) = 0u;
         }
-        mesh_signal(mp, epoch + 2u);
+        if (threadIdx.x == 0) mesh_stamp(mp, st, 4);
+        mesh_barrier_tail(mp, st, epoch + 2u);
+        if (threadIdx.x == 0) mesh_stamp(mp, st, 5);
     }
 }
 
@@ -466,7 +521,8 @@ __global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params 
     const HotState h = load_hot(st);
     if (h.done) return;
     const uint32_t epoch = ((volatile DevState*)st)->mesh_epoch;
-    if (!mesh_wait(mp, st, epoch + 2u)) return;
+    if (mp.wait_at_start && !mesh_wait(mp, st, epoch + 2u)) return;
+    if (((volatile DevState*)st)->mesh_error) return;
     const uint32_t cur = h.cur, qlen = h.qlen[cur & 1u];
     const bool identity = h.identity != 0;
     const uint32_t* __restrict__ queue = cur ? p.queue[1] : p.queue[0];
@@ -537,6 +593,8 @@ __global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params 
     }
 
     if (mesh_last_block(&mp.tickets[3])) {
+      if (threadIdx.x == 0) {
+        mesh_stamp(mp, st, 6);
         volatile DevState* v = st;
         const uint32_t c = v->cur & 1u, ql = v->qlen[c];
         v->rounds = v->rounds + 1;
@@ -552,9 +610,11 @@ __global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params 
         else v->safety_rounds_left = v->safety_rounds_left - 1;
         for (uint32_t g = 0; g < mp.world; ++g)
             *reinterpret_cast<volatile unsigned long long*>(&mp.box[g]->next_total[mp.rank]) = next;
+        mesh_stamp(mp, st, 7);                   // (stamped under the round that just ended)
         v->mesh_round = v->mesh_round + 1u;
-        v->mesh_epoch = epoch + 3u;
-        mesh_signal(mp, epoch + 3u);
+        v->mesh_epoch = epoch + 2u;              // two barriers per round; the queue length travels under the next B1
+        __threadfence_system();
+      }
     }
 }
 
@@ -565,8 +625,9 @@ __global__ void __launch_bounds__(kWideThreads) mesh_init_kernel(const Params p,
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     for (uint32_t j = tid; j < mp.my_objects; j += stride) {
         ObjCell c;
-        c.best = 0ull; c.price = 0.0; c.owner = SLA_DEV_NONE; c.pad0 = 0u; c.pad1 = 0ull;
+        c.price = 0.0; c.owner = SLA_DEV_NONE; c.pad = 0u;
         mp.my_cells[j] = c;
+        mp.my_best[j] = 0ull;
     }
     for (uint32_t i = tid; i < n_local; i += stride) p.p2o[i] = SLA_DEV_NONE;
     if (tid < mp.world) { mp.out_cnt[tid] = 0u; mp.ev_cnt[tid] = 0u; }
@@ -593,12 +654,13 @@ struct sla_mesh_state {
     uint32_t shift = 0, shard = 0;               // objects per rank = 2^shift
     uint32_t cap_bid = 0, cap_words = 0, cap_evict = 0;
     // layout of every rank's block (identical on all ranks): byte offsets
-    size_t off_box = 0, off_cells = 0, off_bid = 0, off_reply = 0, off_evict = 0, block_bytes = 0;
+    size_t off_box = 0, off_cells = 0, off_best = 0, off_bid = 0, off_reply = 0, off_evict = 0, block_bytes = 0;
     unsigned char* block = nullptr;              // this rank's block (cudaMalloc: one IPC handle covers it)
     unsigned char* peer[sla::kMeshMaxRanks] = {};    // every rank's block as mapped here (own included)
     bool connected = false, active = false;
     uint32_t* d_slot_pos = nullptr;
     uint32_t* d_counters = nullptr;              // out_cnt[8] | ev_cnt[8] | tickets[4]
+    unsigned long long* d_timeline = nullptr;    // SLA_MESH_TIMELINE=1: per-round globaltimer stamps of the kernels
     size_t cap_slot_pos = 0;
     sla::MeshParams mp;
     uint32_t epoch = 0;                          // barrier epoch at the start of the next solve (identical on all ranks)
@@ -623,9 +685,10 @@ uint32_t mesh_lpr8(const sla_ctx* c) {           // lanes per row of the uniform
 }
 
 // which: 0 bid, 1 max, 2 resolve, 3 finish
-void mesh_launch_phase(sla_ctx* c, const Params& p, int which, bool first_round) {
+void mesh_launch_phase(sla_ctx* c, const Params& p, int which, bool first_round, bool lockstep) {
     sla_mesh_state* ms = c->mesh;
-    const sla::MeshParams& mp = ms->mp;
+    sla::MeshParams mp = ms->mp;
+    mp.wait_at_start = lockstep ? 1u : 0u;
     const int grid_bid = c->num_sms * 3;
     switch (which) {
         case 0:
@@ -650,9 +713,11 @@ void mesh_launch_phase(sla_ctx* c, const Params& p, int which, bool first_round)
                 else mesh_bid_ragged_kernel<32><<<grid_bid, kWideThreads, 0, c->stream>>>(p, mp);
             }
             break;
-        case 1: mesh_max_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p, mp); break;
-        case 2: mesh_resolve_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p, mp); break;
-        default: mesh_finish_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p, mp); break;
+        // (four blocks per SM: every block fences at system scope and takes a ticket at its end -- more blocks only
+        //  lengthen the short rounds)
+        case 1: mesh_max_kernel<<<c->num_sms * 4, kWideThreads, 0, c->stream>>>(p, mp); break;
+        case 2: mesh_resolve_kernel<<<c->num_sms * 4, kWideThreads, 0, c->stream>>>(p, mp); break;
+        default: mesh_finish_kernel<<<c->num_sms * 4, kWideThreads, 0, c->stream>>>(p, mp); break;
     }
 }
 
@@ -674,6 +739,7 @@ void sla_mesh_free(sla_ctx* ctx) {
     cudaFree(ms->block);
     cudaFree(ms->d_slot_pos);
     cudaFree(ms->d_counters);
+    cudaFree(ms->d_timeline);
     delete ms;
     ctx->mesh = nullptr;
 }
@@ -713,6 +779,7 @@ int sla_mesh_create(sla_ctx* ctx, int rank, int world, const uint32_t* row_begin
     size_t off = 0;
     ms->off_box = off;     off = align256(off + sizeof(sla::MeshMailbox));
     ms->off_cells = off;   off = align256(off + (size_t)ms->shard * sizeof(sla::ObjCell));
+    ms->off_best = off;    off = align256(off + (size_t)ms->shard * sizeof(unsigned long long));
     ms->off_bid = off;     off = align256(off + (size_t)world * ms->cap_bid * sizeof(sla::BidEntry));
     ms->off_reply = off;   off = align256(off + (size_t)world * ms->cap_words * sizeof(uint32_t));
     ms->off_evict = off;   off = align256(off + (size_t)world * ms->cap_evict * sizeof(uint32_t));
@@ -727,6 +794,12 @@ int sla_mesh_create(sla_ctx* ctx, int rank, int world, const uint32_t* row_begin
     CU(cudaMemsetAsync(ms->d_counters, 0, 32 * sizeof(uint32_t), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (const char* t = getenv("SLA_MESH_TIMEOUT_S")) ms->timeout_s = atof(t);
+    if (const char* t = getenv("SLA_MESH_TIMELINE")) {
+        if (atoi(t) != 0) {
+            if ((rc = dev_alloc(ctx, &ms->d_timeline, (size_t)sla::kMeshTimelineRounds * 8))) return rc;
+            CU(cudaMemset(ms->d_timeline, 0, (size_t)sla::kMeshTimelineRounds * 8 * sizeof(unsigned long long)));
+        }
+    }
     if (block) *block = ms->block;
     if (block_bytes) *block_bytes = ms->block_bytes;
     return SLA_OK;
@@ -799,6 +872,7 @@ int sla_mesh_connect(sla_ctx* ctx, void* const* peer_blocks, const int* peer_dev
         mp.evict_out[g] = reinterpret_cast<uint32_t*>(b + ms->off_evict) + (size_t)ms->rank * ms->cap_evict;
     }
     mp.my_cells = reinterpret_cast<sla::ObjCell*>(ms->block + ms->off_cells);
+    mp.my_best = reinterpret_cast<unsigned long long*>(ms->block + ms->off_best);
     mp.my_bid_in = reinterpret_cast<sla::BidEntry*>(ms->block + ms->off_bid);
     mp.my_reply_in = reinterpret_cast<uint32_t*>(ms->block + ms->off_reply);
     mp.my_evict_in = reinterpret_cast<uint32_t*>(ms->block + ms->off_evict);
@@ -814,6 +888,7 @@ int sla_mesh_connect(sla_ctx* ctx, void* const* peer_blocks, const int* peer_dev
     for (int g = 0; g <= ms->world; ++g) mp.row_begin[g] = ms->row_begin[g];
     for (int g = ms->world + 1; g <= sla::kMeshMaxRanks; ++g) mp.row_begin[g] = ms->row_begin[ms->world];
     mp.timeout_ns = (unsigned long long)(ms->timeout_s * 1e9);
+    mp.timeline = ms->d_timeline;
     ms->connected = true;
     if (ms->exec) { cudaGraphExecDestroy(ms->exec); ms->exec = nullptr; }
     return SLA_OK;
@@ -893,7 +968,7 @@ int sla_mesh_phase(sla_ctx* ctx, int which) {
     const Params p = make_params(ctx);
     // (round 1 is the only round whose state says zero_prices; the host mirrors it from the last poll)
     const bool first_round = ctx->h_state->mesh_round <= 1u && ctx->h_state->zero_prices != 0u;
-    mesh_launch_phase(ctx, p, which, first_round);
+    mesh_launch_phase(ctx, p, which, first_round, true);
     ctx->mesh->launches += 1;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
@@ -942,7 +1017,7 @@ int sla_mesh_solve(sla_ctx* ctx) {
                     // the first round's scan + push is bracketed by two event-record nodes (sla_mesh_round1_ms)
                     const bool bracket = first && r == 0 && k == 0;
                     if (bracket) cudaEventRecordWithFlags(ctx->ev[3], ctx->stream, cudaEventRecordExternal);
-                    mesh_launch_phase(ctx, p, k, first && r == 0);
+                    mesh_launch_phase(ctx, p, k, first && r == 0, false);
                     if (bracket) cudaEventRecordWithFlags(ctx->ev[4], ctx->stream, cudaEventRecordExternal);
                 }
             cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
@@ -1047,6 +1122,20 @@ int sla_mesh_objective(sla_ctx* ctx, double* objective) {
     // reference src/solver.rs:111-137: the sign is taken from the (current, possibly negated) first value of the instance
     const double first_eff = ctx->mesh->flip ? -ctx->mesh->gfirst : ctx->mesh->gfirst;
     *objective = (first_eff >= 0.0) ? sum : -sum;
+    return SLA_OK;
+}
+
+// Development aid (SLA_MESH_TIMELINE=1 at sla_mesh_create): globaltimer stamps of the last solve, 8 per round (round r at
+// out[8 r ..]): 0 bid kernel starts, 1 its last block is done locally, 2 barrier B1 passed, 3 max kernel starts,
+// 4 resolve kernel done locally, 5 barrier B2 passed, 6 finish kernel done locally, 7 round accounted (before B3).
+int sla_mesh_timeline(sla_ctx* ctx, unsigned long long* out, size_t capacity) {
+    if (!ctx || !out) return SLA_ERR_INVALID;
+    int rc = mesh_check(ctx, false, false);
+    if (rc) return rc;
+    if (!ctx->mesh->d_timeline) return fail(ctx, SLA_ERR_STATE, "mesh: no timeline (set SLA_MESH_TIMELINE=1 before sla_mesh_create)");
+    const size_t n = std::min<size_t>(capacity, (size_t)sla::kMeshTimelineRounds * 8);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(out, ctx->mesh->d_timeline, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return SLA_OK;
 }
 
