@@ -33,6 +33,9 @@ def run(n, m, k, opts, reps=9, label=""):
 cfg3 = (1_000_000, 4_000_000, 16)
 cfg5 = (16_000_000, 64_000_000, 16)
 run(*cfg3, {}, label="cfg3 default")
+if len(sys.argv) > 1 and sys.argv[1] == "quick":
+    run(*cfg5, {}, reps=5, label="cfg5 default")
+    sys.exit(0)
 run(*cfg3, {"learn_shape": 0}, label="cfg3 no learned shape")
 run(*cfg3, {"prune_gather": 0}, label="cfg3 no prune")
 run(*cfg3, {"prezero_best": 1}, label="cfg3 prezero")

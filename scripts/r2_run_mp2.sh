@@ -10,3 +10,4 @@ tail -3 gpurun_out/${TAG}_mesh_cfg3shape.err; cat gpurun_out/${TAG}_mesh_cfg3sha
 SLA_MESH_TIMELINE=1 SLA_TAG=${TAG}_cfg5 timeout 300 $TR scripts/run_mesh.py 16000000 64000000 16 check 7 > gpurun_out/${TAG}_mesh_cfg5.json 2> gpurun_out/${TAG}_mesh_cfg5.err
 tail -3 gpurun_out/${TAG}_mesh_cfg5.err; cat gpurun_out/${TAG}_mesh_cfg5.json
 cat gpurun_out/${TAG}_cfg5_timeline_rank0.json
+timeout 120 python scripts/r2_probe.py quick > gpurun_out/${TAG}_probe.json 2>&1; cat gpurun_out/${TAG}_probe.json

@@ -62,9 +62,9 @@ if check and rank == 0:
                                      s1["bid_arcs"] == st["global_bid_arcs"] and s1["rounds"] == st["rounds"])
 if os.environ.get("SLA_MESH_TIMELINE"):
     import ctypes as C
-    buf = (C.c_uint64 * (64 * 8))()
-    _lib.check(ctx, _lib.load().sla_mesh_timeline(ctx, buf, 64 * 8))
-    tl = np.array(buf[:], dtype=np.uint64).reshape(64, 8).astype(np.int64)
+    buf = (C.c_uint64 * (64 * 12))()
+    _lib.check(ctx, _lib.load().sla_mesh_timeline(ctx, buf, 64 * 12))
+    tl = np.array(buf[:], dtype=np.uint64).reshape(64, 12).astype(np.int64)
     rows_ = []
     for r in range(1, min(int(st["rounds"]) + 1, 64)):
         t = tl[r]
@@ -73,9 +73,9 @@ if os.environ.get("SLA_MESH_TIMELINE"):
         # us: bid work, B1 wait, max+resolve work (from max start), B2 wait, finish work, whole round (to the next bid start)
         nxt = tl[r + 1][0] if r + 1 < 64 and tl[r + 1][0] else t[7]
         rows_.append([r, round((t[1] - t[0]) / 1e3, 1), round((t[2] - t[1]) / 1e3, 1), round((t[3] - t[2]) / 1e3, 1),
-                      round((t[4] - t[3]) / 1e3, 1), round((t[5] - t[4]) / 1e3, 1), round((t[6] - t[5]) / 1e3, 1),
-                      round((t[7] - t[6]) / 1e3, 1), round((nxt - t[0]) / 1e3, 1)])
-    out_tl = {"rank": rank, "columns": ["round", "bid", "B1", "gap->max", "max+resolve", "B2", "finish", "control", "round_total"],
+                      round((t[8] - t[3]) / 1e3, 1), round((t[4] - t[8]) / 1e3, 1), round((t[5] - t[4]) / 1e3, 1),
+                      round((t[6] - t[5]) / 1e3, 1), round((t[7] - t[6]) / 1e3, 1), round((nxt - t[0]) / 1e3, 1)])
+    out_tl = {"rank": rank, "columns": ["round", "bid", "B1", "gap->max", "max(+gap)", "resolve", "B2", "finish", "control", "round_total"],
               "us": rows_}
     with open(f"gpurun_out/{os.environ.get('SLA_TAG', 'mesh')}_timeline_rank{rank}.json", "w") as f:
         json.dump(out_tl, f)

@@ -704,12 +704,16 @@ __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params 
     // published its emissions (fence) before it takes its ticket, so the last one sees the complete next queue length.
     // The control block is fetched past the L1 with independent 128-bit loads (other blocks changed it with atomics in
     // the L2), worked on in shared memory and stored back -- one L2 round trip instead of a chain of dependent ones.
+    // Only blocks that had a chunk take a ticket (a block without one has written nothing): same-address atomics cost
+    // ~8 ns apiece, which is 5 us for a full grid and nothing for the three working blocks of a short round.
     __shared__ uint32_t s_last;
     __shared__ DevState s_state;
+    const uint32_t working = min((qlen + per - 1u) / per, gridDim.x);
+    if (blockIdx.x >= working) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        s_last = (atomicAdd(&st->assign_ticket, 1u) == gridDim.x - 1u) ? 1u : 0u;
+        s_last = (atomicAdd(&st->assign_ticket, 1u) == working - 1u) ? 1u : 0u;
     }
     __syncthreads();
     if (s_last) {

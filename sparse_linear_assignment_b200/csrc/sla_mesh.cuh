@@ -29,7 +29,7 @@
 
 namespace sla {
 
-constexpr uint32_t kMeshChunkRows = 512;     // bidders one block stages in shared memory before it pushes them
+constexpr uint32_t kMeshChunkRows = 1024;    // bidders one block stages in shared memory before it pushes them
 constexpr uint32_t kMeshPruneMinQueue = 4096; // local bidders from which the gathering scan prunes by value bound
 
 struct alignas(16) BidEntry {
@@ -75,9 +75,9 @@ struct MeshParams {
     // stepped one kernel at a time, possibly on one GPU): at the start of the CONSUMING kernel, where the flags are
     // already there -- a producer that waited in its tail would wait for kernels that have not been launched yet.
     uint32_t wait_at_start;
-    unsigned long long* timeline;                // [kMeshTimelineRounds][8] globaltimer stamps (development aid), or nullptr
+    unsigned long long* timeline;                // [kMeshTimelineRounds][kMeshTimelineSlots] globaltimer stamps (development aid), or nullptr
 };
-constexpr uint32_t kMeshTimelineRounds = 64;
+constexpr uint32_t kMeshTimelineRounds = 64, kMeshTimelineSlots = 12;
 
 // ---- barrier ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
@@ -151,19 +151,22 @@ __device__ __forceinline__ void mesh_barrier_tail(const MeshParams& mp, DevState
 __device__ __forceinline__ void mesh_stamp(const MeshParams& mp, DevState* st, const uint32_t slot) {
     if (mp.timeline) {
         const uint32_t r = ((volatile DevState*)st)->mesh_round;
-        if (r < kMeshTimelineRounds) mp.timeline[r * 8u + slot] = global_timer_ns();
+        if (r < kMeshTimelineRounds) mp.timeline[r * kMeshTimelineSlots + slot] = global_timer_ns();
     }
 }
 
 // Last-block detection (classic threadfence reduction): true in exactly one thread of the grid, after every block's
 // stores are visible to it.
-__device__ __forceinline__ bool mesh_last_block(uint32_t* ticket) {
+// `remote`: this block has stored into another rank's memory since its last fence (block-uniform or not: any thread's
+// word counts).  Only such blocks pay for a system-scope fence (it waits for the acknowledgements from across NVLink);
+// the others order their local stores at GPU scope.
+__device__ __forceinline__ bool mesh_last_block(uint32_t* ticket, const bool remote, const uint32_t participants) {
     __shared__ uint32_t s_is_last;
-    __syncthreads();
+    const int any_remote = __syncthreads_or(remote ? 1 : 0);
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        if (any_remote) __threadfence_system(); else __threadfence();
         const uint32_t t = atomicAdd(ticket, 1u);
-        s_is_last = (t == gridDim.x - 1u) ? 1u : 0u;
+        s_is_last = (t == participants - 1u) ? 1u : 0u;
         if (s_is_last) {
             __threadfence();
             *ticket = 0u;
@@ -187,11 +190,9 @@ __device__ __forceinline__ uint32_t ld_cv_u32(const uint32_t* p) { return *reint
 // =============================================================================================================
 struct MeshStage {
     BidEntry ent[kMeshChunkRows];        // arrival order
-    BidEntry sorted[kMeshChunkRows];     // grouped by owner rank
-    uint32_t slot[kMeshChunkRows];       // queue slot of the entry (arrival order)
-    uint32_t where[kMeshChunkRows];      // owner << 24 | rank within the owner's group (arrival order)
-    uint32_t slot_sorted[kMeshChunkRows];
-    uint32_t cnt[kMeshMaxRanks], off[kMeshMaxRanks + 1], base[kMeshMaxRanks];
+    uint32_t slot[kMeshChunkRows];       // queue slot of the entry
+    uint32_t where[kMeshChunkRows];      // owner << 24 | rank within the owner's entries of this chunk (arrival order)
+    uint32_t cnt[kMeshMaxRanks], base[kMeshMaxRanks];
     uint32_t n, dropped;
     unsigned long long arcs;
 };
@@ -227,35 +228,31 @@ __device__ __forceinline__ void mesh_stage_bid(MeshStage& s, const Params& p, co
     s.where[e] = (g << 24) | rk;
 }
 
-// After a chunk: reserve room in every owner's inbox region (one local atomic per owner), group the staged entries
-// by owner in shared memory, and store them out -- consecutive threads write consecutive 16-byte entries of one owner's
-// region, so the stores that cross NVLink are full 128-byte lines.
+// After a chunk: reserve room in every owner's inbox region -- ONE global atomic per owner and chunk: atomics on one
+// address serialise at ~8 ns apiece -- and store the staged entries out in arrival order.  Entries of one owner that
+// arrived one after the other got consecutive ranks, so the lanes of a warp that write to the same owner write one
+// contiguous run of 16-byte entries: the stores that cross NVLink are whole 128-byte lines without a sort.
 __device__ __forceinline__ void mesh_stage_flush(MeshStage& s, const MeshParams& mp) {
     __syncthreads();
     const uint32_t n = s.n;
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (uint32_t g = 0; g < mp.world; ++g) { s.off[g] = acc; acc += s.cnt[g]; }
-        s.off[mp.world] = acc;
-    }
     if (threadIdx.x < mp.world) s.base[threadIdx.x] = s.cnt[threadIdx.x] ? atomicAdd(&mp.out_cnt[threadIdx.x], s.cnt[threadIdx.x]) : 0u;
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
-        const uint32_t w = s.where[e], g = w >> 24, rk = w & 0xFFFFFFu;
-        s.sorted[s.off[g] + rk] = s.ent[e];
-        s.slot_sorted[s.off[g] + rk] = s.slot[e];
-    }
-    __syncthreads();
-    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
-        uint32_t g = 0;
-        while (t >= s.off[g + 1u]) ++g;
-        const uint32_t pos = s.base[g] + (t - s.off[g]);
-        mp.bid_out[g][pos] = s.sorted[t];
-        mp.slot_pos[s.slot_sorted[t]] = pos;
+        const uint32_t w = s.where[e], g = w >> 24;
+        const uint32_t pos = s.base[g] + (w & 0xFFFFFFu);
+        mp.bid_out[g][pos] = s.ent[e];
+        mp.slot_pos[s.slot[e]] = pos;
     }
     __syncthreads();
     mesh_stage_reset(s);
     __syncthreads();
+}
+
+// Blocks of a grid that take part in the last-block ticket of a kernel: those that had work (at least one; block 0
+// stands in when nobody had).  The others have stored nothing and leave at once.
+__device__ __forceinline__ uint32_t mesh_working_blocks(const uint32_t work_units) {
+    const uint32_t w = work_units < gridDim.x ? work_units : gridDim.x;
+    return w ? w : 1u;
 }
 
 // Start of K1.  Nothing to wait for: the queue is this rank's own (K4 of the previous round), and the prices it gathers
@@ -267,13 +264,24 @@ __device__ __forceinline__ bool mesh_round_begin(const Params& p, const MeshPara
 }
 
 // End of K1 (last block): counts to the owners, barrier B1.
-__device__ __forceinline__ void mesh_bid_end(const Params& p, const MeshParams& mp, MeshStage& s) {
+// Rows a block stages per pass over its share of the queue: the whole staging area for the long rounds (one global atomic
+// per owner and 1,024 bids), less for the short ones so that the queue still spreads over the whole grid.
+__device__ __forceinline__ uint32_t mesh_chunk_rows(const uint32_t qlen) {
+    uint32_t c = (qlen + gridDim.x - 1u) / gridDim.x;
+    c = (c + 255u) & ~255u;
+    return c < 256u ? 256u : (c > kMeshChunkRows ? kMeshChunkRows : c);
+}
+
+__device__ __forceinline__ void mesh_bid_end(const Params& p, const MeshParams& mp, MeshStage& s, const uint32_t qlen) {
     DevState* st = p.st;
+    const uint32_t chunk_rows = mesh_chunk_rows(qlen);
+    const uint32_t working = mesh_working_blocks((qlen + chunk_rows - 1u) / chunk_rows);
+    if (blockIdx.x >= working) return;
     if (threadIdx.x == 0) {
         if (s.dropped) atomicAdd(&st->dropped, s.dropped);
         if (s.arcs) atomicAdd(&st->bid_arcs, s.arcs);
     }
-    if (mesh_last_block(&mp.tickets[0])) {
+    if (mesh_last_block(&mp.tickets[0], qlen != 0u, working)) {
         const uint32_t epoch = ((volatile DevState*)st)->mesh_epoch;
         if (threadIdx.x < mp.world) {
             const uint32_t g = threadIdx.x;
@@ -314,8 +322,9 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params 
     mesh_stage_reset(s);
     if (threadIdx.x == 0) { s.dropped = 0u; s.arcs = 0ull; }
     __syncthreads();
-    for (uint32_t chunk = blockIdx.x * kMeshChunkRows; chunk < qlen; chunk += gridDim.x * kMeshChunkRows) {
-        const uint32_t chunk_end = (chunk + kMeshChunkRows < qlen) ? chunk + kMeshChunkRows : qlen;
+    const uint32_t chunk_rows = mesh_chunk_rows(qlen);
+    for (uint32_t chunk = blockIdx.x * chunk_rows; chunk < qlen; chunk += gridDim.x * chunk_rows) {
+        const uint32_t chunk_end = (chunk + chunk_rows < qlen) ? chunk + chunk_rows : qlen;
         for (uint32_t r0 = chunk; r0 < chunk_end; r0 += GPB * U) {
             uint32_t q[U], i[U];
             bool valid[U];
@@ -357,7 +366,7 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params 
         }
         mesh_stage_flush(s, mp);
     }
-    mesh_bid_end(p, mp, s);
+    mesh_bid_end(p, mp, s, qlen);
 }
 
 // Ragged CSR: aligned 4-arc chunks, masked ends, extents from row_ptr (the layout of bid_wide_kernel).
@@ -380,8 +389,9 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_ragged_kernel(const 
     mesh_stage_reset(s);
     if (threadIdx.x == 0) { s.dropped = 0u; s.arcs = 0ull; }
     __syncthreads();
-    for (uint32_t chunk = blockIdx.x * kMeshChunkRows; chunk < qlen; chunk += gridDim.x * kMeshChunkRows) {
-        const uint32_t chunk_end = (chunk + kMeshChunkRows < qlen) ? chunk + kMeshChunkRows : qlen;
+    const uint32_t chunk_rows = mesh_chunk_rows(qlen);
+    for (uint32_t chunk = blockIdx.x * chunk_rows; chunk < qlen; chunk += gridDim.x * chunk_rows) {
+        const uint32_t chunk_end = (chunk + chunk_rows < qlen) ? chunk + chunk_rows : qlen;
         for (uint32_t r0 = chunk; r0 < chunk_end; r0 += GPB) {
             const uint32_t q = r0 + group;
             const bool valid = q < chunk_end;
@@ -405,7 +415,7 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_ragged_kernel(const 
         }
         mesh_stage_flush(s, mp);
     }
-    mesh_bid_end(p, mp, s);
+    mesh_bid_end(p, mp, s, qlen);
 }
 
 // =============================================================================================================
@@ -426,7 +436,7 @@ __global__ void __launch_bounds__(kWideThreads) mesh_max_kernel(const Params p, 
         for (uint32_t g = 0; g < mp.world; ++g)
             total += *reinterpret_cast<const volatile unsigned long long*>(&mp.box[mp.rank]->next_total[g]);
         if (total == 0ull) {
-            if (mesh_last_block(&mp.tickets[1]) && threadIdx.x == 0) {
+            if (mesh_last_block(&mp.tickets[1], false, gridDim.x) && threadIdx.x == 0) {
                 // this round's B1 has been signalled by every rank: the next solve must start behind it
                 ((volatile DevState*)st)->mesh_epoch = epoch + 2u;
                 ((volatile DevState*)st)->done = 1u;
@@ -452,6 +462,8 @@ __global__ void __launch_bounds__(kWideThreads) mesh_max_kernel(const Params p, 
 // K3: owner side, pass 2 -- winners install price and owner, reply bits go back to the bidders' ranks, evicted
 // persons go to the ranks that hold them.
 // =============================================================================================================
+constexpr uint32_t kResolveChunk = 1024;     // entries one block resolves before it reserves room for their evictions
+
 __global__ void __launch_bounds__(kWideThreads) mesh_resolve_kernel(const Params p, const __grid_constant__ MeshParams mp) {
     DevState* st = p.st;
     const HotState h = load_hot(st);
@@ -459,47 +471,106 @@ __global__ void __launch_bounds__(kWideThreads) mesh_resolve_kernel(const Params
     if (((volatile DevState*)st)->mesh_error) return;
     const uint32_t pbits = h.pbits;
     const bool nobody_owns = h.zero_prices != 0;       // round 1 (K4 clears the flag at its end)
+    if (blockIdx.x == 0 && threadIdx.x == 0) mesh_stamp(mp, st, 8);
     const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t a = 0; a < mp.world; ++a) {
-        const uint32_t cnt = ld_cv_u32(&mp.box[mp.rank]->bid_count[a]);
-        const uint32_t nwords = (cnt + 31u) >> 5;
-        const BidEntry* in = mp.my_bid_in + (size_t)a * mp.cap_bid;
-        for (uint32_t w = warp; w < nwords; w += nwarps) {
-            const uint32_t e = w * 32u + (uint32_t)lane;
-            bool won = false;
-            uint32_t prev = SLA_DEV_NONE;
-            if (e < cnt) {
-                const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(in + e));
-                const double bid = __hiloint2double((int)raw.w, (int)raw.z);
-                won = __ldcg(mp.my_best + raw.x) == pack_bid(bid, raw.y, pbits);
-                if (won) {
-                    ObjCell* cell = mp.my_cells + raw.x;
-                    if (!nobody_owns) prev = __ldcg(&cell->owner);     // first round: every object is still free
-                    // one 128-bit store: {price = the winner's exact bid, owner = its person}
-                    *reinterpret_cast<uint4*>(cell) = make_uint4(raw.z, raw.w, raw.y, 0u);
-                    mp.my_best[raw.x] = 0ull;   // losers that look later see 0 or this word: neither equals theirs
-                }
+    const uint32_t warp = threadIdx.x >> 5;
+    constexpr uint32_t kWarps = kWideThreads / 32;
+
+    // evicted owners of a chunk, staged: ONE global atomic per destination rank and chunk reserves their room
+    __shared__ uint32_t s_evp[kResolveChunk], s_evw[kResolveChunk];
+    __shared__ uint32_t s_cnt[kMeshMaxRanks], s_base[kMeshMaxRanks], s_n;
+
+    // chunks of kResolveChunk entries, sender by sender
+    uint32_t cnt[kMeshMaxRanks], nch[kMeshMaxRanks], total_chunks = 0;
+#pragma unroll
+    for (int a = 0; a < kMeshMaxRanks; ++a) {
+        cnt[a] = ((uint32_t)a < mp.world) ? ld_cv_u32(&mp.box[mp.rank]->bid_count[a]) : 0u;
+        nch[a] = (cnt[a] + kResolveChunk - 1u) / kResolveChunk;
+        total_chunks += nch[a];
+    }
+    const uint32_t working = mesh_working_blocks(total_chunks);
+    if (blockIdx.x >= working) return;
+
+    for (uint32_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+        uint32_t a = 0, lc = c, na = cnt[0];
+#pragma unroll
+        for (int g = 0; g < kMeshMaxRanks - 1; ++g) {
+            const bool past = (a == (uint32_t)g) && (lc >= nch[g]);
+            lc -= past ? nch[g] : 0u;
+            a += past ? 1u : 0u;
+            na = past ? cnt[g + 1] : na;
+        }
+        const uint32_t e0 = lc * kResolveChunk, e1 = (e0 + kResolveChunk < na) ? e0 + kResolveChunk : na;
+        const BidEntry* inb = mp.my_bid_in + (size_t)a * mp.cap_bid;
+        if (threadIdx.x < kMeshMaxRanks) s_cnt[threadIdx.x] = 0u;
+        if (threadIdx.x == 0) s_n = 0u;
+        __syncthreads();
+        // four entries per thread and pass, the loads of each stage issued together: the cell array of a large instance
+        // (hundreds of MB) is far beyond the TLB's reach, a dependent random load costs microseconds, and only
+        // memory-level parallelism hides it
+        constexpr int UE = 4;
+        for (uint32_t w0 = 0; w0 * 32u < e1 - e0; w0 += kWarps * UE) {
+            uint4 raw[UE];
+            unsigned long long word[UE];
+            uint32_t prev[UE];
+            bool in[UE], won[UE];
+#pragma unroll
+            for (int u = 0; u < UE; ++u) {
+                const uint32_t e = e0 + (w0 + (uint32_t)u * kWarps + warp) * 32u + (uint32_t)lane;
+                in[u] = e < e1;
+                raw[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (in[u]) raw[u] = __ldcg(reinterpret_cast<const uint4*>(inb + e));     // stored by another GPU: past the L1
             }
-            const uint32_t wonmask = __ballot_sync(0xffffffffu, won);
-            if (lane == 0) mp.reply_out[a][w] = wonmask;                 // one word per 32 entries, back to the bidder's rank
-            // evicted owners: to the rank that holds the person, one local atomic per destination and warp
-            const bool ev = prev != SLA_DEV_NONE;
-            const uint32_t dest = ev ? mesh_person_rank(mp, prev) : 0xFFu;
-            const uint32_t evmask = __ballot_sync(0xffffffffu, ev);
-            if (evmask) {
-                const uint32_t peers = __match_any_sync(0xffffffffu, dest);
-                if (ev) {
-                    const int leader = __ffs((int)peers) - 1;
-                    uint32_t basepos = 0;
-                    if (lane == leader) basepos = atomicAdd(&mp.ev_cnt[dest], (uint32_t)__popc(peers));
-                    basepos = __shfl_sync(peers, basepos, leader);
-                    mp.evict_out[dest][basepos + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = prev;
+#pragma unroll
+            for (int u = 0; u < UE; ++u) {
+                word[u] = 0ull;
+                if (in[u]) word[u] = __ldcg(mp.my_best + raw[u].x);
+            }
+#pragma unroll
+            for (int u = 0; u < UE; ++u) {
+                const double bid = __hiloint2double((int)raw[u].w, (int)raw[u].z);
+                won[u] = in[u] && word[u] == pack_bid(bid, raw[u].y, pbits);
+                prev[u] = SLA_DEV_NONE;
+                if (won[u] && !nobody_owns) prev[u] = __ldcg(&(mp.my_cells + raw[u].x)->owner);   // first round: every object is free
+            }
+#pragma unroll
+            for (int u = 0; u < UE; ++u) {
+                const uint32_t w = w0 + (uint32_t)u * kWarps + warp;
+                if (won[u]) {
+                    // one 128-bit store: {price = the winner's exact bid, owner = its person}
+                    *reinterpret_cast<uint4*>(mp.my_cells + raw[u].x) = make_uint4(raw[u].z, raw[u].w, raw[u].y, 0u);
+                    mp.my_best[raw[u].x] = 0ull;   // losers that look later see 0 or this word: neither equals theirs
+                }
+                const uint32_t wonmask = __ballot_sync(0xffffffffu, won[u]);
+                if (lane == 0 && w * 32u < e1 - e0) mp.reply_out[a][(e0 >> 5) + w] = wonmask;   // one word per 32 entries, back to the bidder's rank
+                const bool ev = prev[u] != SLA_DEV_NONE;
+                const uint32_t evmask = __ballot_sync(0xffffffffu, ev);
+                if (evmask) {
+                    uint32_t slot0 = 0;
+                    if (lane == 0) slot0 = atomicAdd(&s_n, (uint32_t)__popc(evmask));
+                    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                    if (ev) {
+                        const uint32_t dest = mesh_person_rank(mp, prev[u]);
+                        const uint32_t rk = atomicAdd(&s_cnt[dest], 1u);
+                        const uint32_t i = slot0 + (uint32_t)__popc(evmask & ((1u << lane) - 1u));
+                        s_evp[i] = prev[u];
+                        s_evw[i] = (dest << 24) | rk;
+                    }
                 }
             }
         }
+        __syncthreads();
+        if (threadIdx.x < mp.world) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&mp.ev_cnt[threadIdx.x], s_cnt[threadIdx.x]) : 0u;
+        __syncthreads();
+        const uint32_t n = s_n;
+        for (uint32_t i = threadIdx.x; i < n; i += kWideThreads) {
+            const uint32_t w = s_evw[i], dest = w >> 24;
+            mp.evict_out[dest][s_base[dest] + (w & 0xFFFFFFu)] = s_evp[i];     // to the rank that holds the person
+        }
+        __syncthreads();
     }
-    if (mesh_last_block(&mp.tickets[2])) {
+
+    if (mesh_last_block(&mp.tickets[2], true, working)) {
         const uint32_t epoch = ((volatile DevState*)st)->mesh_epoch;
         if (threadIdx.x < mp.world) {
             const uint32_t b = threadIdx.x;
@@ -544,6 +615,9 @@ __global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params 
     uint32_t per = (items + gridDim.x - 1) / gridDim.x;
     per = ((per + kWideThreads - 1) / kWideThreads) * kWideThreads;
     if (per > (uint32_t)kAssignChunk) per = kAssignChunk;
+    if (per == 0u) per = kWideThreads;
+    const uint32_t working = mesh_working_blocks((items + per - 1u) / per);
+    if (blockIdx.x >= working) return;
     for (uint32_t start = blockIdx.x * per; start < items; start += gridDim.x * per) {
         const uint32_t stop = (start + per < items) ? start + per : items;
         if (threadIdx.x == 0) s_cnt = 0u;
@@ -592,7 +666,7 @@ __global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params 
         __syncthreads();
     }
 
-    if (mesh_last_block(&mp.tickets[3])) {
+    if (mesh_last_block(&mp.tickets[3], false, working)) {
       if (threadIdx.x == 0) {
         mesh_stamp(mp, st, 6);
         volatile DevState* v = st;
@@ -796,8 +870,8 @@ int sla_mesh_create(sla_ctx* ctx, int rank, int world, const uint32_t* row_begin
     if (const char* t = getenv("SLA_MESH_TIMEOUT_S")) ms->timeout_s = atof(t);
     if (const char* t = getenv("SLA_MESH_TIMELINE")) {
         if (atoi(t) != 0) {
-            if ((rc = dev_alloc(ctx, &ms->d_timeline, (size_t)sla::kMeshTimelineRounds * 8))) return rc;
-            CU(cudaMemset(ms->d_timeline, 0, (size_t)sla::kMeshTimelineRounds * 8 * sizeof(unsigned long long)));
+            if ((rc = dev_alloc(ctx, &ms->d_timeline, (size_t)sla::kMeshTimelineRounds * sla::kMeshTimelineSlots))) return rc;
+            CU(cudaMemset(ms->d_timeline, 0, (size_t)sla::kMeshTimelineRounds * sla::kMeshTimelineSlots * sizeof(unsigned long long)));
         }
     }
     if (block) *block = ms->block;
@@ -1125,15 +1199,16 @@ int sla_mesh_objective(sla_ctx* ctx, double* objective) {
     return SLA_OK;
 }
 
-// Development aid (SLA_MESH_TIMELINE=1 at sla_mesh_create): globaltimer stamps of the last solve, 8 per round (round r at
-// out[8 r ..]): 0 bid kernel starts, 1 its last block is done locally, 2 barrier B1 passed, 3 max kernel starts,
-// 4 resolve kernel done locally, 5 barrier B2 passed, 6 finish kernel done locally, 7 round accounted (before B3).
+// Development aid (SLA_MESH_TIMELINE=1 at sla_mesh_create): globaltimer stamps of the last solve, 12 slots per round
+// (round r at out[12 r ..]): 0 bid kernel starts, 1 its last block is done locally, 2 barrier B1 passed, 3 max kernel
+// starts, 8 resolve kernel starts, 4 resolve kernel done locally, 5 barrier B2 passed, 6 finish kernel done locally,
+// 7 round accounted.
 int sla_mesh_timeline(sla_ctx* ctx, unsigned long long* out, size_t capacity) {
     if (!ctx || !out) return SLA_ERR_INVALID;
     int rc = mesh_check(ctx, false, false);
     if (rc) return rc;
     if (!ctx->mesh->d_timeline) return fail(ctx, SLA_ERR_STATE, "mesh: no timeline (set SLA_MESH_TIMELINE=1 before sla_mesh_create)");
-    const size_t n = std::min<size_t>(capacity, (size_t)sla::kMeshTimelineRounds * 8);
+    const size_t n = std::min<size_t>(capacity, (size_t)sla::kMeshTimelineRounds * sla::kMeshTimelineSlots);
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpy(out, ctx->mesh->d_timeline, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return SLA_OK;
