@@ -300,6 +300,7 @@ struct sla_ctx {
     int opt_prune = 1;         // bound-pruned gather in the uniform-degree scans of rounds with >= 32 Ki bidders
     int opt_learn_shape = 1;   // plain Khosla: the first graph of a solve has as many wide rounds as the previous solve of the
                                // same resident CSR needed, followed by one tail launch (no no-op launches in between)
+    int opt_mesh_tail = 1;     // mesh engine: the persistent one-block tail engine runs the short rounds
     int opt_prezero_best = 0;  // development: zero the bid words in front of every solve (the RED targets then sit in the L2)
     uint32_t learned_wide = 0; // wide rounds of the last plain Khosla solve of the resident CSR (0: unknown)
     // tail-engine plan of the current instance (plan_tail): what is mirrored in shared memory and how many bidders fit
@@ -1623,6 +1624,8 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "learn_shape") {
         ctx->opt_learn_shape = value ? 1 : 0;
         ctx->learned_wide = 0;
+    } else if (k == "mesh_tail") {
+        ctx->opt_mesh_tail = value ? 1 : 0;
     } else if (k == "prezero_best") {
         ctx->opt_prezero_best = value ? 1 : 0;
     } else if (k == "regular") {

@@ -66,7 +66,9 @@ struct DevState {
     uint32_t wide_ctl_done;  // control step A of this super-round already ran (in assign_wide_kernel's last block)
     // mesh engine (sla_mesh.cuh): round number of the current solve (from 1), barrier epoch at the start of the round
     // (keeps counting across solves), 1 = a barrier gave up / 2 = safety limit
-    uint32_t mesh_round, mesh_epoch, mesh_error, mesh_pad;
+    uint32_t mesh_round, mesh_epoch, mesh_error;
+    uint32_t mesh_tail;      // the persistent one-block tail engine takes the rounds from here on (short rounds)
+    uint32_t mesh_switch_round, mesh_pad[3];   // round in which mesh_tail was set (graph length of the next solve)
     unsigned long long rounds, bids, bid_arcs, wide_rounds, tail_rounds;
     unsigned long long safety_rounds_left;
     unsigned long long dbg[24];  // cycle counters of the tail engine when built with -DSLA_TAIL_TIMING
@@ -83,6 +85,16 @@ struct alignas(16) HotState {
 };
 static_assert(sizeof(HotState) == 112, "HotState must mirror the first 112 bytes of DevState");
 static_assert(sizeof(DevState) % 16 == 0, "DevState is copied as 128-bit words");
+
+// The same past the L1 (persistent kernels re-read the block every round).
+__device__ __forceinline__ HotState load_hot_cg(const DevState* st) {
+    HotState h;
+    const uint4* src = reinterpret_cast<const uint4*>(st);
+    uint4* dst = reinterpret_cast<uint4*>(&h);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) dst[i] = __ldcg(src + i);
+    return h;
+}
 
 __device__ __forceinline__ HotState load_hot(const DevState* st) {
     HotState h;
@@ -302,7 +314,8 @@ enum PriceMode : int {
     PRICE_CG = 2,     // L2-coherent loads
     PRICE_CA = 3,     // prices mutated by this very CTA (tail / batch engines): coherent L1-cached loads
     PRICE_SMEM = 4,   // `prices` points at a shared-memory copy kept by a single-CTA engine
-    PRICE_MESH = 5    // `prices` points at a MeshView: the price lives in the owner rank's HBM (peer-mapped over NVLink)
+    PRICE_MESH = 5,   // `prices` points at a MeshView: the price lives in the owner rank's HBM (peer-mapped over NVLink)
+    PRICE_MESH_CG = 6 // the same read past the L1: persistent kernels, where prices change between the rounds of one launch
 };
 
 // Mesh engine (sla_mesh.cuh): object state is owner-partitioned over up to kMeshMaxRanks GPUs.  Price and owner of an
@@ -332,6 +345,10 @@ __device__ __forceinline__ double ld_price(const double* prices, uint32_t j) {
         // local L2 and are served by the owner's
         const MeshView* mv = reinterpret_cast<const MeshView*>(prices);
         return __ldg(&(mv->cells[j >> mv->shift] + (j & mv->mask))->price);
+    }
+    if (MODE == PRICE_MESH_CG) {
+        const MeshView* mv = reinterpret_cast<const MeshView*>(prices);
+        return __ldcg(&(mv->cells[j >> mv->shift] + (j & mv->mask))->price);
     }
     return __ldcg(prices + j);
 }

@@ -75,6 +75,7 @@ struct MeshParams {
     // stepped one kernel at a time, possibly on one GPU): at the start of the CONSUMING kernel, where the flags are
     // already there -- a producer that waited in its tail would wait for kernels that have not been launched yet.
     uint32_t wait_at_start;
+    uint32_t tail_engine;                        // option: hand the short rounds to mesh_tail_kernel
     unsigned long long* timeline;                // [kMeshTimelineRounds][kMeshTimelineSlots] globaltimer stamps (development aid), or nullptr
 };
 constexpr uint32_t kMeshTimelineRounds = 64, kMeshTimelineSlots = 12;
@@ -190,9 +191,11 @@ __device__ __forceinline__ uint32_t ld_cv_u32(const uint32_t* p) { return *reint
 // =============================================================================================================
 struct MeshStage {
     BidEntry ent[kMeshChunkRows];        // arrival order
-    uint32_t slot[kMeshChunkRows];       // queue slot of the entry
+    BidEntry sorted[kMeshChunkRows];     // grouped by owner rank
+    uint32_t slot[kMeshChunkRows];       // queue slot of the entry (arrival order)
     uint32_t where[kMeshChunkRows];      // owner << 24 | rank within the owner's entries of this chunk (arrival order)
-    uint32_t cnt[kMeshMaxRanks], base[kMeshMaxRanks];
+    uint32_t slot_sorted[kMeshChunkRows];
+    uint32_t cnt[kMeshMaxRanks], off[kMeshMaxRanks + 1], base[kMeshMaxRanks];
     uint32_t n, dropped;
     unsigned long long arcs;
 };
@@ -229,19 +232,33 @@ __device__ __forceinline__ void mesh_stage_bid(MeshStage& s, const Params& p, co
 }
 
 // After a chunk: reserve room in every owner's inbox region -- ONE global atomic per owner and chunk: atomics on one
-// address serialise at ~8 ns apiece -- and store the staged entries out in arrival order.  Entries of one owner that
-// arrived one after the other got consecutive ranks, so the lanes of a warp that write to the same owner write one
-// contiguous run of 16-byte entries: the stores that cross NVLink are whole 128-byte lines without a sort.
+// address serialise at ~8 ns apiece -- group the staged entries by owner in shared memory, and store them out:
+// consecutive threads write consecutive 16-byte entries of one owner's region, so what crosses NVLink are whole
+// 128-byte lines whatever the number of ranks (in arrival order a warp's 32 entries would split into 64-byte pieces for
+// eight owners: the first round at 8 GPUs was bound by those packets).
 __device__ __forceinline__ void mesh_stage_flush(MeshStage& s, const MeshParams& mp) {
     __syncthreads();
     const uint32_t n = s.n;
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (uint32_t g = 0; g < mp.world; ++g) { s.off[g] = acc; acc += s.cnt[g]; }
+        for (uint32_t g = mp.world; g <= kMeshMaxRanks; ++g) s.off[g] = acc;
+    }
     if (threadIdx.x < mp.world) s.base[threadIdx.x] = s.cnt[threadIdx.x] ? atomicAdd(&mp.out_cnt[threadIdx.x], s.cnt[threadIdx.x]) : 0u;
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
-        const uint32_t w = s.where[e], g = w >> 24;
-        const uint32_t pos = s.base[g] + (w & 0xFFFFFFu);
-        mp.bid_out[g][pos] = s.ent[e];
-        mp.slot_pos[s.slot[e]] = pos;
+        const uint32_t w = s.where[e], g = w >> 24, at = s.off[g] + (w & 0xFFFFFFu);
+        s.sorted[at] = s.ent[e];
+        s.slot_sorted[at] = s.slot[e];
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+        uint32_t g = 0;
+#pragma unroll
+        for (int k = 1; k < kMeshMaxRanks; ++k) g += (t >= s.off[k]) ? 1u : 0u;
+        const uint32_t pos = s.base[g] + (t - s.off[g]);
+        mp.bid_out[g][pos] = s.sorted[t];
+        mp.slot_pos[s.slot_sorted[t]] = pos;
     }
     __syncthreads();
     mesh_stage_reset(s);
@@ -297,10 +314,8 @@ __device__ __forceinline__ void mesh_bid_end(const Params& p, const MeshParams& 
 
 // Uniform-degree CSR (K % 8 == 0).  ZERO: first round of a solve, all prices exactly 0 (no gather); NARROW: values
 // read from their u16 mirror.  Two rows per lane group in flight.
-template <int LPR8, bool ZERO, bool NARROW>
-__global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params p, const __grid_constant__ MeshParams mp) {
-    __shared__ MeshStage s;
-    const HotState h = load_hot(p.st);
+template <int LPR8, bool ZERO, bool NARROW, bool PERSIST>
+__device__ __forceinline__ void mesh_bid_body(const Params& p, const MeshParams& mp, const HotState& h, MeshStage& s) {
     if (!mesh_round_begin(p, mp, h)) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) mesh_stamp(mp, p.st, 0);
     const uint32_t cur = h.cur, qlen = h.qlen[cur & 1u];
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params 
     const uint32_t K = h.regular_k, sign_flip = h.sign_flip, algo = h.algo, base_person = h.person_base;
     const double eps = h.eps, thr = h.threshold;
     const double* mesh_prices = reinterpret_cast<const double*>(&mp);     // ld_price<PRICE_MESH> reads mp.view
-    constexpr int MODE = ZERO ? PRICE_ZERO : PRICE_MESH;
+    constexpr int MODE = ZERO ? PRICE_ZERO : (PERSIST ? PRICE_MESH_CG : PRICE_MESH);
     constexpr int GPB = kWideThreads / LPR8;
     constexpr int U = 2;
     const int lane = threadIdx.x % LPR8;
@@ -338,7 +353,7 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params 
                 choice_init(c[u]);
                 key_choice_init(kc[u]);
                 if (valid[u]) {
-                    i[u] = identity ? q[u] : __ldg(queue + q[u]);
+                    i[u] = identity ? q[u] : (PERSIST ? __ldcg(queue + q[u]) : __ldg(queue + q[u]));
                     const uint32_t a = i[u] * K;
                     if (!prune)
                     for (uint32_t off = 8u * (uint32_t)lane; off < K; off += 8u * LPR8) {
@@ -369,11 +384,16 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params 
     mesh_bid_end(p, mp, s, qlen);
 }
 
-// Ragged CSR: aligned 4-arc chunks, masked ends, extents from row_ptr (the layout of bid_wide_kernel).
-template <int LPR>
-__global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_ragged_kernel(const Params p, const __grid_constant__ MeshParams mp) {
+template <int LPR8, bool ZERO, bool NARROW>
+__global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_kernel(const Params p, const __grid_constant__ MeshParams mp) {
     __shared__ MeshStage s;
     const HotState h = load_hot(p.st);
+    mesh_bid_body<LPR8, ZERO, NARROW, false>(p, mp, h, s);
+}
+
+// Ragged CSR: aligned 4-arc chunks, masked ends, extents from row_ptr (the layout of bid_wide_kernel).
+template <int LPR, bool PERSIST>
+__device__ __forceinline__ void mesh_bid_ragged_body(const Params& p, const MeshParams& mp, const HotState& h, MeshStage& s) {
     if (!mesh_round_begin(p, mp, h)) return;
     const uint32_t cur = h.cur, qlen = h.qlen[cur & 1u];
     const bool identity = h.identity != 0;
@@ -397,18 +417,19 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_ragged_kernel(const 
             const bool valid = q < chunk_end;
             uint32_t i = 0, a = 0, b = 0;
             if (valid) {
-                i = identity ? q : __ldg(queue + q);
+                i = identity ? q : (PERSIST ? __ldcg(queue + q) : __ldg(queue + q));
                 a = __ldg(p.row_ptr + i);
                 b = __ldg(p.row_ptr + i + 1);
             }
+            constexpr int GMODE = PERSIST ? PRICE_MESH_CG : PRICE_MESH;
             Choice c;
             choice_init(c);
             if (zero) scan_row<LPR, PRICE_ZERO>(c, p.cols, p.vals, mesh_prices, a, b, sign_flip, lane);
-            else scan_row<LPR, PRICE_MESH>(c, p.cols, p.vals, mesh_prices, a, b, sign_flip, lane);
+            else scan_row<LPR, GMODE>(c, p.cols, p.vals, mesh_prices, a, b, sign_flip, lane);
             choice_group_reduce<LPR>(c);
             if (valid && lane == 0) {
                 const Bid r = zero ? make_bid<PRICE_ZERO>(c, algo, eps, thr, mesh_prices)
-                                   : make_bid<PRICE_MESH>(c, algo, eps, thr, mesh_prices);
+                                   : make_bid<GMODE>(c, algo, eps, thr, mesh_prices);
                 atomicAdd(&s.arcs, (unsigned long long)(b - a));
                 mesh_stage_bid(s, p, mp, r, q, i + base_person);
             }
@@ -418,12 +439,20 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_ragged_kernel(const 
     mesh_bid_end(p, mp, s, qlen);
 }
 
+template <int LPR>
+__global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_ragged_kernel(const Params p, const __grid_constant__ MeshParams mp) {
+    __shared__ MeshStage s;
+    const HotState h = load_hot(p.st);
+    mesh_bid_ragged_body<LPR, false>(p, mp, h, s);
+}
+
 // =============================================================================================================
 // K2: owner side, pass 1 -- the maximum packed word per object over everything that arrived (local atomics only).
 // =============================================================================================================
-__global__ void __launch_bounds__(kWideThreads) mesh_max_kernel(const Params p, const __grid_constant__ MeshParams mp) {
+constexpr uint32_t kMeshTailTotal = 4096;    // bidders (all ranks together) from which the persistent tail engine takes over
+
+__device__ __forceinline__ void mesh_max_body(const Params& p, const MeshParams& mp, const HotState& h) {
     DevState* st = p.st;
-    const HotState h = load_hot(st);
     if (h.done) return;
     const uint32_t epoch = ((volatile DevState*)st)->mesh_epoch, round = ((volatile DevState*)st)->mesh_round;
     if (mp.wait_at_start && !mesh_wait(mp, st, epoch + 1u)) return;
@@ -432,9 +461,12 @@ __global__ void __launch_bounds__(kWideThreads) mesh_max_kernel(const Params p, 
         // the ranks' queue lengths of THIS round (published by their K4 of the previous one, ordered by B1): all zero means
         // nobody bid -- the solve ends here on every rank, in the same round.  `done` is set by one thread, after every block
         // has read the state (ticket), so that no block of this very launch can take the `h.done` exit while others go on.
-        unsigned long long total = 0;
-        for (uint32_t g = 0; g < mp.world; ++g)
-            total += *reinterpret_cast<const volatile unsigned long long*>(&mp.box[mp.rank]->next_total[g]);
+        unsigned long long total = 0, part[kMeshMaxRanks];
+#pragma unroll
+        for (int g = 0; g < kMeshMaxRanks; ++g)           // all loads in flight together
+            part[g] = ((uint32_t)g < mp.world) ? __ldcg(&mp.box[mp.rank]->next_total[g]) : 0ull;
+#pragma unroll
+        for (int g = 0; g < kMeshMaxRanks; ++g) total += part[g];
         if (total == 0ull) {
             if (mesh_last_block(&mp.tickets[1], false, gridDim.x) && threadIdx.x == 0) {
                 // this round's B1 has been signalled by every rank: the next solve must start behind it
@@ -443,12 +475,23 @@ __global__ void __launch_bounds__(kWideThreads) mesh_max_kernel(const Params p, 
             }
             return;
         }
+        // short rounds from here on: the one-block persistent engine behind this round's finish kernel runs them without
+        // kernel boundaries (every rank takes the same decision from the same numbers)
+        if (total <= kMeshTailTotal && mp.tail_engine && !mp.wait_at_start && blockIdx.x == 0 && threadIdx.x == 0 &&
+            ((volatile DevState*)st)->mesh_tail == 0u) {
+            ((volatile DevState*)st)->mesh_switch_round = round;
+            ((volatile DevState*)st)->mesh_tail = 1u;
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) mesh_stamp(mp, st, 3);
     const uint32_t pbits = h.pbits;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (uint32_t a = 0; a < mp.world; ++a) {
-        const uint32_t cnt = ld_cv_u32(&mp.box[mp.rank]->bid_count[a]);
+    uint32_t cnts[kMeshMaxRanks];
+#pragma unroll
+    for (int a = 0; a < kMeshMaxRanks; ++a) cnts[a] = ((uint32_t)a < mp.world) ? __ldcg(&mp.box[mp.rank]->bid_count[a]) : 0u;
+#pragma unroll
+    for (int a = 0; a < kMeshMaxRanks; ++a) {
+        const uint32_t cnt = cnts[a];
         const BidEntry* in = mp.my_bid_in + (size_t)a * mp.cap_bid;
         for (uint32_t e = tid; e < cnt; e += stride) {
             const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(in + e));      // stored by another GPU: past the L1
@@ -458,15 +501,24 @@ __global__ void __launch_bounds__(kWideThreads) mesh_max_kernel(const Params p, 
     }
 }
 
+__global__ void __launch_bounds__(kWideThreads) mesh_max_kernel(const Params p, const __grid_constant__ MeshParams mp) {
+    const HotState h = load_hot(p.st);
+    mesh_max_body(p, mp, h);
+}
+
 // =============================================================================================================
 // K3: owner side, pass 2 -- winners install price and owner, reply bits go back to the bidders' ranks, evicted
 // persons go to the ranks that hold them.
 // =============================================================================================================
 constexpr uint32_t kResolveChunk = 1024;     // entries one block resolves before it reserves room for their evictions
 
-__global__ void __launch_bounds__(kWideThreads) mesh_resolve_kernel(const Params p, const __grid_constant__ MeshParams mp) {
+struct ResolveSmem {
+    uint32_t evp[kResolveChunk], evw[kResolveChunk];   // evicted owners of a chunk: person, destination << 24 | rank
+    uint32_t cnt[kMeshMaxRanks], base[kMeshMaxRanks], n;
+};
+
+__device__ __forceinline__ void mesh_resolve_body(const Params& p, const MeshParams& mp, const HotState& h, ResolveSmem& rs) {
     DevState* st = p.st;
-    const HotState h = load_hot(st);
     if (h.done) return;
     if (((volatile DevState*)st)->mesh_error) return;
     const uint32_t pbits = h.pbits;
@@ -476,9 +528,12 @@ __global__ void __launch_bounds__(kWideThreads) mesh_resolve_kernel(const Params
     const uint32_t warp = threadIdx.x >> 5;
     constexpr uint32_t kWarps = kWideThreads / 32;
 
-    // evicted owners of a chunk, staged: ONE global atomic per destination rank and chunk reserves their room
-    __shared__ uint32_t s_evp[kResolveChunk], s_evw[kResolveChunk];
-    __shared__ uint32_t s_cnt[kMeshMaxRanks], s_base[kMeshMaxRanks], s_n;
+    // evicted owners of a chunk are staged in `rs`: ONE global atomic per destination rank and chunk reserves their room
+    uint32_t* const s_evp = rs.evp;
+    uint32_t* const s_evw = rs.evw;
+    uint32_t* const s_cnt = rs.cnt;
+    uint32_t* const s_base = rs.base;
+    uint32_t& s_n = rs.n;
 
     // chunks of kResolveChunk entries, sender by sender
     uint32_t cnt[kMeshMaxRanks], nch[kMeshMaxRanks], total_chunks = 0;
@@ -584,12 +639,23 @@ __global__ void __launch_bounds__(kWideThreads) mesh_resolve_kernel(const Params
     }
 }
 
+__global__ void __launch_bounds__(kWideThreads) mesh_resolve_kernel(const Params p, const __grid_constant__ MeshParams mp) {
+    __shared__ ResolveSmem rs;
+    const HotState h = load_hot(p.st);
+    mesh_resolve_body(p, mp, h, rs);
+}
+
 // =============================================================================================================
 // K4: bidder side -- outcomes of this rank's bids, intake of the evicted persons, next queue, round accounting.
 // =============================================================================================================
-__global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params p, const __grid_constant__ MeshParams mp) {
+struct FinishSmem {
+    uint32_t emit[kAssignChunk];
+    uint32_t cnt, base;
+};
+
+template <bool PERSIST>
+__device__ __forceinline__ void mesh_finish_body(const Params& p, const MeshParams& mp, const HotState& h, FinishSmem& fs) {
     DevState* st = p.st;
-    const HotState h = load_hot(st);
     if (h.done) return;
     const uint32_t epoch = ((volatile DevState*)st)->mesh_epoch;
     if (mp.wait_at_start && !mesh_wait(mp, st, epoch + 2u)) return;
@@ -601,8 +667,9 @@ __global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params 
     uint32_t* next_len = &st->qlen[(cur ^ 1u) & 1u];
     const uint32_t my_first = mp.row_begin[mp.rank];
 
-    __shared__ uint32_t s_emit[kAssignChunk];
-    __shared__ uint32_t s_cnt, s_base;
+    uint32_t* const s_emit = fs.emit;
+    uint32_t& s_cnt = fs.cnt;
+    uint32_t& s_base = fs.base;
     const int lane = threadIdx.x & 31;
     // work items: [0, qlen) the slots of this round's bidders, then the evict inbox regions rank by rank; a block takes
     // contiguous chunks of up to kAssignChunk items and reserves room in the next queue once per chunk
@@ -626,10 +693,10 @@ __global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params 
             const uint32_t t = t0 + threadIdx.x;
             uint32_t emit = SLA_DEV_NONE;
             if (t < stop && t < qlen) {
-                const uint32_t j = p.slot_obj[t];
+                const uint32_t j = PERSIST ? __ldcg(p.slot_obj + t) : p.slot_obj[t];
                 if (j != SLA_DEV_NONE) {
-                    const uint32_t i = identity ? t : __ldg(queue + t);
-                    const uint32_t pos = mp.slot_pos[t];
+                    const uint32_t i = identity ? t : (PERSIST ? __ldcg(queue + t) : __ldg(queue + t));
+                    const uint32_t pos = PERSIST ? __ldcg(mp.slot_pos + t) : mp.slot_pos[t];
                     bool won = false;
                     if (pos != SLA_DEV_NONE) {
                         const uint32_t g = j >> mp.view.shift;
@@ -692,6 +759,54 @@ __global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params 
     }
 }
 
+__global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params p, const __grid_constant__ MeshParams mp) {
+    __shared__ FinishSmem fs;
+    const HotState h = load_hot(p.st);
+    mesh_finish_body<false>(p, mp, h, fs);
+}
+
+// =============================================================================================================
+// Tail engine: ONE persistent block per rank runs whole rounds -- the same four phases, a __syncthreads() where the
+// grid-wide path has a kernel boundary -- once all ranks together have at most kMeshTailTotal bidders (DevState::
+// mesh_tail, set by the max kernel on every rank in the same round).  A short round on the grid-wide path is four
+// launches of mostly idle grids plus two flag barriers, ~75 us at 8 GPUs; in here it is the two barriers and a few
+// dependent memory round trips.  Everything another rank or an earlier round of this launch may have changed is read
+// past the L1 (queue, prices, inboxes, the control block).
+// LPR8 > 0: uniform-degree CSR with that many lanes per row (NARROW: u16 value mirror); LPR8 == 0: ragged CSR, LPR lanes.
+// =============================================================================================================
+template <int LPR8, int LPR, bool NARROW>
+__global__ void __launch_bounds__(kWideThreads, 1) mesh_tail_kernel(const Params p, const __grid_constant__ MeshParams mp) {
+    union TailSmem {
+        MeshStage stage;
+        ResolveSmem rs;
+        FinishSmem fs;
+    };
+    __shared__ TailSmem sm;
+    DevState* st = p.st;
+    {
+        const volatile DevState* v = st;
+        if (v->done || !v->mesh_tail || v->mesh_error) return;
+    }
+    for (;;) {
+        HotState h = load_hot_cg(st);
+        if (h.done || ((volatile DevState*)st)->mesh_error) break;
+        if (LPR8 > 0) mesh_bid_body<(LPR8 > 0 ? LPR8 : 1), false, NARROW, true>(p, mp, h, sm.stage);
+        else mesh_bid_ragged_body<(LPR > 0 ? LPR : 2), true>(p, mp, h, sm.stage);
+        __syncthreads();
+        h = load_hot_cg(st);
+        mesh_max_body(p, mp, h);            // (also the termination test)
+        __threadfence();
+        __syncthreads();
+        h = load_hot_cg(st);
+        if (h.done || ((volatile DevState*)st)->mesh_error) break;
+        mesh_resolve_body(p, mp, h, sm.rs);
+        __syncthreads();
+        mesh_finish_body<true>(p, mp, h, sm.fs);
+        __threadfence();
+        __syncthreads();
+    }
+}
+
 // Initialisation of this rank's objects and persons (solver.rs:218-229) and the export of the solved cells into the
 // plain prices / object_to_person arrays the C ABI hands out.
 __global__ void __launch_bounds__(kWideThreads) mesh_init_kernel(const Params p, const __grid_constant__ MeshParams mp,
@@ -744,6 +859,7 @@ struct sla_mesh_state {
     uint64_t exec_generation = 0;
     const void* exec_vals16 = nullptr;
     bool exec_first = false;
+    int exec_tail = -1;
     double eps = 0.0, gfirst = 0.0;
     int flip = 0;
     uint32_t launches = 0, graph_launches = 0;
@@ -758,11 +874,27 @@ uint32_t mesh_lpr8(const sla_ctx* c) {           // lanes per row of the uniform
     return l;
 }
 
-// which: 0 bid, 1 max, 2 resolve, 3 finish
+// which: 0 bid, 1 max, 2 resolve, 3 finish, 4 the persistent tail engine (concurrent ranks only)
 void mesh_launch_phase(sla_ctx* c, const Params& p, int which, bool first_round, bool lockstep) {
     sla_mesh_state* ms = c->mesh;
     sla::MeshParams mp = ms->mp;
     mp.wait_at_start = lockstep ? 1u : 0u;
+    mp.tail_engine = (!lockstep && c->opt_mesh_tail) ? 1u : 0u;
+    if (which == 4) {
+        const bool narrow = narrow_scan_ptr(c) != nullptr && p.vals16 != nullptr;
+        if (use_regular(c)) {
+            const uint32_t l = mesh_lpr8(c);
+#define SLA_MESH_TAIL(L) do { if (narrow) mesh_tail_kernel<L, 0, true><<<1, kWideThreads, 0, c->stream>>>(p, mp); \
+                              else mesh_tail_kernel<L, 0, false><<<1, kWideThreads, 0, c->stream>>>(p, mp); } while (0)
+            if (l == 1) SLA_MESH_TAIL(1); else if (l == 2) SLA_MESH_TAIL(2); else SLA_MESH_TAIL(4);
+#undef SLA_MESH_TAIL
+        } else {
+            if (c->lpr <= 2) mesh_tail_kernel<0, 2, false><<<1, kWideThreads, 0, c->stream>>>(p, mp);
+            else if (c->lpr <= 8) mesh_tail_kernel<0, 8, false><<<1, kWideThreads, 0, c->stream>>>(p, mp);
+            else mesh_tail_kernel<0, 32, false><<<1, kWideThreads, 0, c->stream>>>(p, mp);
+        }
+        return;
+    }
     const int grid_bid = c->num_sms * 3;
     switch (which) {
         case 0:
@@ -1082,12 +1214,13 @@ int sla_mesh_solve(sla_ctx* ctx) {
         // launches: 8 rounds of the general shape
         const int rounds = first ? (ms->learned_rounds ? (int)std::min<uint32_t>(ms->learned_rounds, 256u) : 8) : 8;
         if (!ms->exec || ms->exec_rounds != rounds || ms->exec_generation != ctx->generation ||
-            ms->exec_vals16 != narrow_scan_ptr(ctx) || ms->exec_first != first) {
+            ms->exec_vals16 != narrow_scan_ptr(ctx) || ms->exec_first != first || ms->exec_tail != ctx->opt_mesh_tail) {
             if (ms->exec) { cudaGraphExecDestroy(ms->exec); ms->exec = nullptr; }
             cudaGraph_t graph = nullptr;
             CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            const int phases = ctx->opt_mesh_tail ? 5 : 4;     // the tail engine sits behind every round's finish kernel
             for (int r = 0; r < rounds; ++r)
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < phases; ++k) {
                     // the first round's scan + push is bracketed by two event-record nodes (sla_mesh_round1_ms)
                     const bool bracket = first && r == 0 && k == 0;
                     if (bracket) cudaEventRecordWithFlags(ctx->ev[3], ctx->stream, cudaEventRecordExternal);
@@ -1103,10 +1236,11 @@ int sla_mesh_solve(sla_ctx* ctx) {
             ms->exec_generation = ctx->generation;
             ms->exec_vals16 = narrow_scan_ptr(ctx);
             ms->exec_first = first;
+            ms->exec_tail = ctx->opt_mesh_tail;
         }
         CU(cudaGraphLaunch(ms->exec, ctx->stream));
         ms->graph_launches += 1;
-        ms->launches += (uint32_t)(4 * rounds);
+        ms->launches += (uint32_t)((ctx->opt_mesh_tail ? 5 : 4) * rounds);
         first = false;
         int d = 0;
         if ((rc = sla_mesh_poll(ctx, &d, nullptr, nullptr))) return rc;
@@ -1160,7 +1294,10 @@ int sla_mesh_finish(sla_ctx* ctx, uint32_t* person_to_object, uint32_t* object_t
         }
     }
     ms->epoch = f.mesh_epoch;
-    ms->learned_rounds = (uint32_t)std::min<unsigned long long>(f.rounds + 1ull, 256ull);
+    // graph length of the next solve of this resident shard: up to the round in which the tail engine took over, or
+    // all rounds plus the one that notices the end
+    ms->learned_rounds = f.mesh_tail ? std::max<uint32_t>(f.mesh_switch_round, 1u)
+                                     : (uint32_t)std::min<unsigned long long>(f.rounds + 1ull, 256ull);
     ms->active = false;
     ctx->has_solution = false;      // the plain arrays hold this rank's slices only: the single-GPU post-processing calls do not apply
     ctx->best_dirty = true;

@@ -224,3 +224,61 @@ def test_mesh_threshold_drops_match_model(sla, oracle):
     assert ref["stats"]["num_unassigned"] >= 40
     res = mesh_lockstep_solve(make_mesh_shards(sla, n, m, rp, c, v, 3))
     assert_mesh_equals_model(res, ref)
+
+
+@pytest.mark.parametrize("shape", ["regular_u16", "regular_f64", "ragged", "k64"])
+@pytest.mark.parametrize("tail", [1, 0])
+def test_mesh_concurrent_path_world_one_equals_model(sla, oracle, shape, tail):
+    """The production path of the mesh engine -- sla_mesh_solve: rounds captured into CUDA graphs, barriers waited for in
+    the producing kernel's last block, the persistent one-block tail engine for the short rounds (option mesh_tail) -- with
+    a world of ONE rank (one GPU is enough: the only flags it waits for are its own).  Bit-identical to the model; solved
+    three times on the resident shard (the graph length learned from the previous solve, the running barrier epoch)."""
+    from sparse_linear_assignment_b200.distributed import MeshShard, mesh_assemble
+    rng = np.random.default_rng(77)
+    if shape == "ragged":
+        n, m = 30_000, 50_000
+        counts = rng.integers(2, 12, size=n)
+        rp = np.zeros(n + 1, dtype=np.uint32)
+        rp[1:] = np.cumsum(counts)
+        perm = rng.permutation(m)[:n]
+        rows = []
+        for i in range(n):
+            others = rng.choice(m - 1, size=int(counts[i]) - 1, replace=False)
+            rows.append(np.sort(np.concatenate([[perm[i]], others + (others >= perm[i])])))
+        c = np.concatenate(rows).astype(np.uint32)
+        v = rng.integers(1, 500, size=int(rp[-1])).astype(np.float64)
+        eps = 0.5
+    else:
+        n, m, k = (70_000, 200_000, 16) if shape != "k64" else (20_000, 60_000, 64)
+        rp, c, v = sla.generators.kregular_host(n, m, k, seed=5)
+        if shape == "regular_f64":
+            v = v + 0.125
+        eps = None
+    ref = oracle.jacobi_model("khosla", n, m, rp, c, v, eps=eps, khosla_scaling=False)
+    solver, _ = sla.KhoslaSolver.new(n, m, len(c))
+    solver.set_option("mesh_tail", tail)
+    solver.load_csr(n, m, rp, c, v.copy())
+    shard = MeshShard(solver, 0, 1, [0, n])
+    shard.connect_pointers([shard.block])
+    lo, hi, first = shard.local_value_range()
+    for rep in range(3):
+        shard.begin(False, eps, lo, hi, first)
+        shard.solve()
+        part = shard.finish()
+        res = mesh_assemble([part], [shard.owned()], m)
+        assert np.array_equal(res["p2o"], ref["p2o"]) and np.array_equal(res["o2p"], ref["o2p"])
+        assert np.array_equal(res["prices"], ref["prices"])
+        for key in ("num_unassigned", "bids", "bid_arcs", "dropped", "rounds"):
+            assert res["stats"][key] == ref["stats"][key], (key, rep)
+        assert shard.objective() == oracle_objective(rp, c, v, ref["p2o"])
+    if shape == "regular_u16":
+        assert solver.scan_value_bytes() == 2
+
+
+def oracle_objective(rp, c, v, p2o):
+    """Sum of the chosen arcs' values (all persons assigned, one arc per chosen column)."""
+    n = len(rp) - 1
+    counts = np.diff(rp.astype(np.int64))
+    hit = np.asarray(c, dtype=np.int64) == np.repeat(p2o.astype(np.int64), counts)
+    assert hit.sum() == n
+    return float(np.asarray(v)[hit].sum())
