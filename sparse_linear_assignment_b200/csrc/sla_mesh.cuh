@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_ragged_kernel(const 
 // =============================================================================================================
 // K2: owner side, pass 1 -- the maximum packed word per object over everything that arrived (local atomics only).
 // =============================================================================================================
-constexpr uint32_t kMeshTailTotal = 4096;    // bidders (all ranks together) from which the persistent tail engine takes over
+constexpr uint32_t kMeshTailTotal = 16384;   // bidders (all ranks together) from which the persistent tail engine takes over
 
 __device__ __forceinline__ void mesh_max_body(const Params& p, const MeshParams& mp, const HotState& h) {
     DevState* st = p.st;
@@ -535,28 +535,23 @@ __device__ __forceinline__ void mesh_resolve_body(const Params& p, const MeshPar
     uint32_t* const s_base = rs.base;
     uint32_t& s_n = rs.n;
 
-    // chunks of kResolveChunk entries, sender by sender
-    uint32_t cnt[kMeshMaxRanks], nch[kMeshMaxRanks], total_chunks = 0;
+    // The entries of all senders as ONE index space, every sender's region padded to a multiple of 32 (a warp's 32
+    // consecutive indices then belong to one sender and make up one reply word); blocks take chunks of kResolveChunk
+    // padded indices -- a short round is one chunk whatever the number of senders.
+    uint32_t cnt[kMeshMaxRanks], poff[kMeshMaxRanks + 1];
+    poff[0] = 0u;
 #pragma unroll
     for (int a = 0; a < kMeshMaxRanks; ++a) {
-        cnt[a] = ((uint32_t)a < mp.world) ? ld_cv_u32(&mp.box[mp.rank]->bid_count[a]) : 0u;
-        nch[a] = (cnt[a] + kResolveChunk - 1u) / kResolveChunk;
-        total_chunks += nch[a];
+        cnt[a] = ((uint32_t)a < mp.world) ? __ldcg(&mp.box[mp.rank]->bid_count[a]) : 0u;
+        poff[a + 1] = poff[a] + ((cnt[a] + 31u) & ~31u);
     }
+    const uint32_t total_padded = poff[kMeshMaxRanks];
+    const uint32_t total_chunks = (total_padded + kResolveChunk - 1u) / kResolveChunk;
     const uint32_t working = mesh_working_blocks(total_chunks);
     if (blockIdx.x >= working) return;
 
     for (uint32_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
-        uint32_t a = 0, lc = c, na = cnt[0];
-#pragma unroll
-        for (int g = 0; g < kMeshMaxRanks - 1; ++g) {
-            const bool past = (a == (uint32_t)g) && (lc >= nch[g]);
-            lc -= past ? nch[g] : 0u;
-            a += past ? 1u : 0u;
-            na = past ? cnt[g + 1] : na;
-        }
-        const uint32_t e0 = lc * kResolveChunk, e1 = (e0 + kResolveChunk < na) ? e0 + kResolveChunk : na;
-        const BidEntry* inb = mp.my_bid_in + (size_t)a * mp.cap_bid;
+        const uint32_t p0 = c * kResolveChunk, p1 = (p0 + kResolveChunk < total_padded) ? p0 + kResolveChunk : total_padded;
         if (threadIdx.x < kMeshMaxRanks) s_cnt[threadIdx.x] = 0u;
         if (threadIdx.x == 0) s_n = 0u;
         __syncthreads();
@@ -564,17 +559,25 @@ __device__ __forceinline__ void mesh_resolve_body(const Params& p, const MeshPar
         // (hundreds of MB) is far beyond the TLB's reach, a dependent random load costs microseconds, and only
         // memory-level parallelism hides it
         constexpr int UE = 4;
-        for (uint32_t w0 = 0; w0 * 32u < e1 - e0; w0 += kWarps * UE) {
+        for (uint32_t w0 = 0; w0 * 32u < p1 - p0; w0 += kWarps * UE) {
             uint4 raw[UE];
             unsigned long long word[UE];
-            uint32_t prev[UE];
+            uint32_t prev[UE], snd[UE], eloc[UE];
             bool in[UE], won[UE];
 #pragma unroll
             for (int u = 0; u < UE; ++u) {
-                const uint32_t e = e0 + (w0 + (uint32_t)u * kWarps + warp) * 32u + (uint32_t)lane;
-                in[u] = e < e1;
+                const uint32_t pi = p0 + (w0 + (uint32_t)u * kWarps + warp) * 32u + (uint32_t)lane;   // padded index
+                uint32_t a = 0;
+#pragma unroll
+                for (int k = 1; k < kMeshMaxRanks; ++k) a += (pi >= poff[k]) ? 1u : 0u;
+                uint32_t base_a = 0, cnt_a = 0;
+#pragma unroll
+                for (int k = 0; k < kMeshMaxRanks; ++k) { base_a = (a == (uint32_t)k) ? poff[k] : base_a; cnt_a = (a == (uint32_t)k) ? cnt[k] : cnt_a; }
+                snd[u] = a;
+                eloc[u] = pi - base_a;
+                in[u] = pi < p1 && eloc[u] < cnt_a;
                 raw[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (in[u]) raw[u] = __ldcg(reinterpret_cast<const uint4*>(inb + e));     // stored by another GPU: past the L1
+                if (in[u]) raw[u] = __ldcg(reinterpret_cast<const uint4*>(mp.my_bid_in + (size_t)a * mp.cap_bid + eloc[u]));   // stored by another GPU: past the L1
             }
 #pragma unroll
             for (int u = 0; u < UE; ++u) {
@@ -590,14 +593,16 @@ __device__ __forceinline__ void mesh_resolve_body(const Params& p, const MeshPar
             }
 #pragma unroll
             for (int u = 0; u < UE; ++u) {
-                const uint32_t w = w0 + (uint32_t)u * kWarps + warp;
                 if (won[u]) {
                     // one 128-bit store: {price = the winner's exact bid, owner = its person}
                     *reinterpret_cast<uint4*>(mp.my_cells + raw[u].x) = make_uint4(raw[u].z, raw[u].w, raw[u].y, 0u);
                     mp.my_best[raw[u].x] = 0ull;   // losers that look later see 0 or this word: neither equals theirs
                 }
                 const uint32_t wonmask = __ballot_sync(0xffffffffu, won[u]);
-                if (lane == 0 && w * 32u < e1 - e0) mp.reply_out[a][(e0 >> 5) + w] = wonmask;   // one word per 32 entries, back to the bidder's rank
+                // one word per 32 entries, back to the bidder's rank (the warp's 32 indices belong to one sender; words that
+                // lie wholly in the padding are skipped)
+                const uint32_t any_in = __ballot_sync(0xffffffffu, in[u]);
+                if (lane == 0 && any_in) mp.reply_out[snd[u]][eloc[u] >> 5] = wonmask;
                 const bool ev = prev[u] != SLA_DEV_NONE;
                 const uint32_t evmask = __ballot_sync(0xffffffffu, ev);
                 if (evmask) {
