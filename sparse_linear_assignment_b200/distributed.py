@@ -428,19 +428,35 @@ class MeshKhoslaSolver:
         return [int(x) for x in t.tolist()]
 
     def setup(self):
-        """Shard layout, this rank's mesh block, peer mappings of every other rank's block."""
+        """Shard layout, this rank's mesh block, peer mappings of every other rank's block.  A failure on any rank (no
+        peer access, out of memory, ...) is agreed upon collectively and raised on EVERY rank, so that callers can fall
+        back together instead of leaving the others in a collective."""
         counts = self._gather_i64(self.solver.num_rows())
         self.row_begins = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
-        self.shard = self.shard_factory(self.solver, self.rank, self.world, self.row_begins)
-        mine = torch.frombuffer(bytearray(self.shard.export_handle()), dtype=torch.uint8).to(self.dev)
+        problem = ""
+        mine = torch.zeros(64, dtype=torch.uint8)
+        try:
+            self.shard = self.shard_factory(self.solver, self.rank, self.world, self.row_begins)
+            mine = torch.frombuffer(bytearray(self.shard.export_handle()), dtype=torch.uint8)
+        except Exception as e:          # noqa: BLE001 -- reported through the collective below
+            problem = f"rank {self.rank}: {e}"
         allh = torch.zeros(self.world * 64, dtype=torch.uint8, device=self.dev)
-        allh[self.rank * 64:(self.rank + 1) * 64] = mine
+        allh[self.rank * 64:(self.rank + 1) * 64] = mine.to(self.dev)
         if self.world > 1:
             dist.all_reduce(allh, op=dist.ReduceOp.SUM, group=self.group)      # disjoint slices: a sum is a gather
-        raw = bytes(allh.cpu().numpy().tobytes())
-        self.shard.connect_handles([raw[g * 64:(g + 1) * 64] for g in range(self.world)])
+        if not problem:
+            try:
+                raw = bytes(allh.cpu().numpy().tobytes())
+                self.shard.connect_handles([raw[g * 64:(g + 1) * 64] for g in range(self.world)])
+            except Exception as e:      # noqa: BLE001
+                problem = f"rank {self.rank}: {e}"
+        ok = torch.tensor([0 if problem else 1], dtype=torch.int64, device=self.dev)
         if self.world > 1:
-            dist.barrier(group=self.group)      # every rank has mapped every block before anybody starts a solve
+            # (also the barrier: every rank has mapped every block before anybody starts a solve)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self.shard = None
+            raise _lib.SlaError(_lib.SLA_ERR_CUDA, "mesh setup failed on at least one rank" + (f" ({problem})" if problem else ""))
         return self
 
     def _global_range(self):

@@ -484,8 +484,9 @@ def test_wide_first_round_with_most_persons_losing(sla, oracle):
 def test_cfg1_khosla_1000x10000_k32(sla, oracle):
     from sparse_linear_assignment_b200 import generators as G
     n, m, k, _ = G.CONFIGS["cfg1"]
-    rp, c, v = G.kregular_host(n, m, k, seed=1)
-    solver, z = gpu_solve(sla, "KhoslaSolver", n, m, rp, c, v)                 # (1a) integer costs, eps=None
+    rp, c, v = G.kregular_host(n, m, k, seed=1, value_dist="beta33")          # (1a) floor(700*Beta(3,3)+300), benchmark.rs:60,73
+    assert v.min() >= 300 and v.max() < 1000 and abs(v.mean() - 650) < 5 and abs(v.std() - 132.3) < 4
+    solver, z = gpu_solve(sla, "KhoslaSolver", n, m, rp, c, v)                 # integer costs, eps=None
     o = oracle.OracleSolver("khosla", n, m, n * k)
     o.load_csr(n, m, rp, c, v)
     o.solve()
