@@ -823,7 +823,7 @@ def main_ours(args):
                 if vb == 2:
                     kname = kname[:-1] + ",u16>"
                 roof[key] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": ncu_traffic(kname), "kernel": kname, "launch": "round 1 (all persons bid)",
+                             "traffic": ncu_traffic(kname) if args.workload == "cfg3" else None, "kernel": kname, "launch": "round 1 (all persons bid)",
                              "bidders": rec["bidders"], "arcs": rec["arcs"], "algorithmic_bytes": alg,
                              "launch_us": t_ms * 1e3, "peak_source": peak_src, "value_bytes_in_hbm": vb,
                              "bytes_at_f64_values": survey, "equivalent_f64_gbs": survey / (t_ms * 1e-3) / 1e9}

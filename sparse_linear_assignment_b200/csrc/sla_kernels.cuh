@@ -126,29 +126,35 @@ __device__ __forceinline__ void scan_row_pruned(Choice& c, const Params& p, cons
             }
         }
     }
-    // the lane's two probes: (approximately) its two most valuable arcs
+    // the lane's two probes: (approximately) its two most valuable arcs -- a top-2 over `key with the position in its low
+    // three bits` (integer min / max, three instructions per arc; which two arcs are probed does not matter for the result)
     int b1 = (int)0x80000000, b2 = (int)0x80000000;
-    uint32_t i1 = 0u, i2 = 1u, c1 = cj[0], c2 = cj[1];
-    double v1 = vv[0], v2 = vv[1];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        const bool gt = key[t] > b1 || t == 0, gs = key[t] > b2 || t <= 1;
-        i2 = gt ? i1 : (gs ? (uint32_t)t : i2);
-        c2 = gt ? c1 : (gs ? cj[t] : c2);
-        v2 = gt ? v1 : (gs ? vv[t] : v2);
-        b2 = gt ? b1 : (gs ? key[t] : b2);
-        i1 = gt ? (uint32_t)t : i1;
-        c1 = gt ? cj[t] : c1;
-        v1 = gt ? vv[t] : v1;
-        b1 = gt ? key[t] : b1;
+        const int pk = NARROW ? (int)(((uint32_t)key[t] << 3) | (uint32_t)t) : ((key[t] & ~7) | t);
+        const int lo = min(b1, pk);
+        b1 = max(b1, pk);
+        b2 = max(b2, lo);
     }
-    double p1 = 0.0, p2 = 0.0, hiP = neg_inf(), loP = neg_inf();
-    if (has) {
-        p1 = ld_price<MODE>(prices, c1);
-        p2 = ld_price<MODE>(prices, c2);
-        const double a = v1 - p1, b = v2 - p2;
-        hiP = a > b ? a : b;
-        loP = a > b ? b : a;
+    const uint32_t i1 = (uint32_t)b1 & 7u, i2 = (uint32_t)b2 & 7u;      // distinct: every pk carries its own position
+    double pr[8];
+    double hiP = neg_inf(), loP = neg_inf();
+    {
+        double mx = neg_inf(), mn = __longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const bool probe = has && (((uint32_t)t == i1) || ((uint32_t)t == i2));
+            pr[t] = 0.0;
+            if (probe) pr[t] = ld_price<MODE>(prices, cj[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const bool probe = ((uint32_t)t == i1) || ((uint32_t)t == i2);
+            const double pf = vv[t] - pr[t];
+            mx = (probe && pf > mx) ? pf : mx;
+            mn = (probe && pf < mn) ? pf : mn;
+        }
+        if (has) { hiP = mx; loP = mn; }
     }
 #pragma unroll
     for (int m = LPR8 / 2; m >= 1; m >>= 1) {
@@ -161,21 +167,18 @@ __device__ __forceinline__ void scan_row_pruned(Choice& c, const Params& p, cons
         loP = l2;
     }
     const double bound = loP;
-    double pr[8];
     bool use[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         const bool probe = ((uint32_t)t == i1) || ((uint32_t)t == i2);
-        use[t] = has && (probe || vv[t] >= bound);
-        pr[t] = 0.0;
-        if (has && !probe && vv[t] >= bound) pr[t] = ld_price<MODE>(prices, cj[t]);
+        const bool more = has && !probe && vv[t] >= bound;
+        use[t] = has && (probe || more);
+        if (more) pr[t] = ld_price<MODE>(prices, cj[t]);
     }
     choice_init(c);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const double pt = ((uint32_t)t == i1) ? p1 : (((uint32_t)t == i2) ? p2 : pr[t]);
-        choice_update(c, use[t] ? (vv[t] - pt) : neg_inf(), vv[t], g + t, cj[t]);
-    }
+    for (int t = 0; t < 8; ++t)
+        choice_update(c, use[t] ? (vv[t] - pr[t]) : neg_inf(), vv[t], g + t, cj[t]);
     choice_group_reduce<LPR8>(c);
 }
 
