@@ -449,7 +449,8 @@ __global__ void __launch_bounds__(kWideThreads, 3) mesh_bid_ragged_kernel(const 
 // =============================================================================================================
 // K2: owner side, pass 1 -- the maximum packed word per object over everything that arrived (local atomics only).
 // =============================================================================================================
-constexpr uint32_t kMeshTailTotal = 16384;   // bidders (all ranks together) from which the persistent tail engine takes over
+constexpr uint32_t kMeshTailPerRank = 512;   // average bidders per rank from which the persistent tail engine takes over (two
+                                             // passes of its one block; 2.8 k per rank cost it 266 us a round at 2 GPUs)
 
 __device__ __forceinline__ void mesh_max_body(const Params& p, const MeshParams& mp, const HotState& h) {
     DevState* st = p.st;
@@ -477,7 +478,7 @@ __device__ __forceinline__ void mesh_max_body(const Params& p, const MeshParams&
         }
         // short rounds from here on: the one-block persistent engine behind this round's finish kernel runs them without
         // kernel boundaries (every rank takes the same decision from the same numbers)
-        if (total <= kMeshTailTotal && mp.tail_engine && !mp.wait_at_start && blockIdx.x == 0 && threadIdx.x == 0 &&
+        if (total <= (unsigned long long)kMeshTailPerRank * mp.world && mp.tail_engine && !mp.wait_at_start && blockIdx.x == 0 && threadIdx.x == 0 &&
             ((volatile DevState*)st)->mesh_tail == 0u) {
             ((volatile DevState*)st)->mesh_switch_round = round;
             ((volatile DevState*)st)->mesh_tail = 1u;
@@ -772,7 +773,7 @@ __global__ void __launch_bounds__(kWideThreads) mesh_finish_kernel(const Params 
 
 // =============================================================================================================
 // Tail engine: ONE persistent block per rank runs whole rounds -- the same four phases, a __syncthreads() where the
-// grid-wide path has a kernel boundary -- once all ranks together have at most kMeshTailTotal bidders (DevState::
+// grid-wide path has a kernel boundary -- once the ranks have at most kMeshTailPerRank bidders each on average (DevState::
 // mesh_tail, set by the max kernel on every rank in the same round).  A short round on the grid-wide path is four
 // launches of mostly idle grids plus two flag barriers, ~75 us at 8 GPUs; in here it is the two barriers and a few
 // dependent memory round trips.  Everything another rank or an earlier round of this launch may have changed is read
