@@ -862,7 +862,7 @@ def main_ours(args):
             "roofline_whole_solve": {"achieved": whole, "unit": "GB/s", "frac": whole / peak,
                                      "note": "sum over rounds of 12*A + 8*B (values counted as f64) over the whole solve time, tail rounds included"},
             "cpu_baseline": cpu,
-            "solve": {k_: stats[k_] for k_ in ("rounds", "wide_rounds", "tail_rounds", "bids", "bid_arcs", "num_unassigned",
+            "solve": {k_: stats[k_] for k_ in ("rounds", "wide_rounds", "tail_rounds", "cluster_rounds", "bids", "bid_arcs", "num_unassigned",
                                                "kernel_launches", "graph_launches", "ms_solve")},
             "objective": objective,
         }

@@ -60,11 +60,13 @@ typedef struct sla_stats {
     uint32_t dropped;     /* Khosla: persons dropped by the price threshold (ksparse.rs:218-220) */
     uint32_t values_negated;
     uint64_t wide_rounds; /* rounds run by the grid-wide kernels */
-    uint64_t tail_rounds; /* rounds run by the single-CTA persistent engine */
+    uint64_t tail_rounds; /* rounds run by the persistent engines: the single-CTA tail engine and the cluster engine */
     uint32_t kernel_launches; /* kernels launched for this solve (graph nodes included) */
     uint32_t graph_launches;
     float ms_solve;       /* device time of the solve, CUDA events on the context's stream, D2H excluded */
     float ms_total;       /* ms_solve + result copies */
+    uint64_t cluster_rounds; /* of tail_rounds: rounds run by the thread-block-cluster engine (queues of a few thousand bidders
+                                on instances whose prices do not fit one CTA's shared memory) */
 } sla_stats;
 
 /* One record per bid-scan launch when option "profile" is 1 (host-driven loop, CUDA events around each kernel). */

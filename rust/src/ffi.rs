@@ -31,6 +31,7 @@ pub struct sla_stats {
     pub graph_launches: u32,
     pub ms_solve: f32,
     pub ms_total: f32,
+    pub cluster_rounds: u64,
 }
 
 /// `sla_round_profile` of include/sla.h.

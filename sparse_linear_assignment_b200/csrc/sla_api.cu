@@ -53,6 +53,7 @@ struct GraphSlot {
     size_t l2_bytes = 0;
     const void* vals16 = nullptr;   // u16 value mirror the regular bid kernels were captured with (nullptr: f64 values)
     uint32_t learned_wide = 0;      // > 0: first graph of a plain Khosla solve shaped as `learned_wide` wide rounds + one tail launch
+    uint32_t own_max = 0;           // DevState::tail_own_max the graph was captured for; the cluster engine is in it when own_max < tail_max
 };
 
 }  // namespace
@@ -298,6 +299,11 @@ struct sla_ctx {
     int opt_stream_scan = 0;   // first-round scan through the TMA pipeline (bid_stream_kernel): opt-in, measured 4 % slower
     int opt_smem_prices = 1, opt_smem_owners = 1, opt_khosla_scaling = 1;
     int opt_prune = 1;         // bound-pruned gather in the uniform-degree scans of rounds with >= 32 Ki bidders
+    int opt_cluster_engine = 0; // opt-in ("cluster_engine" = 1; large M, no shared-memory price mirror): queues of kTailSlots+1 ..
+                                // kMidMax bidders run in mid_kernel.  Bit-identical, but measured no faster than the grid-wide pair +
+                                // single-CTA engine it replaces (cfg3 0.181 vs 0.172 ms, cfg5 2.73 vs 2.71 ms: a round is ~7 us of
+                                // dependent memory round trips either way; profiles/r02_cluster_engine_probe.jsonl), hence off
+    int opt_cluster_handover = (int)kTailSlots;   // ... which hands over to the single-CTA engine at this many bidders
     int opt_learn_shape = 1;   // plain Khosla: the first graph of a solve has as many wide rounds as the previous solve of the
                                // same resident CSR needed, followed by one tail launch (no no-op launches in between)
     int opt_mesh_tail = 1;     // mesh engine: the persistent one-block tail engine runs the short rounds
@@ -481,7 +487,7 @@ void launch_bid_regular_m(sla_ctx* c, const Params& p) {
 
 bool use_regular(const sla_ctx* c) { return c->regular_k != 0 && c->opt_regular; }
 
-// which: 0 bid, 1 assign, 2 tail, 3 ecs, 4 phase_apply.  zero_first: this bid launch is the first round of a
+// which: 0 bid, 1 assign, 2 tail, 3 ecs, 4 phase_apply, 5 cluster engine.  zero_first: this bid launch is the first round of a
 // solve and all prices are known to be exactly 0 (only meaningful for the regular bid kernel; the generic one
 // reads the flag from the device state).
 template <int LPR>
@@ -501,6 +507,7 @@ void launch_one_t(sla_ctx* c, const Params& p, int which, bool zero_first) {
             else tail_kernel<LPR, false><<<1, kTailThreads, c->tail_smem_bytes, c->stream>>>(p);
             break;
         case 3: ecs_kernel<LPR><<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
+        case 5: mid_kernel<LPR><<<kMidCtas, kMidThreads, 0, c->stream>>>(p); break;   // one cluster (__cluster_dims__)
         default: phase_apply_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p); break;
     }
 }
@@ -521,6 +528,12 @@ void launch_one(sla_ctx* c, const Params& p, int which, bool zero_first = false)
 // the Khosla super-round as well.
 bool khosla_phases(const sla_ctx* c) { return c->opt_khosla_scaling && c->n_rows == c->n_cols; }
 
+// The cluster engine takes the queues between the single-CTA engine's reach and kMidMax when the tail engine has no
+// shared-memory price mirror (large M); an explicit "tail_max" option keeps the two-engine split it asks for.
+bool use_mid(const sla_ctx* c) {
+    return c->opt_cluster_engine && c->has_csr && !c->tail_smem_prices && !c->tail_max_user && c->tail_max_eff >= kTailSlots;
+}
+
 void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_first, bool tail_only) {
     if (!tail_only) {
         launch_one(c, p, 0, zero_first);
@@ -528,6 +541,7 @@ void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_fir
         if (zero_first) first_assign_objects_kernel<<<c->grid_wide, kWideThreads, 0, c->stream>>>(p);
         launch_one(c, p, 1, zero_first);
     }
+    if (use_mid(c)) launch_one(c, p, 5);
     launch_one(c, p, 2);
     if (forward) {
         launch_one(c, p, 3);
@@ -538,7 +552,7 @@ void launch_super_round(sla_ctx* c, const Params& p, bool forward, bool zero_fir
 }
 
 int kernels_per_super_round(const sla_ctx* c, bool forward, bool tail_only) {
-    return (forward ? 5 : (khosla_phases(c) ? 4 : 3)) - (tail_only ? 2 : 0);
+    return (forward ? 5 : (khosla_phases(c) ? 4 : 3)) - (tail_only ? 2 : 0) + (use_mid(c) ? 1 : 0);
 }
 
 // Plain Khosla rounds (no eps-schedule) finish in a handful of rounds whose first one has all N bidders: when N is
@@ -546,9 +560,17 @@ int kernels_per_super_round(const sla_ctx* c, bool forward, bool tail_only) {
 // the whole GPU -- the tail engine takes over from round 2 (a few per cent of N).  "wide_first" = 0 turns this off.
 constexpr uint32_t kWideFirstMinRows = 640;
 uint32_t solve_tail_max(const sla_ctx* c, bool forward) {
+    if (use_mid(c)) return kMidMax;   // the grid-wide pair stops here; (solve_own_max, kMidMax] is the cluster engine's
     if (!forward && !khosla_phases(c) && c->opt_wide_first && c->n_rows > kWideFirstMinRows && c->n_rows <= c->tail_max_eff)
         return c->n_rows / 2u;
     return c->tail_max_eff;
+}
+
+// DevState::tail_own_max: what the single-CTA engine takes
+uint32_t solve_own_max(const sla_ctx* c, bool forward) {
+    if (!use_mid(c)) return solve_tail_max(c, forward);
+    const uint32_t h = (uint32_t)c->opt_cluster_handover;
+    return h < c->tail_max_eff ? h : c->tail_max_eff;
 }
 
 bool is_tail_only(const sla_ctx* c, bool forward) { return c->n_rows <= solve_tail_max(c, forward); }
@@ -660,7 +682,7 @@ uint32_t learned_shape(const sla_ctx* c, bool forward, bool first_graph) {
 
 int graph_kernel_count(const sla_ctx* c, bool forward, bool first_graph, bool late_init) {
     const uint32_t lw = learned_shape(c, forward, first_graph);
-    int n = lw ? (int)(2u * lw + 1u)
+    int n = lw ? (int)(2u * lw + 1u + (use_mid(c) ? 1u : 0u))
                : super_rounds_for(c, forward) * kernels_per_super_round(c, forward, is_tail_only(c, forward));
     if (late_init && first_graph) n += 1;   // first_assign_objects_kernel sits in the first graph
     return n;
@@ -675,7 +697,8 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, bool first_graph, cud
     if (g.exec && g.generation == ctx->generation && g.lpr == ctx->lpr && g.super_rounds == n_super && g.learned_wide == lw &&
         g.regular_k == reg_key && g.smem_prices == ctx->tail_smem_prices && g.tail_only == tail_only &&
         g.tail_smem_bytes == ctx->tail_smem_bytes && g.tail_max == solve_tail_max(ctx, forward) && g.khosla_phases == khosla_phases(ctx) &&
-        g.l2_bytes == ctx->l2_bytes && g.vals16 == narrow_scan_ptr(ctx) && g.zero_first == zero_first) {
+        g.l2_bytes == ctx->l2_bytes && g.vals16 == narrow_scan_ptr(ctx) && g.zero_first == zero_first &&
+        g.own_max == solve_own_max(ctx, forward)) {
         *out = g.exec;
         return SLA_OK;
     }
@@ -690,6 +713,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, bool first_graph, cud
             if (zf) first_assign_objects_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(p);
             launch_one(ctx, p, 1, zf);
         }
+        if (use_mid(ctx)) launch_one(ctx, p, 5);
         launch_one(ctx, p, 2);
     } else {
         for (int r = 0; r < n_super; ++r) launch_super_round(ctx, p, forward, zero_first && r == 0, tail_only);
@@ -715,6 +739,7 @@ int get_graph(sla_ctx* ctx, bool forward, bool zero_first, bool first_graph, cud
     g.l2_bytes = ctx->l2_bytes;
     g.vals16 = narrow_scan_ptr(ctx);
     g.learned_wide = lw;
+    g.own_max = solve_own_max(ctx, forward);
     g.zero_first = zero_first;
     *out = g.exec;
     return SLA_OK;
@@ -818,6 +843,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
     s.algo = forward ? ALGO_FORWARD : ALGO_KHOSLA;
     s.pbits = person_bits(N);
     s.tail_max = solve_tail_max(ctx, forward);
+    s.tail_own_max = solve_own_max(ctx, forward);
     s.own_mode = ctx->tail_own_mode;
     s.tail_cap = ctx->tail_cap;
     s.skip_zero = (uint32_t)ctx->opt_skip_zero;
@@ -997,6 +1023,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
                 }
                 CU(cudaEventRecord(ctx->ev[1], ctx->stream));
             }
+            if (use_mid(ctx)) { launch_one(ctx, p, 5); launches += 1; }
             launch_one(ctx, p, 2);
             launches += 1;
             if (ctx->opt_profile) {
@@ -1065,6 +1092,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
         stats->values_negated = flip ? 1u : 0u;
         stats->wide_rounds = f.wide_rounds;
         stats->tail_rounds = f.tail_rounds;
+        stats->cluster_rounds = f.cluster_rounds;
         stats->kernel_launches = launches;
         stats->graph_launches = graph_launches;
         if (forward) {
@@ -1619,6 +1647,11 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
         plan_tail(ctx);
     } else if (k == "khosla_scaling") {
         ctx->opt_khosla_scaling = value ? 1 : 0;
+    } else if (k == "cluster_engine") {
+        ctx->opt_cluster_engine = value ? 1 : 0;
+    } else if (k == "cluster_handover") {
+        if (value < 1 || value > 512) return fail(ctx, SLA_ERR_INVALID, "cluster_handover must be in [1, 512]");
+        ctx->opt_cluster_handover = (int)value;
     } else if (k == "prune_gather") {
         ctx->opt_prune = value ? 1 : 0;
     } else if (k == "learn_shape") {

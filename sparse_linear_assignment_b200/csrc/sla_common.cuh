@@ -19,6 +19,12 @@ constexpr int kWideThreads = 256;    // block size of the grid-wide kernels
 #endif
 constexpr int kTailThreads = SLA_TAIL_THREADS;   // block size of the tail engine (24 warps: 80 registers per thread)
 constexpr uint32_t kTailSlots = kTailThreads / 32;   // bidders of a "small" round: one warp per slot
+// Cluster engine (mid_kernel): one thread-block cluster runs the rounds whose queue is too long for one CTA without a
+// shared-memory price mirror and too short to be worth two grid-wide launches.
+constexpr int kMidCtas = 8;                                   // portable cluster size
+constexpr int kMidThreads = 1024;
+constexpr uint32_t kMidLocalCap = 1024;                       // bidders one CTA of the cluster holds
+constexpr uint32_t kMidMax = kMidCtas * kMidLocalCap;         // longest queue the cluster engine accepts
 
 enum : uint32_t { ALGO_KHOSLA = 0, ALGO_FORWARD = 1 };
 enum : uint32_t { ACTION_NONE = 0, ACTION_RESET = 1, ACTION_RESET_ALL = 2 };   // RESET: wipe the assignment; RESET_ALL: and the prices
@@ -68,7 +74,11 @@ struct DevState {
     // (keeps counting across solves), 1 = a barrier gave up / 2 = safety limit
     uint32_t mesh_round, mesh_epoch, mesh_error;
     uint32_t mesh_tail;      // the persistent one-block tail engine takes the rounds from here on (short rounds)
-    uint32_t mesh_switch_round, mesh_pad[3];   // round in which mesh_tail was set (graph length of the next solve)
+    uint32_t mesh_switch_round;   // round in which mesh_tail was set (graph length of the next solve)
+    uint32_t tail_own_max;   // bidders at or below which the single-CTA tail engine runs; queues in (tail_own_max, tail_max]
+                             // belong to the cluster engine when there is one (otherwise tail_own_max == tail_max)
+    uint32_t cluster_rounds; // rounds the cluster engine ran (also counted in tail_rounds)
+    uint32_t mesh_pad[1];
     unsigned long long rounds, bids, bid_arcs, wide_rounds, tail_rounds;
     unsigned long long safety_rounds_left;
     unsigned long long dbg[24];  // cycle counters of the tail engine when built with -DSLA_TAIL_TIMING

@@ -7,6 +7,7 @@
 // replayed without host involvement until DevState::done is set.
 #pragma once
 #include <cstddef>
+#include <cooperative_groups.h>
 #include "sla_common.cuh"
 #include "synth.h"
 
@@ -612,7 +613,9 @@ constexpr int kAssignUnroll = SLA_ASSIGN_UNROLL;   // slots per thread whose dep
 // `first` = 1: first round of a solve behind first_assign_objects_kernel -- the objects have already installed their
 // winners (price, owner, cleared word), so a bidder only has to look up whether it is the owner of its object: it
 // records the match or goes back into the queue.  Every person is a bidder in that round, so this pass also is the
-// initialisation of person_to_object.
+// initialisation of person_to_object.  (Tried in round 2: the object pass scattering the winners into person_to_object
+// so that this pass reads two coalesced words per person -- cfg3 unchanged, cfg5 8 % slower: 13 M scattered 4-byte
+// stores into a 64 MB array cost more than 16 M scattered 4-byte loads; gpurun r2x)
 __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params p, const int first) {
     DevState* st = p.st;
     const HotState h = load_hot(st);
@@ -710,7 +713,7 @@ __global__ void __launch_bounds__(kWideThreads) assign_wide_kernel(const Params 
     // Only blocks that had a chunk take a ticket (a block without one has written nothing): same-address atomics cost
     // ~8 ns apiece, which is 5 us for a full grid and nothing for the three working blocks of a short round.
     __shared__ uint32_t s_last;
-    __shared__ DevState s_state;
+    __shared__ __align__(16) DevState s_state;
     const uint32_t working = min((qlen + per - 1u) / per, gridDim.x);
     if (blockIdx.x >= working) return;
     __syncthreads();
@@ -764,7 +767,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
 
     // The whole control block is fetched with one cooperative copy, mutated in shared memory by thread 0 and written
     // back at the end: the tail kernel is the only kernel running on the stream, so it owns the block meanwhile.
-    __shared__ DevState s_state;
+    __shared__ __align__(16) DevState s_state;
     DevState* const gst = p.st;
     DevState* const st = &s_state;
     const int tid = threadIdx.x;
@@ -779,7 +782,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
         // has been consumed
         if (st->wide_ctl_done) st->wide_ctl_done = 0u; else st->action = ACTION_NONE;
         const uint32_t qlen0 = st->qlen[st->cur];
-        const uint32_t run = (!st->done && qlen0 > 0 && qlen0 <= st->tail_max) ? 1u : 0u;
+        const uint32_t run = (!st->done && qlen0 > 0 && qlen0 <= st->tail_own_max) ? 1u : 0u;
         s_ctl[0] = run;
         s_ctl[1] = qlen0;
         s_arcs = 0;
@@ -1167,6 +1170,218 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_kernel(const Params p) {
     __syncthreads();
     if (tid < kStateWords) reinterpret_cast<uint4*>(gst)[tid] = reinterpret_cast<const uint4*>(st)[tid];
 #undef TK
+}
+
+// =============================================================================================================
+// Cluster engine: ONE thread-block cluster of kMidCtas CTAs runs whole Jacobi rounds while the queue holds between
+// DevState::tail_own_max and DevState::tail_max (<= kMidMax) bidders.  It exists for instances whose prices do not fit
+// the tail engine's shared memory (large M): there a round of a few thousand bidders costs two grid-wide launches
+// (~14 us in the solve graph, almost all of it launch and drain) or, in the single CTA, several serial passes of
+// dependent global loads (~5 us).  Here the queue is SPLIT over the CTAs and never leaves their shared memory:
+//   bid      every CTA scans the rows of its own bidders (prices past the L1, they change between the rounds of this
+//            launch) and posts the packed bid words with atomicMax into the same global words the wide kernels use;
+//   barrier  cluster-wide (release / acquire);
+//   resolve  one thread per local slot compares its word with the winner's; winners install price / owner / assignment
+//            and clear the word; the loser itself or the evicted owner goes into the CTA's OWN next queue (a slot yields
+//            at most one entry, so a local queue never grows); the local lengths are exchanged through distributed
+//            shared memory;
+//   barrier  cluster-wide; every CTA now knows the total and takes the same decision.
+// No global queue, no global counter, no host: two cluster barriers (~0.2 us each) per round.  A Jacobi round does not
+// depend on the order or the placement of its bidders, so the results equal those of the other engines bit for bit.
+// The engine hands back when the queue is short enough for the single-CTA engine (its slot-stable rounds cost ~1 us),
+// empty, or a limit is reached; the local queues are then concatenated into the global queue buffer.
+// =============================================================================================================
+template <int LPR>
+__global__ void __cluster_dims__(kMidCtas, 1, 1) __launch_bounds__(kMidThreads, 1) mid_kernel(const Params p) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ uint32_t s_queue[2][kMidLocalCap];
+    __shared__ uint32_t s_obj[kMidLocalCap];
+    __shared__ __align__(8) double s_bid[kMidLocalCap];
+    __shared__ uint32_t s_counts[2][kMidCtas];          // by round parity: next-queue length of every CTA of the cluster
+    __shared__ unsigned long long s_arcs_all[kMidCtas]; // rank 0's copy is the one that is read
+    __shared__ uint32_t s_dropped_all[kMidCtas];
+    __shared__ uint32_t s_len;
+    __shared__ unsigned long long s_arcs;
+    __shared__ uint32_t s_dropped;
+    __shared__ __align__(16) DevState s_state;
+
+    DevState* const gst = p.st;
+    const HotState h = load_hot(gst);
+    const uint32_t cur = h.cur & 1u;
+    const uint32_t qlen0 = h.qlen[cur];
+    const uint32_t own_max = gst->tail_own_max;
+    // the same values in every CTA: either the whole cluster leaves here or none of it
+    if (h.done || qlen0 <= own_max || qlen0 > h.tail_max || qlen0 > kMidMax) return;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
+    constexpr int G = kMidThreads / LPR;               // bidders one CTA scans per pass
+    const int lane = tid % LPR;
+    const uint32_t group = tid / LPR;
+    const uint32_t rank = cluster.block_rank();
+    const bool identity = h.identity != 0;
+    const uint32_t algo = h.algo, pbits = h.pbits, sign_flip = h.sign_flip, regK = h.regular_k;
+    const double eps = h.eps, thr = h.threshold;
+    const uint32_t max_it = gst->max_iterations, round_cap = gst->tail_round_cap;
+    uint32_t nits = gst->nits;
+    unsigned long long safety = gst->safety_rounds_left;
+    uint32_t* const gqueue = cur ? p.queue[1] : p.queue[0];
+
+    // contiguous share of the global queue
+    const uint32_t share = (qlen0 + kMidCtas - 1u) / kMidCtas;
+    const uint32_t begin = rank * share < qlen0 ? rank * share : qlen0;
+    uint32_t n = (begin + share < qlen0 ? begin + share : qlen0) - begin;
+    for (uint32_t l = tid; l < n; l += kMidThreads) s_queue[0][l] = identity ? begin + l : __ldcg(gqueue + begin + l);
+    if (tid == 0) { s_arcs = 0ull; s_dropped = 0u; s_len = 0u; }
+    __syncthreads();
+
+    uint32_t total = qlen0, buf = 0u;
+    unsigned long long rounds_done = 0ull, bids_done = 0ull, my_arcs = 0ull;
+    uint32_t my_dropped = 0u;
+    bool hit_limit = false;
+    while (true) {
+        // ---- bid: one group of LPR lanes per local bidder ----
+        const uint32_t* sq = s_queue[buf];
+        for (uint32_t base = 0; base < n; base += G) {
+            if (base + (uint32_t)(warp * 32) / LPR >= n) break;   // warp-uniform: the full-mask shuffles stay legal
+            const uint32_t q = base + group;
+            const bool valid = q < n;
+            uint32_t i = 0, a = 0, b = 0;
+            if (valid) {
+                i = sq[q];
+                if (regK) { a = i * regK; b = a + regK; }
+                else { a = __ldg(p.row_ptr + i); b = __ldg(p.row_ptr + i + 1); }
+            }
+            Choice c;
+            choice_init(c);
+            scan_row<LPR, PRICE_CG, false>(c, p.cols, p.vals, p.prices, a, b, sign_flip, lane);
+            choice_group_reduce<LPR>(c);
+            if (valid && lane == 0) {
+                const Bid r = make_bid<PRICE_CG>(c, algo, eps, thr, p.prices);
+                my_arcs += (unsigned long long)(b - a);
+                if (r.dropped) {
+                    s_obj[q] = SLA_DEV_NONE;
+                    my_dropped += 1u;
+                } else {
+                    s_obj[q] = r.obj;
+                    s_bid[q] = r.bid;
+                    if (r.bid == r.bid) atomicMax(p.best + r.obj, pack_bid(r.bid, i, pbits));   // NaN never bids
+                }
+            }
+        }
+        cluster.sync();                                   // every bid word of the round is in the L2
+
+        // ---- resolve: one thread per local slot ----
+        uint32_t* nq = s_queue[buf ^ 1u];
+        for (uint32_t base = 0; base < n; base += kMidThreads) {
+            const uint32_t q = base + tid;
+            uint32_t emit = SLA_DEV_NONE;
+            if (q < n) {
+                const uint32_t j = s_obj[q];
+                if (j != SLA_DEV_NONE) {
+                    const uint32_t i = sq[q];
+                    const double bid = s_bid[q];
+                    const unsigned long long word = __ldcg(p.best + j);
+                    const uint32_t prev = __ldcg(p.o2p + j);      // only the winner uses it (nobody else writes it this round)
+                    const bool won = (bid == bid) && (word == pack_bid(bid, i, pbits));
+                    if (won) {
+                        p.prices[j] = bid;
+                        p.o2p[j] = i;
+                        p.p2o[i] = j;
+                        p.best[j] = 0ull;                         // a loser that reads 0 instead of the winning word has lost all the same
+                        if (prev != SLA_DEV_NONE) {
+                            p.p2o[prev] = SLA_DEV_NONE;
+                            emit = prev;
+                            if (regK && regK <= 64u) {            // the evicted owner bids next round: pull its row towards the L2
+                                const char* rc = reinterpret_cast<const char*>(p.cols + (size_t)prev * regK);
+                                const char* rv = reinterpret_cast<const char*>(p.vals + (size_t)prev * regK);
+                                for (uint32_t off = 0; off < regK * 4u; off += 128u) asm volatile("prefetch.global.L2 [%0];" :: "l"(rc + off));
+                                for (uint32_t off = 0; off < regK * 8u; off += 128u) asm volatile("prefetch.global.L2 [%0];" :: "l"(rv + off));
+                            }
+                        }
+                    } else {
+                        emit = i;
+                    }
+                }
+            }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, emit != SLA_DEV_NONE);
+            if (ballot) {
+                uint32_t wbase = 0;
+                if (lane32 == 0) wbase = atomicAdd(&s_len, (uint32_t)__popc(ballot));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (emit != SLA_DEV_NONE) nq[wbase + __popc(ballot & ((1u << lane32) - 1u))] = emit;
+            }
+        }
+        __syncthreads();
+        const uint32_t n_next = s_len;
+        const uint32_t par = (uint32_t)(rounds_done & 1ull);
+        if (tid < kMidCtas) *cluster.map_shared_rank(&s_counts[par][rank], tid) = n_next;   // my length, into every CTA
+        cluster.sync();                                   // prices / owners / cleared words / lengths of the round are visible
+        uint32_t total_next = 0;
+#pragma unroll
+        for (int r = 0; r < kMidCtas; ++r) total_next += s_counts[par][r];
+        if (tid == 0) s_len = 0u;                         // next use is behind the next round's first barrier
+
+        bids_done += total;
+        rounds_done += 1ull;
+        total = total_next;
+        n = n_next;
+        buf ^= 1u;
+        if (algo == ALGO_FORWARD) nits += 1u;
+        if (total == 0u) break;
+        if (algo == ALGO_FORWARD && nits >= max_it) { hit_limit = true; break; }   // symmetric.rs:326-328
+        if (safety <= 1ull) { hit_limit = true; break; }
+        safety -= 1ull;
+        if (total <= own_max) break;                      // short enough for the single-CTA engine
+        if (rounds_done >= round_cap) break;              // hand control back; the next super-round continues
+    }
+
+    // ---- hand the queue back: local queues concatenated in rank order ----
+    const uint32_t lpar = (uint32_t)((rounds_done - 1ull) & 1ull);
+    uint32_t off = 0;
+#pragma unroll
+    for (int r = 0; r < kMidCtas; ++r) off += ((uint32_t)r < rank) ? s_counts[lpar][r] : 0u;
+    for (uint32_t l = tid; l < n; l += kMidThreads) gqueue[off + l] = s_queue[buf][l];
+    if (my_arcs) atomicAdd(&s_arcs, my_arcs);
+    if (my_dropped) atomicAdd(&s_dropped, my_dropped);
+    __syncthreads();
+    if (tid == 0) {
+        *cluster.map_shared_rank(&s_arcs_all[rank], 0) = s_arcs;
+        *cluster.map_shared_rank(&s_dropped_all[rank], 0) = s_dropped;
+    }
+    cluster.sync();
+    if (rank != 0u) return;
+
+    // ---- rank 0: the control block, fetched past the L1 in one go, updated in shared memory, stored back ----
+    constexpr int kCtlWords = (int)(offsetof(DevState, dbg) / 16);
+    if (tid < kCtlWords) reinterpret_cast<uint4*>(&s_state)[tid] = __ldcg(reinterpret_cast<const uint4*>(gst) + tid);
+    __syncthreads();
+    if (tid == 0) {
+        DevState* const st = &s_state;
+        unsigned long long arcs = 0ull;
+        uint32_t dropped = 0u;
+        for (int r = 0; r < kMidCtas; ++r) { arcs += s_arcs_all[r]; dropped += s_dropped_all[r]; }
+        // control step A of a wide round of this super-round may have left a phase action for the phase kernel: it stays
+        // (the queue was not empty then, so there is none in practice); an older one has been consumed.  The tail engine
+        // that follows keeps whatever this engine decides (wide_ctl_done).
+        if (!st->wide_ctl_done) st->action = ACTION_NONE;
+        st->wide_ctl_done = 1u;
+        st->rounds += rounds_done;
+        st->tail_rounds += rounds_done;
+        st->cluster_rounds += (uint32_t)rounds_done;
+        st->bids += bids_done;
+        st->bid_arcs += arcs;
+        st->dropped += dropped;
+        st->qlen[cur] = total;
+        st->identity = 0u;
+        st->zero_prices = 0u;
+        st->nits = nits;
+        st->safety_rounds_left = safety;
+        if (hit_limit) st->done = 1u;
+        else if (total == 0u) finish_if_possible(st);
+    }
+    __syncthreads();
+    if (tid < kCtlWords) reinterpret_cast<uint4*>(gst)[tid] = reinterpret_cast<const uint4*>(&s_state)[tid];
 }
 
 // =============================================================================================================

@@ -827,6 +827,49 @@ def test_bound_pruned_gather_changes_nothing(sla, oracle):
         assert_equals_model(oracle, "khosla", solver, z, n, m, rp, c, v.copy(), khosla_scaling=False)
 
 
+def test_cluster_engine_changes_nothing(sla, oracle):
+    """Instances whose prices do not fit one CTA's shared memory run their queues of 25 .. 8,192 bidders in the cluster
+    engine (one thread-block cluster, queue split over its CTAs' shared memory).  Option cluster_engine = 0 leaves those
+    rounds to the grid-wide pair and the single-CTA engine.  Identical bits either way and equal to the model: uniform
+    and ragged rows, both solvers, both signs, eps phases with resets (square Khosla, Forward), the engine as the first
+    one of a solve (small N, smem_prices = 0), other hand-over points."""
+    rng = np.random.default_rng(11)
+    cases = []
+    rp, c, v = sla.generators.kregular_host(150_000, 600_000, 16, seed=5)
+    cases.append(("khosla", "KhoslaSolver", 150_000, 600_000, rp, c, v, False, None, dict(khosla_scaling=0), {}))
+    cases.append(("khosla", "KhoslaSolver", 150_000, 600_000, rp, c, v + 0.5, True, None, dict(khosla_scaling=0), {}))
+    rp, c, v = ragged_instance(rng, 6_000, 40_000, 2, 24, True)
+    cases.append(("khosla", "KhoslaSolver", 6_000, 40_000, rp, c, v, False, 1.0 / 40_001, dict(khosla_scaling=0), {}))
+    rp, c, v = sla.generators.kregular_host(36_000, 36_000, 16, seed=6, planted=True)
+    cases.append(("khosla", "KhoslaSolver", 36_000, 36_000, rp, c, v, False, 1.0 / 36_001, {}, {}))          # eps-schedule
+    cases.append(("forward", "ForwardAuctionSolver", 36_000, 36_000, rp, c, v, True, 1.0 / 36_001, {}, {}))
+    rp, c, v = random_sparse_instance(rng, 3000, 5000, 16, integer=True, lo=0, hi=200)
+    cases.append(("khosla", "KhoslaSolver", 3000, 5000, rp, c, v, False, 1.0 / 5001, dict(smem_prices=0, khosla_scaling=0),
+                  dict(khosla_scaling=False)))
+    rp, c, v = random_sparse_instance(rng, 3000, 3000, 16, integer=True, lo=0, hi=200)
+    cases.append(("forward", "ForwardAuctionSolver", 3000, 3000, rp, c, v, False, 1.0 / 3001, dict(smem_prices=0), {}))
+    for kind, cls_name, n, m, rp, c, v, maximize, eps, opts, model_kw in cases:
+        if "khosla_scaling" in opts and kind == "khosla":
+            model_kw = dict(khosla_scaling=False)
+        out = []
+        for extra in (dict(cluster_engine=1), dict(cluster_engine=0), dict(cluster_engine=1, cluster_handover=1),
+                      dict(cluster_engine=1, cluster_handover=300)):
+            solver, z = gpu_solve(sla, cls_name, n, m, rp, c, v.copy(), maximize=maximize, eps=eps,
+                                  options=dict(opts, timeout_s=600, **extra))
+            st = solver.last_stats
+            assert st["wide_rounds"] + st["tail_rounds"] == st["rounds"] and st["cluster_rounds"] <= st["tail_rounds"]
+            assert (st["cluster_rounds"] > 0) == bool(extra["cluster_engine"]), (kind, n, m, extra, st)
+            out.append((z.person_to_object.copy(), z.object_to_person.copy(), solver.prices().copy(),
+                        {q: st[q] for q in ("rounds", "bids", "bid_arcs", "num_unassigned", "dropped", "nits", "nreductions",
+                                            "optimal_soln_found", "eps")}))
+            if extra == dict(cluster_engine=1):
+                assert_equals_model(oracle, kind, solver, z, n, m, rp, c, v.copy(), maximize=maximize, eps=eps, **model_kw)
+        for other in out[1:]:
+            for x, y in zip(out[0][:3], other[:3]):
+                assert np.array_equal(x, y)
+            assert out[0][3] == other[3]
+
+
 def test_resident_repeat_solves_learn_the_graph_shape(sla, oracle):
     """Repeated plain-Khosla solves of a resident CSR capture their first graph as (wide rounds of the previous solve) x
     (bid, assign) + one tail launch; results and counters stay identical, launches go down, and a solve whose round count
