@@ -282,6 +282,7 @@ struct sla_ctx {
 
     // problem
     bool has_csr = false, has_solution = false, best_dirty = true;
+    bool l2_attr_set = false;  // the stream carries a persisting access-policy window (apply_l2_policy)
     uint32_t n_rows = 0, n_cols = 0;
     uint64_t nnz = 0;
     double v_min = 0, v_max = 0, first_value = 0;
@@ -641,9 +642,12 @@ void apply_l2_policy(sla_ctx* c) {
         }
         if (cur < v.accessPolicyWindow.num_bytes) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, v.accessPolicyWindow.num_bytes);
         c->l2_bytes = v.accessPolicyWindow.num_bytes;
+        c->l2_attr_set = true;
     } else {
         release_l2_policy(c);
         c->l2_bytes = 0;
+        if (!c->l2_attr_set) return;     // the stream never had a window: nothing to take back (every small upload comes through here)
+        c->l2_attr_set = false;
         v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
         v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     }
@@ -1278,11 +1282,41 @@ int upload_small(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
         irr |= (b - a != k0) ? 1u : 0u;
     }
     if (bad_r) return fail(ctx, SLA_ERR_INVALID, "row extents are not monotone");
-    // columns, values: one vectorised pass each (copy + bound check, copy + range [+ in-place negation])
-    if (stage_cols(column_indices, s_cols, nnz, num_cols)) return fail(ctx, SLA_ERR_INVALID, "column index out of range (>= num_cols)");
+    // Columns, values: one vectorised pass each (copy + bound check, copy + range [+ in-place negation]).  Every piece
+    // goes onto the wire as soon as it is staged, so that the DMA engine works while the host stages the next one: the
+    // upload ends one piece's transfer after the last pass instead of the whole block's (the values travel in two
+    // pieces from 128 KB up).  Once a copy is in flight the staging block is guarded by ev_small, also on the error paths.
+    auto in_flight = [&]() {
+        cudaEventRecord(ctx->ev_small, ctx->stream);
+        ctx->small_pending = true;
+    };
+    CU(cudaMemcpyAsync(ctx->d_row_ptr, s_rp, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (stage_cols(column_indices, s_cols, nnz, num_cols)) {
+        in_flight();
+        return fail(ctx, SLA_ERR_INVALID, "column index out of range (>= num_cols)");
+    }
+    {
+        const cudaError_t e = cudaMemcpyAsync(ctx->d_cols, s_cols, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { in_flight(); CU(e); }
+    }
     const double first = values[0];
-    double vmin, vmax;
-    if (stage_values(values, s_vals, nnz, negate_host, &vmin, &vmax)) {
+    double vmin = 0.0, vmax = 0.0;
+    bool special = false;
+    {
+        constexpr uint64_t kPieceMin = (uint64_t)16 << 10;      // values (128 KB): below twice this, one piece
+        const uint64_t half = nnz >= 2 * kPieceMin ? ((nnz / 2 + 3) & ~(uint64_t)3) : nnz;
+        for (uint64_t lo = 0; lo < nnz; lo += half) {
+            const uint64_t cnt = (lo + half < nnz) ? half : nnz - lo;
+            double mn, mx;
+            special |= stage_values(values + lo, s_vals + lo, cnt, negate_host, &mn, &mx);
+            if (lo == 0) { vmin = mn; vmax = mx; }
+            else { vmin = mn < vmin ? mn : vmin; vmax = mx > vmax ? mx : vmax; }
+            const cudaError_t e = cudaMemcpyAsync(ctx->d_vals + lo, s_vals + lo, (size_t)cnt * 8, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) { in_flight(); CU(e); }
+        }
+    }
+    in_flight();
+    if (special) {
         // zeros or NaNs present: the range in csr_stats_kernel's total order (-0.0 < +0.0, NaNs at the ends), from the
         // staged copy of the original values
         unsigned long long kmin = ~0ull, kmax = 0ull;
@@ -1296,11 +1330,6 @@ int upload_small(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
         vmin = order_key_to_f64_host(kmin);
         vmax = order_key_to_f64_host(kmax);
     }
-    CU(cudaMemcpyAsync(ctx->d_row_ptr, s_rp, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_cols, s_cols, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_vals, s_vals, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaEventRecord(ctx->ev_small, ctx->stream));
-    ctx->small_pending = true;
     ctx->n_rows = num_rows;
     ctx->n_cols = num_cols;
     ctx->nnz = nnz;

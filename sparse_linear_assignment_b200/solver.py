@@ -28,18 +28,34 @@ from ._lib import SlaError, SlaStats
 __all__ = ["AuctionSolution", "AuctionSolver", "KhoslaSolver", "ForwardAuctionSolver", "SlaError"]
 
 
+_U32 = np.dtype(np.uint32)
+
+
 def _imax(dtype) -> int:
     return int(np.iinfo(dtype).max)
 
 
+_host_threads_cache = {}
+
+
 def host_threads() -> int:
     """Host threads one solver may use for the in-place negation: the cores of the box divided by the number of
-    co-located ranks (torchrun exports LOCAL_WORLD_SIZE), at most 16."""
+    co-located ranks (torchrun exports LOCAL_WORLD_SIZE), at most 16.  Evaluated once per value of the two environment
+    variables: os.cpu_count() and the environment look-ups cost 15 us, half of the Python time of a small solve."""
+    env = os.environ._data if hasattr(os.environ, "_data") else None
+    key = (env.get(b"SLA_HOST_THREADS"), env.get(b"LOCAL_WORLD_SIZE")) if env is not None else \
+        (os.environ.get("SLA_HOST_THREADS"), os.environ.get("LOCAL_WORLD_SIZE"))
+    hit = _host_threads_cache.get(key)
+    if hit is not None:
+        return hit
     if os.environ.get("SLA_HOST_THREADS"):
-        return max(1, min(16, int(os.environ["SLA_HOST_THREADS"])))
-    cores = os.cpu_count() or 1
-    local_world = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1), 1)
-    return max(1, min(16, cores // local_world))
+        out = max(1, min(16, int(os.environ["SLA_HOST_THREADS"])))
+    else:
+        cores = os.cpu_count() or 1
+        local_world = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1), 1)
+        out = max(1, min(16, cores // local_world))
+    _host_threads_cache[key] = out
+    return out
 
 
 _PIN_MIN_BYTES = 1 << 16
@@ -73,6 +89,15 @@ class _Vec:
     def __init__(self, dtype, capacity: int = 0):
         self.a = host_array(max(int(capacity), 1), dtype)
         self.len = 0
+
+    @property
+    def a(self) -> np.ndarray:
+        return self._a
+
+    @a.setter
+    def a(self, arr: np.ndarray):
+        self._a = arr
+        self.addr = arr.ctypes.data     # base address for the C ABI, taken once per (re)allocation: ndarray.ctypes costs ~1.5 us
 
     def reserve(self, n: int):
         if n > self.a.size:
@@ -161,11 +186,24 @@ class AuctionSolver:
         self._column_indices = _Vec(self.index_dtype, arcs_capacity)
         self._values = _Vec(np.float64, arcs_capacity)
         self.nits = 0
-        self.last_stats: Optional[dict] = None
+        self._last_stats: Optional[dict] = None
+        self._last_struct: Optional[SlaStats] = None
+        self._out_cache = None      # (person_to_object, object_to_person, their base addresses) of the last solve
         self._ctx = None
         self._dirty = True
         self._device_only = False   # CSR was generated in HBM (generators.kregular_device): no host copy exists
         self._prices_on_device = False
+
+    @property
+    def last_stats(self) -> Optional[dict]:
+        """sla_stats of the last solve as a dict (built on first access: 7 us that a small solve need not pay)."""
+        if self._last_stats is None and self._last_struct is not None:
+            self._last_stats = self._last_struct.as_dict()
+        return self._last_stats
+
+    @last_stats.setter
+    def last_stats(self, value: Optional[dict]):
+        self._last_stats, self._last_struct = value, None
 
     # ---- construction ------------------------------------------------------------------------------------
     @classmethod
@@ -427,19 +465,24 @@ class AuctionSolver:
         ctx = self._context()
         if self._dirty:
             n, nnz = self._num_rows, self.num_of_arcs()
-            row_ptr = np.ascontiguousarray(self._i_starts_stops.view[: n + 1], dtype=np.uint32)
-            cols = np.ascontiguousarray(self._column_indices.view, dtype=np.uint32)
-            vals = self._values.view
-            _ensure(row_ptr.size == n + 1, "fewer rows populated than num_rows")
-            flip = maximize is not None and (bool(maximize) ^ bool((vals[0] if vals.size else 0.0) >= 0.0))
+            _ensure(self._i_starts_stops.len >= n + 1, "fewer rows populated than num_rows")
+            if self.index_dtype == _U32:        # the host vectors are what the C ABI reads: no copies, cached addresses
+                row_ptr = cols = None
+                rp_addr, cols_addr = self._i_starts_stops.addr, self._column_indices.addr
+            else:                               # u16 indices are widened for the device (kept alive until the call returns)
+                row_ptr = np.ascontiguousarray(self._i_starts_stops.view[: n + 1], dtype=np.uint32)
+                cols = np.ascontiguousarray(self._column_indices.view, dtype=np.uint32)
+                rp_addr, cols_addr = row_ptr.ctypes.data, cols.ctypes.data
+            vals_addr = self._values.addr
+            flip = maximize is not None and (bool(maximize) ^ bool((self._values.a[0] if nnz else 0.0) >= 0.0))
             # any size: small instances are negated in the library's single staging pass, large ones by its worker pool
             self._pre_negated = bool(flip)
             if self._pre_negated:
-                rc = _lib.load().sla_upload_csr_negating(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
-                                                         vals.ctypes.data, nnz, host_threads())
+                rc = _lib.load().sla_upload_csr_negating(ctx, n, self._num_cols, rp_addr, cols_addr, vals_addr, nnz,
+                                                         host_threads())
             else:
-                rc = _lib.load().sla_upload_csr(ctx, n, self._num_cols, row_ptr.ctypes.data, cols.ctypes.data,
-                                                vals.ctypes.data, nnz)
+                rc = _lib.load().sla_upload_csr(ctx, n, self._num_cols, rp_addr, cols_addr, vals_addr, nnz)
+            del row_ptr, cols
             _lib.check(ctx, rc)
             self._dirty = False
         return ctx
@@ -459,7 +502,7 @@ class AuctionSolver:
             return None, False
         lib = _lib.load()
         if vals.size < (1 << 16):      # too small to be worth a helper thread: negate right here
-            lib.sla_host_negate_f64(vals.ctypes.data, vals.size, 1)
+            lib.sla_host_negate_f64(self._values.addr, vals.size, 1)
             return None, True
         th = threading.Thread(target=lib.sla_host_negate_f64,
                               args=(vals.ctypes.data, vals.size, host_threads()))
@@ -492,11 +535,18 @@ class AuctionSolver:
         solution.num_unassigned = int(stats.num_unassigned)
         solution.eps = float(stats.eps)
         self.nits = int(stats.nits)
-        self.last_stats = stats.as_dict()
+        self._last_stats, self._last_struct = None, stats
 
     def _outputs(self, solution: AuctionSolution):
-        """Output buffers: the caller's solution vectors are reused when they already have the right shape (the
-        reference resizes the caller's Vecs in place, solver.rs:221-228); prices stay in HBM until asked for."""
+        """Output buffers and their base addresses: the caller's solution vectors are reused when they already have the
+        right shape (the reference resizes the caller's Vecs in place, solver.rs:221-228); prices stay in HBM until asked
+        for.  The vectors a previous solve of this solver handed out are recognised by identity (the cache holds a
+        reference, so numpy refuses to resize them in place)."""
+        oc = self._out_cache
+        if oc is not None and solution.person_to_object is oc[0] and solution.object_to_person is oc[1] \
+                and oc[0].size == self._num_rows and oc[1].size == self._num_cols:
+            return oc
+
         def fit(arr, n):
             if isinstance(arr, np.ndarray) and arr.dtype == np.uint32 and arr.size == n and arr.flags.c_contiguous \
                     and arr.flags.writeable:
@@ -504,7 +554,8 @@ class AuctionSolver:
             return host_array(n, np.uint32)
         p2o = fit(solution.person_to_object, self._num_rows)
         o2p = fit(solution.object_to_person, self._num_cols)
-        return p2o, o2p
+        self._out_cache = (p2o, o2p, p2o.ctypes.data, o2p.ctypes.data)
+        return self._out_cache
 
     def device_objective(self) -> float:
         """sla_get_objective on the resident solution (exact for integer-valued weights)."""
@@ -565,8 +616,8 @@ class AuctionSolver:
 
     def download_solution(self, solution: AuctionSolution) -> None:
         ctx = self._context()
-        p2o, o2p = self._outputs(solution)
-        _lib.check(ctx, _lib.load().sla_download_solution(ctx, p2o.ctypes.data, o2p.ctypes.data, None))
+        p2o, o2p, p2o_addr, o2p_addr = self._outputs(solution)
+        _lib.check(ctx, _lib.load().sla_download_solution(ctx, p2o_addr, o2p_addr, None))
         st = SlaStats(**{k: v for k, v in (self.last_stats or {}).items()})
         self._finish(solution, st, p2o, o2p)
 
@@ -579,11 +630,11 @@ class KhoslaSolver(AuctionSolver):
         if not self._device_only:
             self.validate_input()
         ctx = self._sync_device(maximize)
-        p2o, o2p = self._outputs(solution)
+        p2o, o2p, p2o_addr, o2p_addr = self._outputs(solution)
         st = SlaStats()
         neg = self._begin_negation(maximize)
         rc = _lib.load().sla_khosla_solve(ctx, int(bool(maximize)), float("nan") if eps is None else float(eps),
-                                          p2o.ctypes.data, o2p.ctypes.data, None, C.byref(st))
+                                          p2o_addr, o2p_addr, None, C.byref(st))
         if neg[0] is not None:
             neg[0].join()
         self._check_solve(ctx, rc)
@@ -613,7 +664,7 @@ class ForwardAuctionSolver(AuctionSolver):
         if not self._device_only:
             self.validate_input()
         ctx = self._sync_device(maximize)
-        p2o, o2p = self._outputs(solution)
+        p2o, o2p, p2o_addr, o2p_addr = self._outputs(solution)
         # Some(0) behaves like Some(1) in the reference (the check runs after the first round, symmetric.rs:326)
         self.max_iterations = max(int(max_iterations), 1) if max_iterations is not None else self.MAX_ITERATIONS
         st = SlaStats()
@@ -621,7 +672,7 @@ class ForwardAuctionSolver(AuctionSolver):
         neg = self._begin_negation(maximize)
         rc = _lib.load().sla_forward_solve(ctx, int(bool(maximize)), nan if eps is None else float(eps),
                                            nan if start_eps is None else float(start_eps), self.max_iterations,
-                                           p2o.ctypes.data, o2p.ctypes.data, None, C.byref(st))
+                                           p2o_addr, o2p_addr, None, C.byref(st))
         if neg[0] is not None:
             neg[0].join()
         self._check_solve(ctx, rc)
