@@ -744,7 +744,8 @@ def main_ours(args):
         torch.cuda.synchronize(device)
         t0 = time.perf_counter()
         solver.solve(solution, False, eps)         # includes the in-place sign normalisation of values (solver.rs:214-216)
-        torch.cuda.synchronize(device)
+        # solve() is synchronous: it returns after the library's own cudaStreamSynchronize, with person_to_object /
+        # object_to_person in the caller's host arrays and the negation workers joined -- no second device sync here
         e2e_s += time.perf_counter() - t0
         e2e_arcs += solver.last_stats["bid_arcs"]
     h2d, value_bytes = solver.last_upload()        # bytes the library actually moved: integer costs cross PCIe as u16
