@@ -1239,6 +1239,16 @@ __global__ void __cluster_dims__(kMidCtas, 1, 1) __launch_bounds__(kMidThreads, 
     unsigned long long rounds_done = 0ull, bids_done = 0ull, my_arcs = 0ull;
     uint32_t my_dropped = 0u;
     bool hit_limit = false;
+#ifdef SLA_MID_TIMING
+    // development instrumentation: cycle stamps of thread 0 of cluster rank 0 (in-order issue: a stamp behind an
+    // instruction that consumes loaded data is taken after the data has arrived)
+    long long mt[6] = {0, 0, 0, 0, 0, 0}, mlast, mround;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(mlast) :: "memory");
+    mround = mlast;
+#define MT(i) do { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); mt[i] += t_ - mlast; mlast = t_; } while (0)
+#else
+#define MT(i) do { } while (0)
+#endif
     while (true) {
         // ---- bid: one group of LPR lanes per local bidder ----
         const uint32_t* sq = s_queue[buf];
@@ -1269,7 +1279,9 @@ __global__ void __cluster_dims__(kMidCtas, 1, 1) __launch_bounds__(kMidThreads, 
                 }
             }
         }
+        MT(0);
         cluster.sync();                                   // every bid word of the round is in the L2
+        MT(1);
 
         // ---- resolve: one thread per local slot ----
         uint32_t* nq = s_queue[buf ^ 1u];
@@ -1312,16 +1324,27 @@ __global__ void __cluster_dims__(kMidCtas, 1, 1) __launch_bounds__(kMidThreads, 
                 if (emit != SLA_DEV_NONE) nq[wbase + __popc(ballot & ((1u << lane32) - 1u))] = emit;
             }
         }
+        MT(2);
         __syncthreads();
         const uint32_t n_next = s_len;
         const uint32_t par = (uint32_t)(rounds_done & 1ull);
         if (tid < kMidCtas) *cluster.map_shared_rank(&s_counts[par][rank], tid) = n_next;   // my length, into every CTA
+        MT(3);
         cluster.sync();                                   // prices / owners / cleared words / lengths of the round are visible
+        MT(4);
         uint32_t total_next = 0;
 #pragma unroll
         for (int r = 0; r < kMidCtas; ++r) total_next += s_counts[par][r];
         if (tid == 0) s_len = 0u;                         // next use is behind the next round's first barrier
 
+#ifdef SLA_MID_TIMING
+        if (rank == 0u && tid == 0 && rounds_done < 8ull) {
+            long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory");
+            gst->dbg[8 + 2 * rounds_done] = (unsigned long long)(t_ - mround);       // cycles of this round
+            gst->dbg[9 + 2 * rounds_done] = total;                                     // its bidders
+            mround = t_;
+        }
+#endif
         bids_done += total;
         rounds_done += 1ull;
         total = total_next;
@@ -1336,6 +1359,13 @@ __global__ void __cluster_dims__(kMidCtas, 1, 1) __launch_bounds__(kMidThreads, 
         if (rounds_done >= round_cap) break;              // hand control back; the next super-round continues
     }
 
+#ifdef SLA_MID_TIMING
+    if (rank == 0u && tid == 0) {
+        for (int i = 0; i < 5; ++i) atomicAdd(&gst->dbg[i], (unsigned long long)mt[i]);
+        atomicAdd(&gst->dbg[6], rounds_done);
+    }
+#endif
+#undef MT
     // ---- hand the queue back: local queues concatenated in rank order ----
     const uint32_t lpar = (uint32_t)((rounds_done - 1ull) & 1ull);
     uint32_t off = 0;
