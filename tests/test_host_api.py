@@ -206,3 +206,59 @@ def test_host_narrowing_is_lossless_or_refuses(sla):
             edge[0] = 65535.0
             edge[-1] = 0.0
             run(edge, 2, negate)
+
+
+def test_cached_addresses_follow_reallocation_and_outputs_are_recognised_by_identity(sla, monkeypatch):
+    """The wrapper hands the C ABI cached base addresses (ndarray.ctypes costs more than the rest of a small solve's
+    Python time): they must follow every reallocation of the growable vectors, the solution vectors of the previous
+    solve are reused only while they are the very same arrays of the right size, and the host-thread count follows the
+    environment it was computed from."""
+    from sparse_linear_assignment_b200 import solver as SV
+    v = SV._Vec(np.float64, 4)
+    assert v.addr == v.a.ctypes.data
+    v.extend(np.arange(4.0))
+    first = v.addr
+    v.extend(np.arange(1000.0))                               # grows: new block, new address
+    assert v.addr == v.a.ctypes.data and v.len == 1004 and np.array_equal(v.view[:4], np.arange(4.0))
+    assert v.addr != first or v.a.size >= 1004
+    v.assign(np.arange(5000.0))
+    assert v.addr == v.a.ctypes.data and v.view[-1] == 4999.0
+
+    s, z = sla.KhoslaSolver.new(3, 5, 9)
+    s.init(3, 5)
+    s.extend_from_values(0, [0, 1], [1.0, 2.0])
+    s.extend_from_values(1, [1, 2], [3.0, 4.0])
+    s.extend_from_values(2, [3, 4], [5.0, 6.0])
+    for name in ("_i_starts_stops", "_column_indices", "_values"):
+        vec = getattr(s, name)
+        assert vec.addr == vec.a.ctypes.data
+    p2o, o2p, a1, a2 = s._outputs(z)
+    assert p2o.size == 3 and o2p.size == 5 and a1 == p2o.ctypes.data and a2 == o2p.ctypes.data
+    z.person_to_object, z.object_to_person = p2o, o2p         # what _finish leaves in the caller's solution
+    again = s._outputs(z)
+    assert again[0] is p2o and again[1] is o2p and again[2:] == (a1, a2)
+    z.object_to_person = np.zeros(5, dtype=np.uint32)         # another array of the same shape: taken as it is
+    other = s._outputs(z)
+    assert other[1] is z.object_to_person and other[3] == z.object_to_person.ctypes.data
+    s.init(2, 5)                                              # another shape: fresh vectors
+    s.extend_from_values(0, [0], [1.0])
+    s.extend_from_values(1, [1], [1.0])
+    third = s._outputs(z)
+    assert third[0].size == 2 and third[0] is not p2o
+
+    s.last_stats = {"rounds": 3}
+    assert s.last_stats == {"rounds": 3}
+    st = SV.SlaStats()
+    st.rounds = 7
+    s._last_stats, s._last_struct = None, st                  # what _finish records: the dict is built on first access
+    assert s.last_stats["rounds"] == 7 and s.last_stats is s.last_stats
+
+    monkeypatch.setenv("SLA_HOST_THREADS", "3")
+    assert SV.host_threads() == 3
+    monkeypatch.setenv("SLA_HOST_THREADS", "64")
+    assert SV.host_threads() == 16
+    monkeypatch.delenv("SLA_HOST_THREADS")
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "100000")
+    assert SV.host_threads() == 1
+    monkeypatch.delenv("LOCAL_WORLD_SIZE")
+    assert 1 <= SV.host_threads() <= 16
