@@ -262,6 +262,8 @@ struct sla_ctx {
     unsigned char* h_small = nullptr;     // small instances: one block for the CSR on its way up and the results on their way down
     size_t h_small_cap = 0;
     cudaEvent_t ev_small = nullptr;       // the last H2D copy out of h_small has completed
+    cudaStream_t stream_ride = nullptr;   // u16 uploads: the kernels that ride behind the pieces run here, so that the copies
+    cudaEvent_t ev_ride = nullptr;        // on `stream` stay back to back (created on first use)
     bool small_pending = false;
     // large uploads: values that survive a round trip through u16 / f32 cross PCIe narrow and are widened on the device
     void* h_narrow = nullptr;             // page-locked staging (tier bytes per value)
@@ -300,6 +302,7 @@ struct sla_ctx {
     int opt_stream_scan = 0;   // first-round scan through the TMA pipeline (bid_stream_kernel): opt-in, measured 4 % slower
     int opt_smem_prices = 1, opt_smem_owners = 1, opt_khosla_scaling = 1;
     int opt_prune = 1;         // bound-pruned gather in the uniform-degree scans of rounds with >= 32 Ki bidders
+    int opt_upload_ride = 1;   // u16 uploads: statistics + widening behind every run of pieces instead of two passes at the end
     int opt_cluster_engine = 0; // opt-in ("cluster_engine" = 1; large M, no shared-memory price mirror): queues of kTailSlots+1 ..
                                 // kMidMax bidders run in mid_kernel.  Bit-identical, but measured no faster than the grid-wide pair +
                                 // single-CTA engine it replaces (cfg3 0.181 vs 0.172 ms, cfg5 2.73 vs 2.71 ms: a round is ~7 us of
@@ -817,7 +820,7 @@ int poll_state(sla_ctx* ctx) {
     return SLA_OK;
 }
 
-int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz, bool build_mirror = false);
+int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz, bool build_mirror = false, bool prestats = false);
 
 // The solve driver shared by both algorithms.
 int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double start_eps_in, uint32_t max_iterations,
@@ -1113,13 +1116,24 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
 }
 
 // After the three CSR arrays are resident: statistics + validation (solver.rs:232-243).
-int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz, bool build_mirror) {
+// Resets the statistics block on the device (stream-ordered; the page-locked source is rewritten with the same bytes only).
+int csr_stats_reset(sla_ctx* ctx) {
     DevCsrStats init;
     init.min_key = ~0ull; init.max_key = 0ull; init.bad_cols = 0; init.bad_rows = 0; init.irregular_rows = 0; init.not_u16 = 0;
     *ctx->h_csr_stats = init;
     CU(cudaMemcpyAsync(ctx->d_csr_stats, ctx->h_csr_stats, sizeof(DevCsrStats), cudaMemcpyHostToDevice, ctx->stream));
-    csr_stats_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(ctx->d_row_ptr, ctx->d_cols, ctx->d_vals, num_rows,
-                                                                      num_cols, nnz, ctx->d_csr_stats);
+    return SLA_OK;
+}
+
+// `prestats`: the statistics were accumulated on the way up (u16 uploads: csr_row_stats_kernel + widen_u16_stats_kernel
+// behind the copies); only their read-back is left.
+int finish_csr(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, uint64_t nnz, bool build_mirror, bool prestats) {
+    if (!prestats) {
+        int rc0 = csr_stats_reset(ctx);
+        if (rc0) return rc0;
+        csr_stats_kernel<<<ctx->grid_wide, kWideThreads, 0, ctx->stream>>>(ctx->d_row_ptr, ctx->d_cols, ctx->d_vals, num_rows,
+                                                                          num_cols, nnz, ctx->d_csr_stats);
+    }
     CU(cudaMemcpyAsync(ctx->h_csr_stats, ctx->d_csr_stats, sizeof(DevCsrStats), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(ctx->h_partial, ctx->d_vals, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(ctx->h_scratch, ctx->d_row_ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1418,8 +1432,33 @@ int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
         }
     }
 
-    CU(cudaMemcpyAsync(ctx->d_cols, column_indices, total * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // u16 tier: statistics and widening ride behind the copies (csr_row_stats_kernel behind the extents, one
+    // widen_u16_stats_kernel behind every run of staged pieces), so that the upload ends a few microseconds after the
+    // last piece has landed instead of a widening pass + a statistics pass over the whole CSR later (cfg3: ~0.11 ms)
+    // The kernels run on a second stream, each behind an event of the copy it needs: the link is the second-longest
+    // pole of the upload (100 MB at ~54 GB/s against 1.9 ms of host pass), kernels in between the copies on one stream
+    // cost it 0.1 ms of bubbles.
+    bool ride = tier == 2 && ctx->opt_upload_ride;
+    if (ride && !ctx->stream_ride) {
+        if (cudaStreamCreateWithFlags(&ctx->stream_ride, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_ride, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            if (ctx->stream_ride) { cudaStreamDestroy(ctx->stream_ride); ctx->stream_ride = nullptr; }
+            ride = false;
+        }
+    }
+    auto ride_after_copy = [&]() -> cudaError_t {      // stream_ride continues behind what `stream` holds so far
+        cudaError_t x = cudaEventRecord(ctx->ev_ride, ctx->stream);
+        if (x == cudaSuccess) x = cudaStreamWaitEvent(ctx->stream_ride, ctx->ev_ride, 0);
+        return x;
+    };
+    if (ride) { int rc0 = csr_stats_reset(ctx); if (rc0) return rc0; }
     CU(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, ((size_t)num_rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ride) {
+        CU(ride_after_copy());
+        csr_row_stats_kernel<<<ctx->num_sms * 4, kWideThreads, 0, ctx->stream_ride>>>(ctx->d_row_ptr, num_rows, nnz, ctx->d_csr_stats);
+    }
+    CU(cudaMemcpyAsync(ctx->d_cols, column_indices, total * 4, cudaMemcpyHostToDevice, ctx->stream));
 
     bool narrowed = false;
     if (tier) {
@@ -1454,6 +1493,11 @@ int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
                 const size_t lo = (size_t)sent * piece, end = (size_t)(sent + run) * piece, hi = end < total ? end : total;
                 ce = cudaMemcpyAsync((char*)ctx->d_narrow + lo * tier, (const char*)ctx->h_narrow + lo * tier, (hi - lo) * tier,
                                      cudaMemcpyHostToDevice, ctx->stream);
+                if (ride && ce == cudaSuccess && (ce = ride_after_copy()) == cudaSuccess) {
+                    widen_u16_stats_kernel<<<ctx->num_sms * 8, kWideThreads, 0, ctx->stream_ride>>>(
+                        (const uint16_t*)ctx->d_narrow, ctx->d_vals, ctx->d_cols, lo, hi, num_cols, ctx->d_csr_stats);
+                    ce = cudaGetLastError();
+                }
                 if (dbg && sent == 0) t_first = ms_since();
                 if (dbg && sent < npieces / 2 && sent + run >= npieces / 2) t_half = ms_since();
                 sent += run;
@@ -1465,6 +1509,13 @@ int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
         }
         if (dbg) fprintf(stderr, "[sla] narrow tier %d: first piece sent %.3f ms, half %.3f ms, all %.3f ms\n", tier, t_first, t_half, ms_since());
         np.wait();                                                        // the staging pass is over (or was abandoned)
+        if (ride) {
+            // `stream` continues behind the riding kernels (statistics complete, d_vals written; on abandonment the f64
+            // copies below must not be overtaken by a kernel still widening an earlier run)
+            cudaError_t x = cudaEventRecord(ctx->ev_ride, ctx->stream_ride);
+            if (x == cudaSuccess) x = cudaStreamWaitEvent(ctx->stream, ctx->ev_ride, 0);
+            if (ce == cudaSuccess) ce = x;
+        }
         if (ce != cudaSuccess) return fail(ctx, SLA_ERR_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(ce));
         narrowed = sent == npieces && !np.narrow_fail.load();
         if (!narrowed && negate) {
@@ -1480,7 +1531,8 @@ int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
 
     if (narrowed) {
         const int grid = ctx->num_sms * 8;
-        if (tier == 2) widen_values_kernel<uint16_t><<<grid, kWideThreads, 0, ctx->stream>>>((const uint16_t*)ctx->d_narrow, ctx->d_vals, total);
+        if (ride) { /* widened run by run behind the copies */ }
+        else if (tier == 2) widen_values_kernel<uint16_t><<<grid, kWideThreads, 0, ctx->stream>>>((const uint16_t*)ctx->d_narrow, ctx->d_vals, total);
         else           widen_values_kernel<float><<<grid, kWideThreads, 0, ctx->stream>>>((const float*)ctx->d_narrow, ctx->d_vals, total);
         ctx->last_upload_bytes += total * (size_t)tier;
         ctx->last_upload_value_bytes = (uint32_t)tier;
@@ -1508,7 +1560,7 @@ int upload_large(sla_ctx* ctx, uint32_t num_rows, uint32_t num_cols, const uint3
         ctx->last_upload_bytes += total * 8;
     }
     if (dbg) fprintf(stderr, "[sla] upload enqueued at %.3f ms\n", ms_since());
-    int rc = finish_csr(ctx, num_rows, num_cols, nnz);
+    int rc = finish_csr(ctx, num_rows, num_cols, nnz, false, narrowed && ride);
     if (dbg) fprintf(stderr, "[sla] upload complete (statistics read back) at %.3f ms\n", ms_since());
     if (rc) {
         // rejected (validate_input / column bound): no solve will follow, so the caller's values go back to what they were
@@ -1641,6 +1693,8 @@ void sla_ctx_destroy(sla_ctx* ctx) {
     if (ctx->h_narrow) cudaFreeHost(ctx->h_narrow);
     if (ctx->d_narrow) cudaFree(ctx->d_narrow);
     if (ctx->ev_small) cudaEventDestroy(ctx->ev_small);
+    if (ctx->ev_ride) cudaEventDestroy(ctx->ev_ride);
+    if (ctx->stream_ride) cudaStreamDestroy(ctx->stream_ride);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_csr_stats) cudaFreeHost(ctx->h_csr_stats);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
@@ -1676,6 +1730,8 @@ int sla_set_option(sla_ctx* ctx, const char* key, int64_t value) {
         plan_tail(ctx);
     } else if (k == "khosla_scaling") {
         ctx->opt_khosla_scaling = value ? 1 : 0;
+    } else if (k == "upload_ride") {
+        ctx->opt_upload_ride = value ? 1 : 0;
     } else if (k == "cluster_engine") {
         ctx->opt_cluster_engine = value ? 1 : 0;
     } else if (k == "cluster_handover") {

@@ -361,6 +361,78 @@ __global__ void __launch_bounds__(kWideThreads) widen_values_kernel(const T* __r
     }
 }
 
+// u16 uploads: ONE launch per run of staged pieces, right behind the run's copy on the same stream, so that nothing but
+// the last run's few microseconds is left to do when the last piece has landed: restores values [lo, hi) of the f64 array
+// from their u16 image, folds their range into the statistics csr_stats_kernel would compute (for non-negative integers
+// the order of the f64 keys is the order of the u16 images) and checks the column indices of the same arcs (the whole
+// column array crossed PCIe in front of the first piece).  `lo` is a multiple of the piece size (64 Ki values).
+__global__ void __launch_bounds__(kWideThreads) widen_u16_stats_kernel(const uint16_t* __restrict__ src, double* __restrict__ dst,
+                                                                       const uint32_t* __restrict__ cols, const size_t lo,
+                                                                       const size_t hi, const uint32_t n_cols, DevCsrStats* out) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    uint32_t mn = 0xFFFFu, mx = 0u;
+    unsigned long long bad_c = 0ull;
+    bool any = false;
+    const size_t octs = (hi - lo) / 8u;
+    for (size_t t = tid; t < octs; t += stride) {
+        const size_t g = lo + 8u * t;
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + g));
+        const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(cols + g)), c1 = __ldg(reinterpret_cast<const uint4*>(cols + g + 4));
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t a = ww[u] & 0xFFFFu, b = ww[u] >> 16;
+            mn = min(mn, min(a, b));
+            mx = max(mx, max(a, b));
+            *reinterpret_cast<double2*>(dst + g + 2 * u) = make_double2((double)a, (double)b);
+        }
+        bad_c += (c0.x >= n_cols ? 1u : 0u) + (c0.y >= n_cols ? 1u : 0u) + (c0.z >= n_cols ? 1u : 0u) + (c0.w >= n_cols ? 1u : 0u) +
+                 (c1.x >= n_cols ? 1u : 0u) + (c1.y >= n_cols ? 1u : 0u) + (c1.z >= n_cols ? 1u : 0u) + (c1.w >= n_cols ? 1u : 0u);
+        any = true;
+    }
+    for (size_t g = lo + octs * 8u + tid; g < hi; g += stride) {
+        const uint32_t a = src[g];
+        mn = min(mn, a);
+        mx = max(mx, a);
+        dst[g] = (double)a;
+        bad_c += (cols[g] >= n_cols) ? 1u : 0u;
+        any = true;
+    }
+    const uint32_t have = __ballot_sync(0xffffffffu, any);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) bad_c += __shfl_xor_sync(0xffffffffu, bad_c, m);
+    if ((threadIdx.x & 31) == 0 && have) {
+        atomicMin(&out->min_key, f64_order_key((double)mn));
+        atomicMax(&out->max_key, f64_order_key((double)mx));
+        if (bad_c) atomicAdd(&out->bad_cols, bad_c);
+    }
+}
+
+// The row half of csr_stats_kernel (extents monotone and within nnz, uniform degree), for the same upload path.
+__global__ void __launch_bounds__(kWideThreads) csr_row_stats_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t n_rows,
+                                                                     const unsigned long long nnz, DevCsrStats* out) {
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad_r = 0, irr = 0;
+    const uint32_t k0 = row_ptr[1] - row_ptr[0];
+    for (unsigned long long i = tid; i < n_rows; i += stride) {
+        const uint32_t a = row_ptr[i], b = row_ptr[i + 1];
+        bad_r += (b < a || (unsigned long long)b > nnz) ? 1u : 0u;
+        irr += (b - a != k0) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        bad_r += __shfl_xor_sync(0xffffffffu, bad_r, m);
+        irr += __shfl_xor_sync(0xffffffffu, irr, m);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad_r) atomicAdd(&out->bad_rows, bad_r);
+        if (irr) atomicAdd(&out->irregular_rows, irr);
+    }
+}
+
 // Empty kernel: the "profile" mode launches it in front of an event so that the event is recorded by the compute
 // front-end right before the kernel it times (and not behind the copy engine's upload of the control block).
 __global__ void profile_fence_kernel() {}
