@@ -67,6 +67,10 @@ typedef struct sla_stats {
     float ms_total;       /* ms_solve + result copies */
     uint64_t cluster_rounds; /* of tail_rounds: rounds run by the thread-block-cluster engine (queues of a few thousand bidders
                                 on instances whose prices do not fit one CTA's shared memory) */
+    uint32_t restarts;    /* Khosla on a square instance (option "khosla_scaling"): 1 when a phase of the eps-schedule dropped
+                             somebody and the solve started over with the plain fixed-eps rounds; batch
+                             totals: number of instances that did.  nreductions counts the phases of the schedule */
+    uint32_t reserved_;   /* keeps the size a multiple of 8 on every ABI; always 0 */
 } sla_stats;
 
 /* One record per bid-scan launch when option "profile" is 1 (host-driven loop, CUDA events around each kernel). */
@@ -109,7 +113,25 @@ void sla_host_negate_f64(double *values, size_t n, int threads);
  * solves with 641 .. tail_max persons run their first round on the grid-wide kernels), "narrow_upload" (1: see
  * sla_last_upload), "narrow_scan" (1: see sla_scan_value_bytes), "stream_scan" (1: first-round scan of a uniform-degree CSR through the TMA pipeline
  * bid_stream_kernel instead of the LDG.256 kernel; identical results), "l2_persist" (1: access-policy window that
- * keeps the bid words persisting in the L2), "profile_repeat" (development: launches of the scan per profile bracket). */
+ * keeps the bid words persisting in the L2), "profile_repeat" (development: launches of the scan per profile bracket),
+ * "prune_gather" (1: rounds with >= 32 Ki bidders gather only the prices that can still matter -- prices never fall, so
+ * profit <= value; identical choices), "learn_shape" (1: the first graph of a plain Khosla solve of a resident CSR is
+ * shaped by the previous solve's number of wide rounds), "upload_ride" (1: u16 uploads run their statistics and the
+ * widening behind every run of staged pieces on a second stream instead of two passes at the end), "cluster_engine"
+ * (0; 1: queues of 25 .. 8,192 bidders of large-M instances run in one thread-block cluster, mid_kernel; identical
+ * results, measured no faster) with "cluster_handover" (queue length at which it hands over to the single-CTA engine),
+ * "mesh_tail" (1: the mesh engine's persistent one-block tail), "prezero_best" (0; development), "profile_graph"
+ * (1: the profile bracket is one small graph launch).  Every option is a performance / engine-selection switch: none
+ * changes a result bit, with ONE documented exception in what is compared against:
+ *
+ * Guarantee for KhoslaSolver on SQUARE instances (num_rows == num_cols) with "khosla_scaling" = 1 (the default): the
+ * returned assignment and prices satisfy eps-complementary slackness at the caller's eps (the last phase runs at exactly
+ * that eps) and num_unassigned equals the reference's -- that, not equality of prices / nits / the assignment itself
+ * with the reference's single fixed-eps pass (ksparse.rs:153-251), is what is promised: optimal objective for integer
+ * weights with eps < 1/n, within n * eps otherwise.  stats.nreductions then counts the phases and stats.restarts says
+ * whether the schedule was abandoned for the plain rounds (a phase dropped somebody at the price threshold,
+ * ksparse.rs:218-220: such instances return exactly what "khosla_scaling" = 0 returns).  Rectangular instances never
+ * run a schedule. */
 int sla_set_option(sla_ctx *ctx, const char *key, int64_t value);
 
 /* ---- CSR mirror: the host keeps ownership of i_starts_stops / column_indices / values built by

@@ -32,6 +32,8 @@ pub struct sla_stats {
     pub ms_solve: f32,
     pub ms_total: f32,
     pub cluster_rounds: u64,
+    pub restarts: u32,
+    pub reserved_: u32,
 }
 
 /// `sla_round_profile` of include/sla.h.

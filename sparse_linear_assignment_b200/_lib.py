@@ -43,6 +43,7 @@ class SlaStats(C.Structure):
         ("bid_arcs", C.c_uint64), ("dropped", C.c_uint32), ("values_negated", C.c_uint32),
         ("wide_rounds", C.c_uint64), ("tail_rounds", C.c_uint64), ("kernel_launches", C.c_uint32),
         ("graph_launches", C.c_uint32), ("ms_solve", C.c_float), ("ms_total", C.c_float), ("cluster_rounds", C.c_uint64),
+        ("restarts", C.c_uint32), ("reserved_", C.c_uint32),
     ]
 
     def as_dict(self):

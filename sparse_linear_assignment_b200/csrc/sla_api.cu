@@ -1100,6 +1100,7 @@ int solve_common(sla_ctx* ctx, int algo, int maximize, double eps_in, double sta
         stats->wide_rounds = f.wide_rounds;
         stats->tail_rounds = f.tail_rounds;
         stats->cluster_rounds = f.cluster_rounds;
+        stats->restarts = (s.kscale && !f.kscale) ? 1u : 0u;   // the eps-schedule was abandoned (finish_if_possible)
         stats->kernel_launches = launches;
         stats->graph_launches = graph_launches;
         if (forward) {

@@ -25,6 +25,7 @@ struct DevInstStats {   // per-instance result scalars (expanded into sla_stats 
     double eps;
     unsigned long long rounds, bids, bid_arcs;
     uint32_t dropped, values_negated;
+    uint32_t restarts, pad_;   // restarts: 1 when the Khosla eps-schedule was abandoned for the plain rounds
 };
 
 struct BatchParams {
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(kBatchThreads, SLA_BATCH_MINBLOCKS) batch_kern
         // Khosla on a square instance: rounds under the eps-schedule c/2, x0.15, ..., caller's eps; a phase that drops
         // anybody makes the instance start over with the plain rounds (same rule as finish_if_possible)
         bool kscale = false;
+        uint32_t restarts = 0;
         if (algo == ALGO_KHOSLA && p.khosla_scaling && N == M) {
             const double c = fmax(fabs(w_min), fabs(w_max));
             if (c / 2.0 > eps) { kscale = true; eps = c / 2.0; }
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(kBatchThreads, SLA_BATCH_MINBLOCKS) batch_kern
                 __syncthreads();
                 if (any_dropped) {
                     kscale = false;
+                    restarts = 1;
                     eps = target;
                     my_dropped = 0;
                     for (uint32_t j = tid; j < M; j += kBatchThreads) s_prices[j] = 0.0;
@@ -407,6 +410,8 @@ __global__ void __launch_bounds__(kBatchThreads, SLA_BATCH_MINBLOCKS) batch_kern
             st.bid_arcs = s_arcs;
             st.dropped = s_dropped;
             st.values_negated = negate ? 1u : 0u;
+            st.restarts = restarts;
+            st.pad_ = 0u;
             if (algo == ALGO_KHOSLA) { st.nits = (uint32_t)bids; st.num_unassigned = s_dropped; }
             else { st.nits = nits; st.num_unassigned = qlen; }
             p.stats[inst] = st;
@@ -639,11 +644,11 @@ int sla_batch_solve(sla_ctx* ctx, int algo, int maximize, double eps, double sta
             memset(&o, 0, sizeof o);
             o.num_unassigned = d.num_unassigned; o.nits = d.nits; o.nreductions = d.nreductions;
             o.optimal_soln_found = d.optimal; o.eps = d.eps; o.rounds = d.rounds; o.bids = d.bids; o.bid_arcs = d.bid_arcs;
-            o.dropped = d.dropped; o.values_negated = d.values_negated; o.tail_rounds = d.rounds;
+            o.dropped = d.dropped; o.values_negated = d.values_negated; o.tail_rounds = d.rounds; o.restarts = d.restarts;
         }
         sum.num_unassigned += d.num_unassigned; sum.nits += d.nits; sum.nreductions += d.nreductions;
         sum.optimal_soln_found &= d.optimal; sum.rounds += d.rounds; sum.bids += d.bids; sum.bid_arcs += d.bid_arcs;
-        sum.dropped += d.dropped; sum.values_negated += d.values_negated; sum.tail_rounds += d.rounds;
+        sum.dropped += d.dropped; sum.values_negated += d.values_negated; sum.tail_rounds += d.rounds; sum.restarts += d.restarts;
     }
     sum.kernel_launches = 1;
     cudaEventElapsedTime(&sum.ms_solve, ctx->ev[0], ctx->ev[1]);

@@ -602,11 +602,11 @@ def test_khosla_eps_schedule_on_square_instances(sla, oracle):
     solver, z = gpu_solve(sla, "KhoslaSolver", n, n, rp, c, v)
     assert z.num_unassigned == o.num_unassigned == 0 and z.eps == o.eps
     assert abs(solver.get_objective(z) - o.get_objective()) <= n * z.eps    # n * eps_final (non-integer weights)
-    assert solver.last_stats["nreductions"] >= 5
+    assert solver.last_stats["nreductions"] >= 5 and solver.last_stats["restarts"] == 0
     assert_equals_model(oracle, "khosla", solver, z, n, n, rp, c, v)
     scaled_rounds = solver.last_stats["rounds"]
     plain, zp = gpu_solve(sla, "KhoslaSolver", n, n, rp, c, v, options=dict(khosla_scaling=0))
-    assert zp.num_unassigned == 0 and plain.last_stats["nreductions"] == 0
+    assert zp.num_unassigned == 0 and plain.last_stats["nreductions"] == 0 and plain.last_stats["restarts"] == 0
     assert abs(plain.get_objective(zp) - o.get_objective()) <= n * zp.eps
     assert_equals_model(oracle, "khosla", plain, zp, n, n, rp, c, v, khosla_scaling=False)
     assert scaled_rounds * 3 < plain.last_stats["rounds"]
@@ -630,6 +630,7 @@ def test_khosla_eps_schedule_on_square_instances(sla, oracle):
         r = assert_equals_model(oracle, "khosla", solver, z, nn, nn, rp, c, v)
         if o.num_unassigned:
             infeasible += 1
+            assert solver.last_stats["restarts"] == 1              # sla_stats reports the abandoned schedule
             plain = oracle.jacobi_model("khosla", nn, nn, rp, c, v, khosla_scaling=False)
             assert np.array_equal(r["p2o"], plain["p2o"]) and np.array_equal(r["prices"], plain["prices"])
     assert infeasible >= 2
@@ -754,6 +755,8 @@ def test_square_khosla_feasibility_boundary_equals_reference(sla, oracle):
         check_matching(n, n, rp, c, z.person_to_object, z.object_to_person, o.num_unassigned)
         if planted:
             assert z.num_unassigned == 0
+        if o.num_unassigned:
+            assert solver.last_stats["restarts"] == 1              # nobody ends unassigned under the schedule itself
         infeasible += int(o.num_unassigned > 0)
         feasible += int(o.num_unassigned == 0)
     assert infeasible >= 100 and feasible >= 50

@@ -46,6 +46,32 @@ def test_host_only_library_and_rust_binding_cover_the_header(sla):
         assert os.path.exists(os.path.join(ROOT, rel)), rel
 
 
+def test_stats_struct_layout_agrees_across_the_three_bindings(sla, tmp_path):
+    """sla_stats crosses the C ABI by layout: the ctypes mirror must have the compiler's size and field offsets for
+    include/sla.h, and rust/src/ffi.rs must list the same fields in the same order with the same widths."""
+    import subprocess
+    from sparse_linear_assignment_b200 import _lib
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "sla.h")).read(), flags=re.S)
+    body = re.search(r"typedef struct sla_stats \{(.*?)\} sla_stats;", header, flags=re.S).group(1)
+    c_fields = re.findall(r"\b(uint32_t|uint64_t|double|float)\s+([a-z_0-9]+)\s*;", body)
+    assert [n for _, n in c_fields] == [n for n, _ in _lib.SlaStats._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sla.h"\nint main(void) {\n'
+                   '  printf("%zu", sizeof(sla_stats));\n'
+                   + "".join(f'  printf(" %zu", offsetof(sla_stats, {n}));\n' for _, n in c_fields)
+                   + '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    nums = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert nums[0] == C.sizeof(_lib.SlaStats) and nums[0] % 8 == 0
+    assert nums[1:] == [getattr(_lib.SlaStats, n).offset for _, n in c_fields]
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    rs_body = re.search(r"pub struct sla_stats \{(.*?)\}", ffi, flags=re.S).group(1)
+    rs_fields = re.findall(r"pub ([a-z_0-9]+): (u32|u64|f64|f32)", rs_body)
+    width = {"uint32_t": "u32", "uint64_t": "u64", "double": "f64", "float": "f32"}
+    assert rs_fields == [(n, width[ty]) for ty, n in c_fields]
+
+
 def test_no_gpu_means_loud_failure(sla):
     """Without a device the product path must fail, never fall back to a CPU solve."""
     import torch
