@@ -29,6 +29,7 @@ typedef struct {
     double eps;
     uint64_t rounds, bids, bid_arcs;
     uint32_t dropped, values_negated;
+    uint32_t restarts, reserved_;   /* restarts: 1 when the Khosla eps-schedule was abandoned for the plain rounds */
 } jm_stats;
 
 /* 1: Khosla rounds on square instances run under an eps-schedule (set by the tests / the bindings) */
@@ -210,6 +211,7 @@ int jm_solve(int algo, uint32_t n_rows, uint32_t n_cols, const uint32_t *row_ptr
                 /* somebody hit the price threshold under the schedule: start over with the plain rounds, which alone
                  * define what the threshold does on an instance without a perfect matching */
                 scaled = 0;
+                st->restarts = 1;
                 eps = target;
                 st->dropped = 0;
                 for (uint32_t j = 0; j < n_cols; ++j) prices[j] = 0.0;

@@ -53,6 +53,7 @@ class JmStats(C.Structure):
         ("num_unassigned", C.c_uint32), ("nits", C.c_uint32), ("nreductions", C.c_uint32),
         ("optimal_soln_found", C.c_uint32), ("eps", C.c_double), ("rounds", C.c_uint64), ("bids", C.c_uint64),
         ("bid_arcs", C.c_uint64), ("dropped", C.c_uint32), ("values_negated", C.c_uint32),
+        ("restarts", C.c_uint32), ("reserved_", C.c_uint32),
     ]
 
 

@@ -17,7 +17,7 @@ def check_batch(sla, oracle, kind, instances, res, eps, **kw):
         assert np.array_equal(o2p, model["o2p"]), idx
         assert np.array_equal(prices, model["prices"]), idx
         for key in ("num_unassigned", "nits", "nreductions", "optimal_soln_found", "rounds", "bids", "bid_arcs", "dropped",
-                    "values_negated"):
+                    "values_negated", "restarts"):
             assert st[key] == model["stats"][key], (idx, key)
         assert st["eps"] == model["stats"]["eps"]
         # the Khosla eps-schedule only exists on square instances; abandoning it is reported, and whoever ends with

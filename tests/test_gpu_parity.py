@@ -35,7 +35,7 @@ def assert_equals_model(O, kind, solver, z, n, m, rp, c, v, maximize=False, eps=
     assert np.array_equal(z.object_to_person.astype(np.uint32), r["o2p"]), "object_to_person differs from the model"
     assert np.array_equal(solver.prices(), r["prices"]), "prices differ from the model (bit-exact f64)"
     for key in ("num_unassigned", "nits", "nreductions", "optimal_soln_found", "rounds", "bids", "bid_arcs", "dropped",
-                "values_negated"):
+                "values_negated", "restarts"):
         assert st[key] == r["stats"][key], f"{key}: gpu {st[key]} != model {r['stats'][key]}"
     assert st["eps"] == r["stats"]["eps"]
     return r
