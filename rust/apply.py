@@ -52,6 +52,9 @@ def main():
     crate = sys.argv[1]
     if 'version = "0.1.5"' not in open(os.path.join(crate, "Cargo.toml")).read():
         raise SystemExit("the ed scripts are line-addressed against v0.1.5")
+    if os.path.exists(os.path.join(crate, "src", "device.rs")) or "mod device;" in open(os.path.join(crate, "src", "lib.rs")).read():
+        raise SystemExit("this checkout is already patched (src/device.rs / `mod device;` present): the ed scripts are "
+                         "line-addressed against the pristine v0.1.5 sources and must not be applied twice")
     for rel in ("src/ksparse.rs", "src/symmetric.rs", "src/lib.rs", "Cargo.toml"):
         apply_ed(os.path.join(crate, rel), os.path.join(HERE, "patches", os.path.basename(rel) + ".ed"))
     for rel in ("src/ffi.rs", "src/device.rs", "build.rs"):

@@ -117,6 +117,8 @@ def test_rust_patches_apply_to_the_reference_and_are_consistent(sla, tmp_path):
             os.chmod(os.path.join(dirpath, f), 0o644)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "rust", "apply.py"), str(crate)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+    again = subprocess.run([sys.executable, os.path.join(ROOT, "rust", "apply.py"), str(crate)], capture_output=True, text=True)
+    assert again.returncode != 0 and "already patched" in again.stderr      # line-addressed patches: never twice
     srcs = {rel: open(crate / rel).read() for rel in ("src/ksparse.rs", "src/symmetric.rs", "src/lib.rs", "src/device.rs",
                                                        "src/ffi.rs", "build.rs", "Cargo.toml")}
     for rel, text in srcs.items():
