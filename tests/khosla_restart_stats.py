@@ -2,7 +2,8 @@
 Runs oracle/jacobi_model.c -- the bit-exact CPU model of the device rounds (tests assert device == model, restarts
 included) -- over the instance families of the tests and of the reference's symmetric bench, and prints one JSON line per
 family: instances, feasible ones, restarts among the feasible, rounds with and without the schedule.
-    python scripts/khosla_restart_stats.py > profiles/r02_khosla_restart_stats.jsonl"""
+    python tests/khosla_restart_stats.py > profiles/r02_khosla_restart_stats.jsonl
+(lives under tests/ because it runs the oracle package, which is test infrastructure)"""
 import json
 import os
 import sys
@@ -43,9 +44,11 @@ def family(name, gen, count):
             assert p["stats"]["num_unassigned"] == 0
             rounds_s += s["stats"]["rounds"]
             rounds_p += p["stats"]["rounds"]
-    print(json.dumps(dict(family=name, instances=inst, feasible=feas, restarts_among_feasible=restarts_feasible,
-                          restarts_among_all=restarts_all, rounds_feasible_with_schedule=int(rounds_s),
-                          rounds_feasible_plain=int(rounds_p))), flush=True)
+    rec = dict(family=name, instances=inst, feasible=feas, restarts_among_feasible=restarts_feasible,
+               restarts_among_all=restarts_all, rounds_feasible_with_schedule=int(rounds_s),
+               rounds_feasible_plain=int(rounds_p))
+    print(json.dumps(rec), flush=True)
+    return rec
 
 
 def main():

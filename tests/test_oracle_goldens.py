@@ -217,3 +217,34 @@ def test_model_khosla_eps_schedule_keeps_parity_with_the_oracle():
             plain = O.jacobi_model("khosla", n, n, rp, c, v, khosla_scaling=False)
             assert np.array_equal(scaled["p2o"], plain["p2o"]) and np.array_equal(scaled["prices"], plain["prices"])
     assert fallbacks >= 2
+
+
+def test_model_reports_restarts_only_without_a_perfect_matching(oracle):
+    """`restarts` of the CPU model (the counter sla_stats.restarts is compared with on the GPU): a Khosla solve on a
+    square instance abandons its eps-schedule exactly when somebody is dropped at the price threshold.  On the tests'
+    instance families no feasible instance does, every infeasible one does (the full statistics:
+    tests/khosla_restart_stats.py -> profiles/r02_khosla_restart_stats.jsonl), and a rectangular or unscheduled solve
+    never reports one."""
+    import khosla_restart_stats as K
+
+    def planted(seed):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(100, 400))
+        return (n,) + K.symmetric_instance(n, float(rng.uniform(2.0, 4.0)), 800 + seed, True, 0.0, 10.0)
+
+    def unplanted(seed):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(10, 120))
+        return (n,) + K.symmetric_instance(n, float(rng.uniform(2.0, 4.0)), 900 + seed, False, 0.0, 10.0)
+
+    a = K.family("planted", planted, 12)
+    assert a["feasible"] == a["instances"] and a["restarts_among_all"] == 0
+    assert a["rounds_feasible_with_schedule"] * 2 < a["rounds_feasible_plain"]
+    b = K.family("unplanted", unplanted, 40)
+    assert b["feasible"] < b["instances"]
+    assert b["restarts_among_feasible"] == 0 and b["restarts_among_all"] == b["instances"] - b["feasible"]
+    n, rp, c, v = unplanted(3)
+    assert oracle.jacobi_model("khosla", n, n, rp, c, v, khosla_scaling=False)["stats"]["restarts"] == 0
+    from helpers import random_sparse_instance
+    rp, c, v = random_sparse_instance(np.random.default_rng(5), 50, 80, 6, integer=True, lo=0, hi=100)
+    assert oracle.jacobi_model("khosla", 50, 80, rp, c, v)["stats"]["restarts"] == 0
